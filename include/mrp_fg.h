@@ -1,0 +1,218 @@
+/*
+ * mrp_fg.h — C ABI of the B200 feature-generation engine.
+ *
+ * This is the drop-in boundary for ONE stage of JackDamato/micro-regime-propogation:
+ * the per-snapshot feature engine (`microregime::FeatureProcessor` + `FeatureNormalizer`).
+ * Nothing like this ABI exists in the reference (it is a single C++ process); each entry
+ * point below names the reference interface it stands in for, as
+ *   ref: <file>:<line>   (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain C, no exceptions across the boundary: every call returns an int status
+ *     (MRP_FG_OK == 0) and `mrp_fg_last_error()` gives a thread-local message
+ *     (ref: the reference signals errors with C++ exceptions that `main` maps to exit
+ *      code 1, feature_generation/src/data/features_to_csv.cpp:141-147);
+ *   - one context per (host thread, GPU); contexts share no state
+ *     (ref: one FeatureProcessor per instrument, feature_generation/include/dual_feature_pipeline.hpp:46-47);
+ *   - all kernels are enqueued on the caller's CUDA stream (passed as void*, a cudaStream_t);
+ *   - there is NO CPU fallback: if the CUDA device or the kernels are unavailable the
+ *     call fails with MRP_FG_ERR_CUDA.
+ *
+ * Data model (structure of arrays; "stream" = one instrument-day = one FeatureProcessor instance)
+ *   A batch holds S independent streams stored back to back on three axes:
+ *     snapshot axis  N rows    one row per FeatureInputSnapshot
+ *                              (ref: data_ingestion/include/feature_snapshot.hpp:12-44)
+ *     tick axis      K ticks   the 50 ms (midprice, spread) samples pushed by
+ *                              FeatureEngine::UpdateMidpriceAndSpread
+ *                              (ref: data_ingestion/src/core/feature_engine.cpp:130-150)
+ *     trade axis     T trades  the trade directions pushed by FeatureEngine::update_trade
+ *                              (ref: data_ingestion/src/core/feature_engine.cpp:87-93)
+ *   Row t of a stream carries two cursors: tick_cursor[t] / trade_cursor[t] = how many ticks /
+ *   trades of THIS stream had been pushed when the snapshot was taken.  The reference's
+ *   rolling deques are then exactly
+ *     rolling_midprices / rolling_spreads = ticks [max(0,k-mid_window), k)        (cap 1800)
+ *     rolling_tick_directions             = tick dirs [max(0,k-dir_window), k)    (cap 1500)
+ *     rolling_trade_directions            = trades [max(0,j-dir_window), j)       (cap 1500)
+ *   Per-level book arrays are level-major: element (level i, row r) at [i * n_rows + r].
+ *   The per-level depth-change directions (ref: data_ingestion/src/core/order_book.cpp:208-239,
+ *   both branches reduce to sign(new_size - old_size)) are derived on the device from the
+ *   sizes of rows t and t-1 (row 0 compares with an all-zero book, order_book.cpp:115,168).
+ */
+#ifndef MRP_FG_H
+#define MRP_FG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRP_FG_ABI_VERSION 1
+
+/* status codes */
+#define MRP_FG_OK 0
+#define MRP_FG_ERR_INVALID 1 /* bad argument / inconsistent view            */
+#define MRP_FG_ERR_CUDA 2    /* CUDA runtime or kernel failure, or no GPU   */
+#define MRP_FG_ERR_STATE 3   /* call order (run before bind, ...)           */
+#define MRP_FG_ERR_NOMEM 4
+
+/* Output column order == FeatureSet declaration order == CSV column order
+ * (ref: feature_generation/include/feature_set.hpp:15-43,
+ *       feature_generation/src/data/features_to_csv.cpp:62-80). */
+enum mrp_fg_feature {
+    MRP_F_MIDPRICE = 0,
+    MRP_F_LOG_SPREAD,
+    MRP_F_LOG_RETURN,
+    MRP_F_EWM_VOLATILITY,
+    MRP_F_REALIZED_VARIANCE,
+    MRP_F_DIRECTIONAL_VOLATILITY,
+    MRP_F_SPREAD_VOLATILITY,
+    MRP_F_OFI,
+    MRP_F_SIGNED_VOLUME_PRESSURE,
+    MRP_F_ORDER_ARRIVAL_RATE,
+    MRP_F_DEPTH_IMBALANCE,
+    MRP_F_MARKET_DEPTH,
+    MRP_F_LOB_SLOPE,
+    MRP_F_PRICE_GAP,
+    MRP_F_TICK_DIRECTION_ENTROPY,
+    MRP_F_REVERSAL_RATE,
+    MRP_F_AGGRESSOR_BIAS,
+    MRP_F_SHANNON_ENTROPY,
+    MRP_F_LIQUIDITY_STRESS,
+    MRP_FG_NUM_FEATURES /* 19 */
+};
+
+/* Optional integer window-count columns (bit-exact against the oracle). */
+enum mrp_fg_count {
+    MRP_C_RET_VALID = 0, /* valid return pairs in the mid window   (feature_processor.cpp:55-60)  */
+    MRP_C_RET_UP,        /* of those, ret > 0                       (feature_processor.cpp:87-89)  */
+    MRP_C_TICK_UP,       /* tick dirs > 0 in the dir window         (feature_processor.cpp:217-221)*/
+    MRP_C_TICK_DOWN,
+    MRP_C_TICK_TOTAL,
+    MRP_C_TRADE_POS,     /* trade dirs > 0                          (feature_processor.cpp:255-259)*/
+    MRP_C_TRADE_NEG,
+    MRP_C_TRADE_REVERSALS, /*                                       (feature_processor.cpp:233-238)*/
+    MRP_C_TRADE_TOTAL,
+    MRP_C_TRADE_DIR_SUM,   /*                                       (feature_processor.cpp:242-245)*/
+    MRP_C_NORM_N,          /* normaliser window size n              (feature_normalizer.cpp:71)    */
+    MRP_FG_NUM_COUNTS /* 11 */
+};
+
+/* Every compile-time constant of the reference path, as a run-time field.
+ * Defaults (mrp_fg_default_params) are the reference values. */
+typedef struct mrp_fg_params {
+    int32_t depth_levels;    /* DEPTH_LEVELS = 10       ref: data_ingestion/include/common_constants.hpp:8  */
+    int32_t mid_window;      /* 1800 mids/spreads kept  ref: data_ingestion/src/core/feature_engine.cpp:146 */
+    int32_t dir_window;      /* ROLLING_WINDOW = 1500   ref: common_constants.hpp:9, feature_engine.cpp:90,143 */
+    int32_t spread_divisor;  /* ROLLING_WINDOW = 1500   ref: feature_processor.cpp:101,106 (not the deque length) */
+    int32_t ewm_span;        /* ROLLING_WINDOW: alpha = 2/(span+1)   ref: feature_processor.cpp:64 */
+    int32_t norm_window;     /* WINDOW_SIZE = 30000     ref: common_constants.hpp:10, feature_normalizer.cpp:48 */
+    int32_t return_lag;      /* 10e9 / SNAPSHOT_INTERVAL_NS = 20 -> reads the row 21 back
+                                ref: feature_processor.cpp:37, feature_normalizer.hpp:19-24 */
+    int32_t stress_levels;   /* LEVELS_TO_USE = 5       ref: feature_processor.cpp:274 */
+    double ofi_depth_decay;  /* 0.5                     ref: feature_processor.cpp:114 */
+    double ofi_alpha;        /* 0.2                     ref: feature_processor.cpp:115 */
+    double ofi_min_total_vol;/* 1e-6                    ref: feature_processor.cpp:116 */
+    double stress_min_size;  /* 5.0                     ref: feature_processor.cpp:275 */
+    double stress_distance_decay; /* 10.0               ref: feature_processor.cpp:276 */
+    double stress_alpha;     /* 0.1                     ref: feature_processor.cpp:277 */
+    int32_t norm_mode;       /* MRP_NORM_COMPENSATED (default) or MRP_NORM_FAITHFUL */
+    int32_t emit_dirs;       /* also write the int8 per-level depth-change directions */
+    int32_t emit_counts;     /* also write the int32 window-count columns             */
+    int32_t reserved;
+} mrp_fg_params;
+
+/* norm_mode */
+#define MRP_NORM_COMPENSATED 0 /* exact windowed sums (block partials + in-tile scans); more accurate than the reference */
+#define MRP_NORM_FAITHFUL 1    /* re-enacts the reference's add-then-evict running sums in its own
+                                  rounding order (feature_normalizer.cpp:37-51): serial per column, slow, for validation */
+
+/* A batch of S streams, structure of arrays.  `memory` says where the pointers live. */
+#define MRP_MEM_DEVICE 0
+#define MRP_MEM_HOST 1
+
+typedef struct mrp_fg_soa_view {
+    int32_t n_streams;           /* S >= 1 */
+    int32_t memory;              /* MRP_MEM_DEVICE or MRP_MEM_HOST for the array pointers below */
+    /* offsets are ALWAYS host arrays of S+1 entries; stream s owns [off[s], off[s+1]) */
+    const int64_t* row_offsets;
+    const int64_t* tick_offsets;
+    const int64_t* trade_offsets;
+    /* snapshot axis, n_rows = row_offsets[S] */
+    const uint64_t* ts_ns;        /* [n_rows]     FeatureInputSnapshot::timestamp_ns              */
+    const double* bid_px;         /* [L][n_rows]  bid_prices  (level 0 == best_bid_price)         */
+    const double* ask_px;         /* [L][n_rows]  ask_prices  (level 0 == best_ask_price)         */
+    const int32_t* bid_sz;        /* [L][n_rows]  bid_sizes                                       */
+    const int32_t* ask_sz;        /* [L][n_rows]  ask_sizes                                       */
+    const double* buy_vol;        /* [n_rows]     rolling_buy_volume                              */
+    const double* sell_vol;       /* [n_rows]     rolling_sell_volume                             */
+    const int32_t* adds;          /* [n_rows]     adds_since_last_snapshot                        */
+    const uint32_t* tick_cursor;  /* [n_rows]     ticks of this stream pushed before the snapshot */
+    const uint32_t* trade_cursor; /* [n_rows]     trades of this stream pushed before the snapshot*/
+    /* tick axis, n_ticks = tick_offsets[S] */
+    const double* mid;            /* [n_ticks]    OrderBookManager::GetMidPrice() samples */
+    const double* spread;         /* [n_ticks]    OrderBookManager::GetSpread() samples   */
+    /* trade axis, n_trades = trade_offsets[S] */
+    const int8_t* trade_dir;      /* [n_trades]   +1 / -1 (order_engine.cpp:106)          */
+} mrp_fg_soa_view;
+
+typedef struct mrp_fg_ctx mrp_fg_ctx;
+
+/* Fill `p` with the reference constants (common_constants.hpp:8-11, feature_processor.cpp:64,114-116,274-277). */
+int mrp_fg_default_params(mrp_fg_params* p);
+
+/* Replaces: constructing a FeatureProcessor (feature_processor.hpp:11-12).  `device` = CUDA ordinal. */
+int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out);
+int mrp_fg_destroy(mrp_fg_ctx* ctx);
+
+/* Bind caller-owned DEVICE arrays (view->memory must be MRP_MEM_DEVICE); nothing is copied except
+ * the three small offset arrays.  Replaces: handing FeatureInputSnapshot rows to
+ * FeatureProcessor::GetRawFeatureSet (feature_processor.cpp:11), for all rows at once. */
+int mrp_fg_bind_inputs(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view);
+
+/* Copy a HOST view (view->memory == MRP_MEM_HOST; pinned memory recommended) into context-owned
+ * device buffers, asynchronously on `stream`, and bind them.  Buffers are reused across calls
+ * when the shape allows. */
+int mrp_fg_upload(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, void* stream);
+
+/* Enqueue the whole feature pass (raw features, then rolling z-scores) for every bound stream.
+ * Replaces, for every row: FeatureProcessor::GetRawFeatureSet + GetProcessedFeatureSet
+ * (feature_processor.cpp:11-29, feature_normalizer.cpp:32-83).  Asynchronous. */
+int mrp_fg_run(mrp_fg_ctx* ctx, void* stream);
+
+/* Device pointers to the context-owned outputs (valid until the next bind/upload/destroy).
+ *   raw, norm : double [19][n_rows]     column c, row r at [c * n_rows + r]
+ *   bid_dir, ask_dir : int8 [L][n_rows] (NULL unless params.emit_dirs)
+ *   counts : int32 [MRP_FG_NUM_COUNTS][n_rows] (NULL unless params.emit_counts)
+ * Any out pointer may be NULL. */
+int mrp_fg_outputs(mrp_fg_ctx* ctx, const double** raw, const double** norm,
+                   const int8_t** bid_dir, const int8_t** ask_dir, const int32_t** counts);
+
+/* Copy outputs to HOST buffers (same layouts), asynchronously on `stream`; NULL = skip. */
+int mrp_fg_download(mrp_fg_ctx* ctx, double* raw, double* norm, int8_t* bid_dir, int8_t* ask_dir,
+                    int32_t* counts, void* stream);
+
+/* Per-column moments of the RAW features over all bound rows: out[c*3 + {0,1,2}] = {n, sum x, sum x^2}
+ * (double [19*3], host).  These are what a caller allreduces across GPUs to get global
+ * (StandardScaler-style) statistics (ref: regime_classifier/python/data_checks.py:79-80).
+ * Synchronises `stream`. */
+int mrp_fg_moments(mrp_fg_ctx* ctx, double* out, void* stream);
+
+/* Block until everything enqueued on `stream` by this context has finished; surfaces kernel faults. */
+int mrp_fg_sync(mrp_fg_ctx* ctx, void* stream);
+
+/* Introspection for benchmarks. */
+int mrp_fg_num_kernels(void);                        /* kernels launched by one mrp_fg_run            */
+const char* mrp_fg_kernel_name(int i);
+/* With timing enabled, mrp_fg_run brackets every kernel with CUDA events on the launching stream. */
+int mrp_fg_enable_timing(mrp_fg_ctx* ctx, int on);
+int mrp_fg_kernel_times_ms(mrp_fg_ctx* ctx, float* ms /* [mrp_fg_num_kernels()] */);
+int64_t mrp_fg_launch_count(const mrp_fg_ctx* ctx); /* kernels launched so far by this context */
+
+const char* mrp_fg_last_error(void);
+int mrp_fg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRP_FG_H */

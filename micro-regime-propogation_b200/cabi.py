@@ -1,0 +1,242 @@
+"""ctypes view of include/mrp_fg.h — a thin Python host layer over the C ABI.
+
+The product's host side is C++20 (host/), because the reference is C++; this module exists so
+that the parity tests, the benchmark driver and the validation harness can call the SAME C-ABI
+shared library (`csrc/libmrp_fg.so`) from Python.  It contains no feature arithmetic and no
+fallback: if the library is missing, `load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libmrp_fg.so")
+
+NUM_FEATURES = 19
+FEATURES = (
+    "midprice", "log_spread", "log_return", "ewm_volatility", "realized_variance",
+    "directional_volatility", "spread_volatility", "ofi", "signed_volume_pressure",
+    "order_arrival_rate", "depth_imbalance", "market_depth", "lob_slope", "price_gap",
+    "tick_direction_entropy", "reversal_rate", "aggressor_bias", "shannon_entropy", "liquidity_stress",
+)
+COUNTS = (
+    "ret_valid", "ret_up", "tick_up", "tick_down", "tick_total", "trade_pos", "trade_neg",
+    "trade_reversals", "trade_total", "trade_dir_sum", "norm_n",
+)
+NUM_COUNTS = len(COUNTS)
+MEM_DEVICE, MEM_HOST = 0, 1
+NORM_COMPENSATED, NORM_FAITHFUL = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("depth_levels", C.c_int32), ("mid_window", C.c_int32), ("dir_window", C.c_int32),
+        ("spread_divisor", C.c_int32), ("ewm_span", C.c_int32), ("norm_window", C.c_int32),
+        ("return_lag", C.c_int32), ("stress_levels", C.c_int32),
+        ("ofi_depth_decay", C.c_double), ("ofi_alpha", C.c_double), ("ofi_min_total_vol", C.c_double),
+        ("stress_min_size", C.c_double), ("stress_distance_decay", C.c_double), ("stress_alpha", C.c_double),
+        ("norm_mode", C.c_int32), ("emit_dirs", C.c_int32), ("emit_counts", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SoaView(C.Structure):
+    _fields_ = [
+        ("n_streams", C.c_int32), ("memory", C.c_int32),
+        ("row_offsets", C.c_void_p), ("tick_offsets", C.c_void_p), ("trade_offsets", C.c_void_p),
+        ("ts_ns", C.c_void_p), ("bid_px", C.c_void_p), ("ask_px", C.c_void_p),
+        ("bid_sz", C.c_void_p), ("ask_sz", C.c_void_p), ("buy_vol", C.c_void_p), ("sell_vol", C.c_void_p),
+        ("adds", C.c_void_p), ("tick_cursor", C.c_void_p), ("trade_cursor", C.c_void_p),
+        ("mid", C.c_void_p), ("spread", C.c_void_p), ("trade_dir", C.c_void_p),
+    ]
+
+
+_ARRAY_FIELDS = ("ts_ns", "bid_px", "ask_px", "bid_sz", "ask_sz", "buy_vol", "sell_vol", "adds",
+                 "tick_cursor", "trade_cursor", "mid", "spread", "trade_dir")
+_HOST_DTYPES = {
+    "ts_ns": np.uint64, "bid_px": np.float64, "ask_px": np.float64, "bid_sz": np.int32, "ask_sz": np.int32,
+    "buy_vol": np.float64, "sell_vol": np.float64, "adds": np.int32, "tick_cursor": np.uint32,
+    "trade_cursor": np.uint32, "mid": np.float64, "spread": np.float64, "trade_dir": np.int8,
+}
+
+
+def default_params(**over) -> Params:
+    """Reference constants (common_constants.hpp:8-11, feature_processor.cpp:64,114-116,274-277)."""
+    p = Params(10, 1800, 1500, 1500, 1500, 30000, 20, 5, 0.5, 0.2, 1e-6, 5.0, 10.0, 0.1, 0, 0, 0, 0)
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+class HostView:
+    """Keeps numpy arrays alive and exposes them as a mrp_fg_soa_view (memory = HOST)."""
+
+    def __init__(self, batch: Dict[str, object]):
+        self.arrays = {}
+        for k in _ARRAY_FIELDS:
+            a = np.ascontiguousarray(np.asarray(batch[k]), dtype=_HOST_DTYPES[k])
+            self.arrays[k] = a
+        for k in ("row_offsets", "tick_offsets", "trade_offsets"):
+            self.arrays[k] = np.ascontiguousarray(np.asarray(batch[k], dtype=np.int64))
+        self.n_streams = len(self.arrays["row_offsets"]) - 1
+        self.n_rows = int(self.arrays["row_offsets"][-1])
+        self.n_ticks = int(self.arrays["tick_offsets"][-1])
+        self.n_trades = int(self.arrays["trade_offsets"][-1])
+        self.levels = self.arrays["bid_px"].size // max(self.n_rows, 1)
+        v = SoaView()
+        v.n_streams, v.memory = self.n_streams, MEM_HOST
+        for k, a in self.arrays.items():
+            setattr(v, k, a.ctypes.data)
+        self.view = v
+
+
+def device_view(batch: Dict[str, object]) -> "tuple[SoaView, list]":
+    """mrp_fg_soa_view over CUDA torch tensors (memory = DEVICE).  Returns (view, keepalive)."""
+    keep = []
+    v = SoaView()
+    v.memory = MEM_DEVICE
+    for k in ("row_offsets", "tick_offsets", "trade_offsets"):
+        a = np.ascontiguousarray(np.asarray(batch[k], dtype=np.int64))
+        keep.append(a)
+        setattr(v, k, a.ctypes.data)
+    v.n_streams = len(keep[0]) - 1
+    for k in _ARRAY_FIELDS:
+        t = batch[k]
+        assert t.is_cuda and t.is_contiguous(), k
+        keep.append(t)
+        setattr(v, k, t.data_ptr())
+    return v, keep
+
+
+_lib = None
+
+
+def load(path: Optional[str] = None) -> C.CDLL:
+    """Load libmrp_fg.so.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "This package has no CPU fallback.")
+    lib = C.CDLL(p)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    PP = C.POINTER(Params)
+    PV = C.POINTER(SoaView)
+    lib.mrp_fg_default_params.argtypes = [PP]
+    lib.mrp_fg_create.argtypes = [PP, i32, C.POINTER(vp)]
+    lib.mrp_fg_destroy.argtypes = [vp]
+    lib.mrp_fg_bind_inputs.argtypes = [vp, PV]
+    lib.mrp_fg_upload.argtypes = [vp, PV, vp]
+    lib.mrp_fg_run.argtypes = [vp, vp]
+    lib.mrp_fg_outputs.argtypes = [vp] + [C.POINTER(vp)] * 5
+    lib.mrp_fg_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mrp_fg_moments.argtypes = [vp, vp, vp]
+    lib.mrp_fg_sync.argtypes = [vp, vp]
+    lib.mrp_fg_num_kernels.argtypes = []
+    lib.mrp_fg_kernel_name.argtypes = [i32]
+    lib.mrp_fg_kernel_name.restype = C.c_char_p
+    lib.mrp_fg_enable_timing.argtypes = [vp, i32]
+    lib.mrp_fg_kernel_times_ms.argtypes = [vp, vp]
+    lib.mrp_fg_launch_count.argtypes = [vp]
+    lib.mrp_fg_launch_count.restype = i64
+    lib.mrp_fg_last_error.argtypes = []
+    lib.mrp_fg_last_error.restype = C.c_char_p
+    lib.mrp_fg_abi_version.argtypes = []
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class MrpError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One mrp_fg_ctx.  Mirrors the C ABI one to one."""
+
+    def __init__(self, params: Optional[Params] = None, device: int = 0):
+        self.lib = load()
+        self.params = params or default_params()
+        self.ctx = C.c_void_p()
+        self._keep = None
+        self.n_rows = 0
+        self._check(self.lib.mrp_fg_create(C.byref(self.params), device, C.byref(self.ctx)))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise MrpError(f"mrp_fg error {rc}: {self.lib.mrp_fg_last_error().decode()}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.mrp_fg_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs
+    def bind_device(self, batch: Dict[str, object]):
+        view, keep = device_view(batch)
+        self._keep = keep
+        self.n_rows = int(np.asarray(batch["row_offsets"])[-1])
+        self._check(self.lib.mrp_fg_bind_inputs(self.ctx, C.byref(view)))
+
+    def upload(self, hv: HostView, stream: int = 0):
+        self._keep = hv
+        self.n_rows = hv.n_rows
+        self._check(self.lib.mrp_fg_upload(self.ctx, C.byref(hv.view), C.c_void_p(stream)))
+
+    # -- compute
+    def run(self, stream: int = 0):
+        self._check(self.lib.mrp_fg_run(self.ctx, C.c_void_p(stream)))
+
+    def sync(self, stream: int = 0):
+        self._check(self.lib.mrp_fg_sync(self.ctx, C.c_void_p(stream)))
+
+    # -- outputs
+    def output_ptrs(self):
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self._check(self.lib.mrp_fg_outputs(self.ctx, *[C.byref(p) for p in ptrs]))
+        return [p.value for p in ptrs]
+
+    def download(self, stream: int = 0, raw=True, norm=True):
+        """Returns dict of numpy arrays: raw/norm [19, n], bid_dir/ask_dir [L, n], counts [NUM_COUNTS, n]."""
+        n, L = self.n_rows, self.params.depth_levels
+        out = {}
+        out["raw"] = np.empty((NUM_FEATURES, n), np.float64) if raw else None
+        out["norm"] = np.empty((NUM_FEATURES, n), np.float64) if norm else None
+        out["bid_dir"] = np.empty((L, n), np.int8) if self.params.emit_dirs else None
+        out["ask_dir"] = np.empty((L, n), np.int8) if self.params.emit_dirs else None
+        out["counts"] = np.empty((NUM_COUNTS, n), np.int32) if self.params.emit_counts else None
+        p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
+        self._check(self.lib.mrp_fg_download(self.ctx, p(out["raw"]), p(out["norm"]), p(out["bid_dir"]),
+                                             p(out["ask_dir"]), p(out["counts"]), C.c_void_p(stream)))
+        self.sync(stream)
+        return out
+
+    def moments(self, stream: int = 0) -> np.ndarray:
+        m = np.empty((NUM_FEATURES, 3), np.float64)
+        self._check(self.lib.mrp_fg_moments(self.ctx, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
+        return m
+
+    # -- introspection
+    def enable_timing(self, on: bool = True):
+        self._check(self.lib.mrp_fg_enable_timing(self.ctx, int(on)))
+
+    def kernel_times_ms(self) -> Dict[str, float]:
+        k = self.lib.mrp_fg_num_kernels()
+        buf = (C.c_float * k)()
+        self._check(self.lib.mrp_fg_kernel_times_ms(self.ctx, C.cast(buf, C.c_void_p)))
+        return {self.lib.mrp_fg_kernel_name(i).decode(): float(buf[i]) for i in range(k)}
+
+    def launch_count(self) -> int:
+        return int(self.lib.mrp_fg_launch_count(self.ctx))

@@ -1,0 +1,98 @@
+"""ctypes bindings of the CHECKERS: oracle/libmrp_oracle.so (plain-C restatement) and, when
+present, oracle/_ref/libmrp_ref*.so (the unmodified reference compiled from /root/reference).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs, never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+from mrp_b200.cabi import NUM_COUNTS, NUM_FEATURES, HostView, Params, SoaView, default_params
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libmrp_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libmrp_ref.so")
+REF_L50_SO = os.path.join(HERE, "_ref", "libmrp_ref_L50.so")
+
+
+def build(quiet: bool = True) -> None:
+    """(Re)build the checkers with oracle/Makefile (reference part only if /root/reference exists)."""
+    subprocess.run(["make", "-C", HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+_oracle = None
+_refs: Dict[str, C.CDLL] = {}
+
+
+def oracle_lib() -> C.CDLL:
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        lib = C.CDLL(ORACLE_SO)
+        lib.mrp_oracle_run.argtypes = [C.POINTER(Params), C.POINTER(SoaView)] + [C.c_void_p] * 5 + [C.c_int]
+        _oracle = lib
+    return _oracle
+
+
+def ref_available(levels: int = 10) -> bool:
+    return os.path.exists(REF_SO if levels == 10 else REF_L50_SO) and levels in (10, 50)
+
+
+def ref_lib(levels: int = 10) -> C.CDLL:
+    path = REF_SO if levels == 10 else REF_L50_SO
+    if path not in _refs:
+        lib = C.CDLL(path)
+        lib.mrp_ref_run.argtypes = [C.POINTER(SoaView), C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
+        assert lib.mrp_ref_depth_levels() == levels
+        _refs[path] = lib
+    return _refs[path]
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p()
+
+
+def run_oracle(hv: HostView, params: Optional[Params] = None, nthreads: int = 0,
+               want_dirs: bool = True, want_counts: bool = True) -> Dict[str, np.ndarray]:
+    """The C restatement on a host batch."""
+    p = params or default_params()
+    n, L = hv.n_rows, p.depth_levels
+    out = {
+        "raw": np.empty((NUM_FEATURES, n), np.float64), "norm": np.empty((NUM_FEATURES, n), np.float64),
+        "bid_dir": np.empty((L, n), np.int8) if want_dirs else None,
+        "ask_dir": np.empty((L, n), np.int8) if want_dirs else None,
+        "counts": np.zeros((NUM_COUNTS, n), np.int32) if want_counts else None,
+    }
+    rc = oracle_lib().mrp_oracle_run(C.byref(p), C.byref(hv.view), _ptr(out["raw"]), _ptr(out["norm"]),
+                                     _ptr(out["bid_dir"]), _ptr(out["ask_dir"]), _ptr(out["counts"]),
+                                     nthreads or (os.cpu_count() or 1))
+    if rc != 0:
+        raise RuntimeError(f"mrp_oracle_run failed ({rc})")
+    return out
+
+
+def run_reference(hv: HostView, trade_size: Optional[np.ndarray] = None, use_book: bool = False,
+                  nthreads: int = 1) -> Dict[str, np.ndarray]:
+    """The compiled, unmodified reference (L = 10 or 50 as hv.levels says)."""
+    n, L = hv.n_rows, hv.levels
+    lib = ref_lib(L)
+    ts = np.ascontiguousarray(trade_size, dtype=np.float64) if trade_size is not None else None
+    out = {
+        "raw": np.empty((NUM_FEATURES, n), np.float64), "norm": np.empty((NUM_FEATURES, n), np.float64),
+        "bid_dir": np.empty((L, n), np.int8), "ask_dir": np.empty((L, n), np.int8),
+        "snap_buy": np.empty(n, np.float64), "snap_sell": np.empty(n, np.float64),
+    }
+    rc = lib.mrp_ref_run(C.byref(hv.view), _ptr(ts), int(use_book), _ptr(out["raw"]), _ptr(out["norm"]),
+                         _ptr(out["bid_dir"]), _ptr(out["ask_dir"]), _ptr(out["snap_buy"]), _ptr(out["snap_sell"]),
+                         nthreads)
+    if rc != 0:
+        raise RuntimeError(f"mrp_ref_run failed ({rc})")
+    return out
