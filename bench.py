@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — feature rows/s of the feature_generation hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+
+One "step" = one pass of the whole hot path (19 raw features + 19 rolling z-scores for every snapshot row)
+over one synthetic instrument-day resident in HBM.  Workload at N = 1: BASELINE.json configs[1], a single
+instrument-day of 50 M snapshots x 10 levels (m = 10 ticks and ~2 trades per snapshot).  For N > 1 every
+rank owns one such instrument-day (the reference shards by instrument-day, scripts/multidate_feature_to_csv.sh:24):
+weak scaling, no data-path collective; the only collective is the NCCL all-reduce of the 19x3 global column
+moments after the pass (and the timing barrier).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over ranks);
+`e2e` goes through the C ABI with pinned HOST buffers (H2D + pass + D2H inside the timed region).
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified reference
+compiled from /root/reference; falls back to the oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "feature_rows_per_sec"
+UNIT = "rows/s"
+LEVELS = 10
+TICKS_PER_ROW = 10
+FULL_ROWS = 50_000_000
+
+
+def algorithmic_bytes_per_row(levels: int, m: int, q: float) -> float:
+    """inputs read once + 19 raw + 19 normalised doubles written once."""
+    return 340 + 24 * levels + 16 * m + q
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, m = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = max(mx, m)
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            sm = [float(l.split(",")[1]) for _, l in self.lines[-3:] if len(l.split(",")) > 2] or [0.0]
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_arm(args, rank: int, world: int):
+    """The reference's own CPU implementation on the host cores (bounded sample of the same workload)."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    import mrp_b200
+    from mrp_b200 import synth
+    from oracle import binding as ob
+
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    rows_each = args.ref_rows
+    # one independent instrument-day prefix per host thread: the reference is single-threaded per stream and
+    # parallel across instrument-days (scripts/multidate_feature_to_csv.sh:24,52-66)
+    specs = [synth.SynthSpec(n_rows=rows_each, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + i) for i in range(threads)]
+    batch = synth.to_numpy(synth.make_batch(specs))
+    hv = mrp_b200.HostView(batch)
+    use_ref = ob.ref_available(LEVELS)
+    kind = "reference" if use_ref else "port"
+
+    def one():
+        t0 = time.perf_counter()
+        if use_ref:
+            ob.run_reference(hv, None, use_book=False, nthreads=threads)
+        else:
+            ob.run_oracle(hv, nthreads=threads, want_dirs=False, want_counts=False)
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        one()
+    times = [one() for _ in range(max(1, args.steps))]
+    sec = sum(times) / len(times)
+    rows = hv.n_rows
+    value = rows / sec
+    sample = f"{threads} streams x {rows_each} rows (prefix of the 50 M-row instrument-day shape), {threads} host threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, args.steps),
+        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"single instrument-day, {FULL_ROWS} snapshots x {LEVELS} levels (BASELINE.json configs[1])",
+                   "levels": LEVELS, "ticks_per_row": TICKS_PER_ROW, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(levels: int, budget_rows: int):
+    """Bounded CPU sample timed beside the GPU number (rank 0, N = 1 only)."""
+    import mrp_b200
+    from mrp_b200 import synth
+    from oracle import binding as ob
+
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    specs = [synth.SynthSpec(n_rows=budget_rows, levels=levels, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + i) for i in range(threads)]
+    hv = mrp_b200.HostView(synth.to_numpy(synth.make_batch(specs)))
+    use_ref = ob.ref_available(levels)
+    t0 = time.perf_counter()
+    if use_ref:
+        ob.run_reference(hv, None, use_book=False, nthreads=threads)
+    else:
+        ob.run_oracle(hv, nthreads=threads, want_dirs=False, want_counts=False)
+    sec = time.perf_counter() - t0
+    return {"value": hv.n_rows / sec, "unit": UNIT, "cores": threads, "kind": "reference" if use_ref else "port",
+            "sample": f"{threads} streams x {budget_rows} rows, one host thread per stream, {sec:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=FULL_ROWS, help="snapshot rows per GPU (default: the 50 M-row config)")
+    ap.add_argument("--e2e-rows", type=int, default=0, help="rows for the host-buffer end-to-end leg (0 = same as --rows if host memory allows)")
+    ap.add_argument("--ref-rows", type=int, default=12000, help="rows per stream of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mrp_b200
+    from mrp_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic instrument-day, generated on the device (never crosses PCIe)
+    rows = args.rows
+    spec = synth.SynthSpec(n_rows=rows, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + rank)
+    batch = synth.make_batch([spec], device=dev)
+    n_ticks, n_trades = batch["tick_offsets"][-1], batch["trade_offsets"][-1]
+    q = n_trades / rows
+    m_eff = n_ticks / rows
+    torch.cuda.synchronize()
+
+    eng = mrp_b200.Engine(mrp_b200.default_params(), device=local_rank)
+    eng.bind_device(batch)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(max(args.warmup, 3)):
+        eng.run(stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = eng.launch_count()
+    eng.enable_timing(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kt_acc = {}
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.run(stream)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    kt = eng.kernel_times_ms()      # last step's per-kernel CUDA-event durations (same stream)
+    eng.enable_timing(False)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = rows * world / (ms_per_step * 1e-3)
+
+    # ---- the one collective on this path: global column moments (19 x {n, sum, sum^2})
+    mom = torch.from_numpy(eng.moments(stream)).to(dev)
+    if world > 1:
+        dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+    mom = mom.cpu().numpy()
+
+    # ---- roofline of the dominant kernel (live CUDA events on the launching stream, last timed step)
+    peak, peak_src = measured_peaks()
+    bytes_row = algorithmic_bytes_per_row(LEVELS, m_eff, q)
+    # algorithmic bytes per kernel: what each kernel must read + write once
+    kb = {
+        "tick_returns": rows * (8 * m_eff + 4 + 4 * 8),          # mids, tick cursor, 4 feature columns
+        "tick_spread": rows * (8 * m_eff + 4 + 8),               # spreads, cursor (re-read), 1 column
+        "trades": rows * (q + 4 + 3 * 8),                        # trade dirs, trade cursor, 3 columns
+        "book": rows * (8 + 24 * LEVELS + 16 + 4 + 11 * 8),      # ts, prices, sizes, buy/sell, adds, 11 columns
+        "normalize": rows * (2 * 19 * 8),                        # raw read once, z written once
+    }
+    dom = max(kt, key=kt.get)
+    whole_gbs = rows * bytes_row / (ms_per_step * 1e-3) / 1e9
+    roof = {
+        "bound": "hbm", "kernel": dom, "achieved": kb[dom] / (kt[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": kb[dom] / (kt[dom] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "whole_pass": {"bytes_per_row": bytes_row, "achieved": whole_gbs, "frac": whole_gbs / peak},
+        "kernels_ms": kt,
+        "kernels_gbs": {k: kb[k] / (kt[k] * 1e-3) / 1e9 for k in kt},
+    }
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        e2e_rows = args.e2e_rows or rows
+        try:
+            import psutil
+
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 64 << 30
+        need = e2e_rows * (algorithmic_bytes_per_row(LEVELS, m_eff, q) + 64)
+        while need > 0.6 * avail / max(1, min(world, 8)) and e2e_rows > 1_000_000:
+            e2e_rows //= 2
+            need = e2e_rows * (algorithmic_bytes_per_row(LEVELS, m_eff, q) + 64)
+        del eng
+        if e2e_rows == rows:
+            hb = batch
+        else:
+            del batch
+            torch.cuda.empty_cache()
+            hb = synth.make_batch([dataclass_replace(spec, n_rows=e2e_rows)], device=dev)
+        host = {}
+        for k, v in hb.items():
+            if isinstance(v, torch.Tensor):
+                if k == "trade_size":
+                    continue
+                host[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                host[k].copy_(v)
+            else:
+                host[k] = v
+        del hb
+        if e2e_rows == rows:
+            del batch
+        torch.cuda.empty_cache()
+        hv = mrp_b200.HostView({k: (v.numpy() if isinstance(v, torch.Tensor) else v) for k, v in host.items()})
+        raw_h = torch.empty((19, e2e_rows), dtype=torch.float64, pin_memory=True)
+        norm_h = torch.empty((19, e2e_rows), dtype=torch.float64, pin_memory=True)
+        eng2 = mrp_b200.Engine(mrp_b200.default_params(), device=local_rank)
+        import ctypes as C
+
+        def e2e_step():
+            eng2.upload(hv, stream)
+            eng2.run(stream)
+            eng2._check(eng2.lib.mrp_fg_download(eng2.ctx, C.c_void_p(raw_h.data_ptr()), C.c_void_p(norm_h.data_ptr()),
+                                                 C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(stream)))
+            eng2.sync(stream)
+
+        e2e_step()
+        barrier()
+        nst = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(nst):
+            e2e_step()
+        ev1.record()
+        barrier()
+        e_ms = ev0.elapsed_time(ev1) / nst
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        h2d = sum(v.numel() * v.element_size() for k, v in host.items() if isinstance(v, torch.Tensor))
+        d2h = raw_h.numel() * 8 * 2
+        e2e = {"value": e2e_rows * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "rows_per_gpu": e2e_rows, "ms_per_step": e_ms,
+               "checksum": float(norm_h[0, :1000].sum().item())}
+        eng2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(LEVELS, args.ref_rows)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"single instrument-day per GPU, {rows} snapshots x {LEVELS} levels, {m_eff:.2f} ticks and {q:.2f} trades per snapshot"
+                                   + (" (BASELINE.json configs[1])" if rows == FULL_ROWS else " (REDUCED rows: not the headline config)"),
+                       "rows_per_gpu": rows, "levels": LEVELS, "sharding": "instrument-day per GPU, no data-path collective",
+                       "l2": "inputs (>= 20 GB at 50 M rows) far exceed the 126 MB L2; no explicit flush"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "global_moments_midprice": [float(x) for x in mom[0]],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dataclass_replace(spec, **kw):
+    import dataclasses
+
+    return dataclasses.replace(spec, **kw)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,560 @@
+// api.cu — implementation of the C ABI declared in include/mrp_fg.h.
+//
+// Host-side plumbing only: argument checking, device buffers, the segment / tile tables, launch order
+// and timing.  No feature arithmetic lives here and there is no CPU fallback: every entry point that
+// needs the GPU fails with MRP_FG_ERR_CUDA when the device or a kernel is unavailable.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mrp_device.cuh"
+
+namespace mrp {
+cudaError_t launch_tick_returns(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_tick_spread(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_trades(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, const DevParams&, cudaStream_t);
+cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
+size_t ret_ring_bytes(int);
+size_t spr_ring_bytes(int);
+size_t trd_ring_bytes(int);
+}  // namespace mrp
+
+using namespace mrp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return MRP_FG_ERR_CUDA;
+}
+#define CU(call)                                             \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+constexpr int kNumKernels = 5;
+const char* kKernelNames[kNumKernels] = {"tick_returns", "tick_spread", "trades", "book", "normalize"};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return MRP_FG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            g_err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+            return e == cudaErrorMemoryAllocation ? MRP_FG_ERR_NOMEM : MRP_FG_ERR_CUDA;
+        }
+        cap = bytes;
+        return MRP_FG_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct mrp_fg_ctx {
+    mrp_fg_params p{};
+    int device = 0;
+    bool bound = false;
+    int n_streams = 0;
+    int64_t n_rows = 0, n_ticks = 0, n_trades = 0;
+    std::vector<int64_t> row_off, tick_off, trade_off;
+    DevInputs in{};
+    DevOutputs out{};
+    DevParams dp{};
+    // owned copies of the inputs (mrp_fg_upload)
+    DevBuf b_ts, b_bpx, b_apx, b_bsz, b_asz, b_buy, b_sell, b_adds, b_kcur, b_jcur, b_mid, b_spread, b_tdir;
+    // outputs
+    DevBuf b_raw, b_norm, b_bdir, b_adir, b_counts;
+    // tables
+    DevBuf b_segs, b_tiles, b_tile_tot, b_flags, b_tables, b_row_off;
+    int nseg = 0, ntiles = 0;
+    // timing
+    bool timing = false, have_times = false;
+    cudaEvent_t ev[kNumKernels + 1] = {};
+    bool ev_made = false;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int check_params(const mrp_fg_params& p) {
+    if (p.depth_levels < 2 || p.depth_levels > 1024) return fail(MRP_FG_ERR_INVALID, "depth_levels must be in [2,1024] (price_gap reads levels 0 and 1)");
+    if (p.stress_levels < 0 || p.stress_levels > p.depth_levels) return fail(MRP_FG_ERR_INVALID, "stress_levels must be in [0,depth_levels]");
+    if (p.mid_window < 1 || p.dir_window < 1 || p.spread_divisor < 1 || p.ewm_span < 0 || p.norm_window < 1)
+        return fail(MRP_FG_ERR_INVALID, "windows must be positive");
+    if (p.return_lag < 0 || p.return_lag + 1 > kThreads) return fail(MRP_FG_ERR_INVALID, "return_lag must be in [0,255]");
+    if (p.norm_mode != MRP_NORM_COMPENSATED && p.norm_mode != MRP_NORM_FAITHFUL) return fail(MRP_FG_ERR_INVALID, "unknown norm_mode");
+    return MRP_FG_OK;
+}
+
+int pick_tile_rows(int W) {
+    if (W <= 2048) return W;
+    int best = 0;
+    for (int t = 2048; t >= 128; --t)
+        if (W % t == 0) {
+            // prefer tiles around 1000-1500 rows: enough parallel tiles, short look-back (W/t totals)
+            if (best == 0) best = t;
+            if (t <= 1536) return t;
+        }
+    return best;
+}
+
+// Build device parameters, ring geometry and the host-computed constant tables.
+int setup_params(mrp_fg_ctx* c) {
+    const mrp_fg_params& p = c->p;
+    DevParams& d = c->dp;
+    d = DevParams{};
+    d.L = p.depth_levels;
+    d.mid_window = p.mid_window;
+    d.dir_window = p.dir_window;
+    d.spread_divisor = p.spread_divisor;
+    d.norm_window = p.norm_window;
+    d.return_lag = p.return_lag;
+    d.stress_levels = p.stress_levels;
+    d.emit_counts = p.emit_counts;
+    d.ewm_alpha = 2.0 / (p.ewm_span + 1);  // feature_processor.cpp:64
+    d.ewm_decay = 1 - d.ewm_alpha;         // :74
+    d.ofi_alpha = p.ofi_alpha;
+    d.ofi_decay = 1.0 - p.ofi_alpha;       // :133
+    d.ofi_min_total_vol = p.ofi_min_total_vol;
+    d.stress_alpha = p.stress_alpha;
+    d.stress_decay = 1.0 - p.stress_alpha; // :313
+    d.stress_min_size = p.stress_min_size;
+    d.stress_distance_decay = p.stress_distance_decay;
+
+    auto round4 = [](int x) { return (x + 3) & ~3; };
+    const int wmax = std::max(p.mid_window, p.dir_window + 1);
+    d.ret_ring = round4(wmax + kChunk + 4);
+    d.spr_ring = round4(p.mid_window + kChunk + 4);
+    d.trd_ring = round4(p.dir_window + kChunk + 4);
+    const size_t smem_max = 227 * 1024 - 2048;
+    if (ret_ring_bytes(d.ret_ring) > smem_max || spr_ring_bytes(d.spr_ring) > smem_max || trd_ring_bytes(d.trd_ring) > smem_max ||
+        (d.ret_ring + kChunk - 1) / kChunk + 1 > kMaxRingChunks)
+        return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window too large for the on-chip window ring (limit about 5000 ticks)");
+
+    // EMA halo: decay^rows < 1e-17 for the slower of the two EMAs, rounded up to whole chunks; also covers the lag
+    const double slow = std::max(d.ofi_decay, d.stress_decay);
+    int warm = 0;
+    if (slow > 0.0 && slow < 1.0) warm = (int)std::ceil(std::log(1e-17) / std::log(slow));
+    else if (slow >= 1.0) return fail(MRP_FG_ERR_INVALID, "EMA alphas must be in (0,1]");
+    warm = std::max(warm, p.return_lag + 1);
+    d.ema_warm_rows = ((warm + kThreads - 1) / kThreads) * kThreads;
+
+    d.tile_rows = pick_tile_rows(p.norm_window);
+    if (d.tile_rows <= 0) return fail(MRP_FG_ERR_INVALID, "norm_window above 2048 needs a divisor in [128,2048]");
+    d.tiles_back = p.norm_window / d.tile_rows;
+
+    // constant tables, evaluated by the host libm so that they are bit-identical to the reference's factors
+    std::vector<double> tab;
+    const size_t o_w = 0;
+    for (int i = 0; i < p.depth_levels; ++i) tab.push_back(std::exp(-i * p.ofi_depth_decay));  // feature_processor.cpp:121
+    const size_t o_e = tab.size();
+    for (int n = 0; n <= p.mid_window; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
+    const size_t o_o = tab.size();
+    for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
+    const size_t o_s = tab.size();
+    for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.stress_decay, (long double)n));
+    int rc = c->b_tables.ensure(tab.size() * sizeof(double));
+    if (rc) return rc;
+    CU(cudaMemcpy(c->b_tables.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    const double* t = static_cast<const double*>(c->b_tables.p);
+    d.ofi_weight = t + o_w;
+    d.ewm_pow = t + o_e;
+    d.ofi_pow = t + o_o;
+    d.stress_pow = t + o_s;
+    return MRP_FG_OK;
+}
+
+int check_view(const mrp_fg_ctx* c, const mrp_fg_soa_view* v, int want_memory) {
+    (void)c;
+    if (!v) return fail(MRP_FG_ERR_INVALID, "view is NULL");
+    if (v->memory != want_memory) return fail(MRP_FG_ERR_INVALID, want_memory == MRP_MEM_DEVICE ? "mrp_fg_bind_inputs needs a DEVICE view" : "mrp_fg_upload needs a HOST view");
+    if (v->n_streams < 1) return fail(MRP_FG_ERR_INVALID, "n_streams must be >= 1");
+    if (!v->row_offsets || !v->tick_offsets || !v->trade_offsets) return fail(MRP_FG_ERR_INVALID, "offset arrays are required");
+    const int S = v->n_streams;
+    if (v->row_offsets[0] != 0 || v->tick_offsets[0] != 0 || v->trade_offsets[0] != 0) return fail(MRP_FG_ERR_INVALID, "offsets must start at 0");
+    for (int s = 0; s < S; ++s) {
+        if (v->row_offsets[s + 1] < v->row_offsets[s] || v->tick_offsets[s + 1] < v->tick_offsets[s] || v->trade_offsets[s + 1] < v->trade_offsets[s])
+            return fail(MRP_FG_ERR_INVALID, "offsets must be non-decreasing");
+        if (v->tick_offsets[s + 1] - v->tick_offsets[s] > 0xfffffff0ll || v->trade_offsets[s + 1] - v->trade_offsets[s] > 0xfffffff0ll)
+            return fail(MRP_FG_ERR_INVALID, "a stream may hold at most 2^32-16 ticks / trades (cursors are uint32)");
+    }
+    const int64_t N = v->row_offsets[S];
+    if (N > 0 && (!v->ts_ns || !v->bid_px || !v->ask_px || !v->bid_sz || !v->ask_sz || !v->buy_vol || !v->sell_vol || !v->adds ||
+                  !v->tick_cursor || !v->trade_cursor))
+        return fail(MRP_FG_ERR_INVALID, "a snapshot-axis array is NULL");
+    if (v->tick_offsets[S] > 0 && (!v->mid || !v->spread)) return fail(MRP_FG_ERR_INVALID, "mid / spread are NULL");
+    if (v->trade_offsets[S] > 0 && !v->trade_dir) return fail(MRP_FG_ERR_INVALID, "trade_dir is NULL");
+    return MRP_FG_OK;
+}
+
+// Shape-dependent state: outputs, segment table, tile table.
+int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
+    const int S = v->n_streams;
+    c->n_streams = S;
+    c->row_off.assign(v->row_offsets, v->row_offsets + S + 1);
+    c->tick_off.assign(v->tick_offsets, v->tick_offsets + S + 1);
+    c->trade_off.assign(v->trade_offsets, v->trade_offsets + S + 1);
+    c->n_rows = c->row_off[S];
+    c->n_ticks = c->tick_off[S];
+    c->n_trades = c->trade_off[S];
+    const int64_t N = c->n_rows;
+    const int L = c->p.depth_levels;
+
+    int rc;
+    if ((rc = c->b_raw.ensure((size_t)N * MRP_FG_NUM_FEATURES * sizeof(double)))) return rc;
+    if ((rc = c->b_norm.ensure((size_t)N * MRP_FG_NUM_FEATURES * sizeof(double)))) return rc;
+    c->out.raw = static_cast<double*>(c->b_raw.p);
+    c->out.norm = static_cast<double*>(c->b_norm.p);
+    c->out.bdir = c->out.adir = nullptr;
+    c->out.counts = nullptr;
+    if (c->p.emit_dirs) {
+        if ((rc = c->b_bdir.ensure((size_t)N * L))) return rc;
+        if ((rc = c->b_adir.ensure((size_t)N * L))) return rc;
+        c->out.bdir = static_cast<int8_t*>(c->b_bdir.p);
+        c->out.adir = static_cast<int8_t*>(c->b_adir.p);
+    }
+    if (c->p.emit_counts) {
+        if ((rc = c->b_counts.ensure((size_t)N * MRP_FG_NUM_COUNTS * sizeof(int32_t)))) return rc;
+        c->out.counts = static_cast<int32_t*>(c->b_counts.p);
+        CU(cudaMemset(c->out.counts, 0, (size_t)N * MRP_FG_NUM_COUNTS * sizeof(int32_t)));
+    }
+
+    // row segments: enough CTAs to fill 148 SMs several times over, long enough to amortise the window halo
+    int64_t seg_rows = (N + 1183) / 1184;
+    seg_rows = std::min<int64_t>(std::max<int64_t>(seg_rows, 2048), 16384);
+    seg_rows = ((seg_rows + kThreads - 1) / kThreads) * kThreads;
+    if (const char* e = std::getenv("MRP_FG_SEGMENT_ROWS")) {
+        long v2 = std::atol(e);
+        if (v2 >= 1) seg_rows = v2;
+    }
+    std::vector<DevSegment> segs;
+    std::vector<DevTile> tiles;
+    const int TR = c->dp.tile_rows;
+    for (int s = 0; s < S; ++s) {
+        const int64_t r0 = c->row_off[s], r1 = c->row_off[s + 1];
+        for (int64_t a = r0; a < r1; a += seg_rows) {
+            DevSegment g{};
+            g.row_begin = a;
+            g.row_end = std::min(a + seg_rows, r1);
+            g.stream_row0 = r0;
+            g.stream_row1 = r1;
+            g.tick0 = c->tick_off[s];
+            g.n_ticks = c->tick_off[s + 1] - c->tick_off[s];
+            g.trade0 = c->trade_off[s];
+            g.n_trades = c->trade_off[s + 1] - c->trade_off[s];
+            segs.push_back(g);
+        }
+        const int first = (int)tiles.size();
+        int idx = 0;
+        for (int64_t a = r0; a < r1; a += TR, ++idx) {
+            DevTile t{};
+            t.row = a;
+            t.stream_row0 = r0;
+            t.n = (int32_t)std::min<int64_t>(TR, r1 - a);
+            t.index = idx;
+            t.first_id = first;
+            tiles.push_back(t);
+        }
+    }
+    c->nseg = (int)segs.size();
+    c->ntiles = (int)tiles.size();
+    if ((rc = c->b_segs.ensure(segs.size() * sizeof(DevSegment)))) return rc;
+    if ((rc = c->b_tiles.ensure(tiles.size() * sizeof(DevTile)))) return rc;
+    if ((rc = c->b_tile_tot.ensure(tiles.size() * 2 * MRP_FG_NUM_FEATURES * sizeof(double)))) return rc;
+    if ((rc = c->b_flags.ensure((tiles.size() + 1) * sizeof(int)))) return rc;
+    if ((rc = c->b_row_off.ensure((S + 1) * sizeof(int64_t)))) return rc;
+    if (!segs.empty()) CU(cudaMemcpy(c->b_segs.p, segs.data(), segs.size() * sizeof(DevSegment), cudaMemcpyHostToDevice));
+    if (!tiles.empty()) CU(cudaMemcpy(c->b_tiles.p, tiles.data(), tiles.size() * sizeof(DevTile), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->b_row_off.p, c->row_off.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    return MRP_FG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrp_fg_abi_version(void) { return MRP_FG_ABI_VERSION; }
+const char* mrp_fg_last_error(void) { return g_err.c_str(); }
+
+int mrp_fg_default_params(mrp_fg_params* p) {
+    if (!p) return fail(MRP_FG_ERR_INVALID, "params is NULL");
+    std::memset(p, 0, sizeof(*p));
+    p->depth_levels = 10;
+    p->mid_window = 1800;
+    p->dir_window = 1500;
+    p->spread_divisor = 1500;
+    p->ewm_span = 1500;
+    p->norm_window = 30000;
+    p->return_lag = 20;
+    p->stress_levels = 5;
+    p->ofi_depth_decay = 0.5;
+    p->ofi_alpha = 0.2;
+    p->ofi_min_total_vol = 1e-6;
+    p->stress_min_size = 5.0;
+    p->stress_distance_decay = 10.0;
+    p->stress_alpha = 0.1;
+    p->norm_mode = MRP_NORM_COMPENSATED;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out) {
+    if (!out) return fail(MRP_FG_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    mrp_fg_params pp;
+    if (p) pp = *p;
+    else mrp_fg_default_params(&pp);
+    int rc = check_params(pp);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(MRP_FG_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                         " (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(MRP_FG_ERR_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(MRP_FG_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100-class; the kernels are built for sm_100a only");
+    mrp_fg_ctx* c = new mrp_fg_ctx();
+    c->p = pp;
+    c->device = device;
+    rc = setup_params(c);
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_destroy(mrp_fg_ctx* c) {
+    if (!c) return MRP_FG_OK;
+    cudaSetDevice(c->device);
+    DevBuf* bufs[] = {&c->b_ts, &c->b_bpx, &c->b_apx, &c->b_bsz, &c->b_asz, &c->b_buy, &c->b_sell, &c->b_adds, &c->b_kcur,
+                      &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
+                      &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off};
+    for (DevBuf* b : bufs) b->release();
+    if (c->ev_made)
+        for (auto& ev : c->ev) cudaEventDestroy(ev);
+    delete c;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_bind_inputs(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    int rc = check_view(c, v, MRP_MEM_DEVICE);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    c->bound = false;
+    if ((rc = setup_shape(c, v))) return rc;
+    DevInputs& in = c->in;
+    in.n_rows = c->n_rows;
+    in.ts = v->ts_ns;
+    in.bid_px = v->bid_px;
+    in.ask_px = v->ask_px;
+    in.bid_sz = v->bid_sz;
+    in.ask_sz = v->ask_sz;
+    in.buy = v->buy_vol;
+    in.sell = v->sell_vol;
+    in.adds = v->adds;
+    in.kcur = v->tick_cursor;
+    in.jcur = v->trade_cursor;
+    in.mid = v->mid;
+    in.spread = v->spread;
+    in.tdir = v->trade_dir;
+    c->bound = true;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_upload(mrp_fg_ctx* c, const mrp_fg_soa_view* v, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    int rc = check_view(c, v, MRP_MEM_HOST);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    c->bound = false;
+    // the cursors are on the host here: validate what the kernels rely on
+    const int S = v->n_streams;
+    for (int s = 0; s < S; ++s) {
+        const int64_t K = v->tick_offsets[s + 1] - v->tick_offsets[s], T = v->trade_offsets[s + 1] - v->trade_offsets[s];
+        uint32_t pk = 0, pj = 0;
+        for (int64_t r = v->row_offsets[s]; r < v->row_offsets[s + 1]; ++r) {
+            const uint32_t k = v->tick_cursor[r], j = v->trade_cursor[r];
+            if (k < pk || j < pj) return fail(MRP_FG_ERR_INVALID, "cursors must be non-decreasing within a stream");
+            if ((int64_t)k > K || (int64_t)j > T) return fail(MRP_FG_ERR_INVALID, "a cursor points past the end of its stream's tick / trade arrays");
+            pk = k;
+            pj = j;
+        }
+    }
+    if ((rc = setup_shape(c, v))) return rc;
+    const int64_t N = c->n_rows, K = c->n_ticks, T = c->n_trades;
+    const int L = c->p.depth_levels;
+    struct Copy { DevBuf* b; const void* src; size_t bytes; };
+    const Copy copies[] = {
+        {&c->b_ts, v->ts_ns, (size_t)N * 8},       {&c->b_bpx, v->bid_px, (size_t)N * L * 8}, {&c->b_apx, v->ask_px, (size_t)N * L * 8},
+        {&c->b_bsz, v->bid_sz, (size_t)N * L * 4}, {&c->b_asz, v->ask_sz, (size_t)N * L * 4}, {&c->b_buy, v->buy_vol, (size_t)N * 8},
+        {&c->b_sell, v->sell_vol, (size_t)N * 8},  {&c->b_adds, v->adds, (size_t)N * 4},      {&c->b_kcur, v->tick_cursor, (size_t)N * 4},
+        {&c->b_jcur, v->trade_cursor, (size_t)N * 4}, {&c->b_mid, v->mid, (size_t)K * 8},     {&c->b_spread, v->spread, (size_t)K * 8},
+        {&c->b_tdir, v->trade_dir, (size_t)T},
+    };
+    for (const Copy& cp : copies) {
+        if ((rc = cp.b->ensure(cp.bytes))) return rc;
+        if (cp.bytes) CU(cudaMemcpyAsync(cp.b->p, cp.src, cp.bytes, cudaMemcpyHostToDevice, st));
+    }
+    DevInputs& in = c->in;
+    in.n_rows = N;
+    in.ts = static_cast<const uint64_t*>(c->b_ts.p);
+    in.bid_px = static_cast<const double*>(c->b_bpx.p);
+    in.ask_px = static_cast<const double*>(c->b_apx.p);
+    in.bid_sz = static_cast<const int32_t*>(c->b_bsz.p);
+    in.ask_sz = static_cast<const int32_t*>(c->b_asz.p);
+    in.buy = static_cast<const double*>(c->b_buy.p);
+    in.sell = static_cast<const double*>(c->b_sell.p);
+    in.adds = static_cast<const int32_t*>(c->b_adds.p);
+    in.kcur = static_cast<const uint32_t*>(c->b_kcur.p);
+    in.jcur = static_cast<const uint32_t*>(c->b_jcur.p);
+    in.mid = static_cast<const double*>(c->b_mid.p);
+    in.spread = static_cast<const double*>(c->b_spread.p);
+    in.tdir = static_cast<const int8_t*>(c->b_tdir.p);
+    c->bound = true;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "mrp_fg_run before mrp_fg_bind_inputs / mrp_fg_upload");
+    if (c->n_rows == 0) return MRP_FG_OK;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const DevSegment* segs = static_cast<const DevSegment*>(c->b_segs.p);
+    const bool tm = c->timing;
+    if (tm && !c->ev_made) {
+        for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+        c->ev_made = true;
+    }
+    if (tm) CU(cudaEventRecord(c->ev[0], st));
+    CU(launch_tick_returns(c->in, c->out, segs, c->nseg, c->dp, st));
+    if (tm) CU(cudaEventRecord(c->ev[1], st));
+    CU(launch_tick_spread(c->in, c->out, segs, c->nseg, c->dp, st));
+    if (tm) CU(cudaEventRecord(c->ev[2], st));
+    CU(launch_trades(c->in, c->out, segs, c->nseg, c->dp, st));
+    if (tm) CU(cudaEventRecord(c->ev[3], st));
+    CU(launch_book(c->in, c->out, segs, c->nseg, c->dp, st));
+    if (tm) CU(cudaEventRecord(c->ev[4], st));
+    CU(launch_normalize(c->out, c->n_rows, static_cast<const DevTile*>(c->b_tiles.p), c->ntiles,
+                        static_cast<double*>(c->b_tile_tot.p), static_cast<int*>(c->b_flags.p), c->dp, st));
+    c->launches += kNumKernels;
+    if (c->p.norm_mode == MRP_NORM_FAITHFUL) {
+        CU(launch_normalize_faithful(c->out, c->n_rows, static_cast<const int64_t*>(c->b_row_off.p), c->n_streams, c->dp, st));
+        c->launches += 1;
+    }
+    if (tm) {
+        CU(cudaEventRecord(c->ev[5], st));
+        c->have_times = true;
+    }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_outputs(mrp_fg_ctx* c, const double** raw, const double** norm, const int8_t** bid_dir, const int8_t** ask_dir,
+                   const int32_t** counts) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    if (raw) *raw = c->out.raw;
+    if (norm) *norm = c->out.norm;
+    if (bid_dir) *bid_dir = c->out.bdir;
+    if (ask_dir) *ask_dir = c->out.adir;
+    if (counts) *counts = c->out.counts;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_download(mrp_fg_ctx* c, double* raw, double* norm, int8_t* bid_dir, int8_t* ask_dir, int32_t* counts, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t N = (size_t)c->n_rows, L = (size_t)c->p.depth_levels;
+    if (N == 0) return MRP_FG_OK;
+    if (raw) CU(cudaMemcpyAsync(raw, c->out.raw, N * MRP_FG_NUM_FEATURES * 8, cudaMemcpyDeviceToHost, st));
+    if (norm) CU(cudaMemcpyAsync(norm, c->out.norm, N * MRP_FG_NUM_FEATURES * 8, cudaMemcpyDeviceToHost, st));
+    if ((bid_dir || ask_dir) && !c->out.bdir) return fail(MRP_FG_ERR_STATE, "directions were not requested (params.emit_dirs)");
+    if (bid_dir) CU(cudaMemcpyAsync(bid_dir, c->out.bdir, N * L, cudaMemcpyDeviceToHost, st));
+    if (ask_dir) CU(cudaMemcpyAsync(ask_dir, c->out.adir, N * L, cudaMemcpyDeviceToHost, st));
+    if (counts && !c->out.counts) return fail(MRP_FG_ERR_STATE, "counts were not requested (params.emit_counts)");
+    if (counts) CU(cudaMemcpyAsync(counts, c->out.counts, N * MRP_FG_NUM_COUNTS * 4, cudaMemcpyDeviceToHost, st));
+    return MRP_FG_OK;
+}
+
+int mrp_fg_moments(mrp_fg_ctx* c, double* out, void* stream) {
+    if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the normaliser's per-tile totals already hold sum x and sum x^2 of every tile: add them up in extended precision
+    std::vector<double> tot((size_t)c->ntiles * 2 * MRP_FG_NUM_FEATURES);
+    if (!tot.empty()) CU(cudaMemcpyAsync(tot.data(), c->b_tile_tot.p, tot.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int f = 0; f < MRP_FG_NUM_FEATURES; ++f) {
+        long double s = 0, s2 = 0;
+        for (int t = 0; t < c->ntiles; ++t) {
+            s += tot[(size_t)t * 2 * MRP_FG_NUM_FEATURES + f];
+            s2 += tot[(size_t)t * 2 * MRP_FG_NUM_FEATURES + MRP_FG_NUM_FEATURES + f];
+        }
+        out[f * 3 + 0] = (double)c->n_rows;
+        out[f * 3 + 1] = (double)s;
+        out[f * 3 + 2] = (double)s2;
+    }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_sync(mrp_fg_ctx* c, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    CU(cudaGetLastError());
+    return MRP_FG_OK;
+}
+
+int mrp_fg_num_kernels(void) { return kNumKernels; }
+const char* mrp_fg_kernel_name(int i) { return (i >= 0 && i < kNumKernels) ? kKernelNames[i] : ""; }
+
+int mrp_fg_enable_timing(mrp_fg_ctx* c, int on) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    c->timing = on != 0;
+    c->have_times = false;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_kernel_times_ms(mrp_fg_ctx* c, float* ms) {
+    if (!c || !ms) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->have_times) return fail(MRP_FG_ERR_STATE, "no timed run yet (mrp_fg_enable_timing, then mrp_fg_run)");
+    CU(cudaEventSynchronize(c->ev[kNumKernels]));
+    for (int i = 0; i < kNumKernels; ++i) CU(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    return MRP_FG_OK;
+}
+
+int64_t mrp_fg_launch_count(const mrp_fg_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,347 @@
+// kernels_row.cu — trade-axis pass and snapshot-axis (book) pass.
+//
+//   k_trades : reversal_rate, aggressor_bias, shannon_entropy
+//              (ref: feature_processor.cpp:231-247 and :254-269 over rolling_trade_directions, feature_engine.cpp:88-93)
+//   k_book   : midprice, log_spread, log_return, ofi, signed_volume_pressure, order_arrival_rate, depth_imbalance,
+//              market_depth, lob_slope, price_gap, liquidity_stress, and the int8 depth-change directions
+//              (ref: feature_processor.cpp:32-43, 111-153, 157-212, 271-317; order_book.cpp:208-239)
+#include "mrp_device.cuh"
+
+namespace mrp {
+
+// ------------------------------------------------------------------------------------------------
+// trade pass: integer prefix counts in a ring, same skeleton as the tick passes
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) TrdEntry {
+    uint32_t pos, neg, rev;  // running counts: dir > 0, dir < 0, reversal pairs (j-1, j)
+    int32_t sum;             // running sum of directions
+};
+__device__ __forceinline__ unsigned trd_byte(int slot) { return (unsigned)slot * 16u + ((unsigned)slot >> 2) * 16u; }
+
+__global__ void __launch_bounds__(kThreads, 4)
+k_trades(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
+    extern __shared__ __align__(16) unsigned char ring[];
+    __shared__ int sWarpD[kWarps];
+    __shared__ int sCarD;
+    __shared__ uint32_t sPos[kWarps], sNeg[kWarps], sRev[kWarps];
+    __shared__ int32_t sSum[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevSegment sg = segs[blockIdx.x];
+    const int64_t ra = sg.row_begin, rb = sg.row_end;
+    const int8_t* __restrict__ tdir = in.tdir + sg.trade0;
+    const uint32_t* __restrict__ jcur = in.jcur;
+    const int RING = P.trd_ring;
+    const int64_t jend = jcur[rb - 1];
+    int64_t base = (int64_t)jcur[ra] - P.dir_window - 2;
+    if (base < 0) base = 0;
+    int64_t nchunks = (jend - base + kChunk - 1) / kChunk;
+    if (nchunks < 1) nchunks = 1;
+
+    uint32_t cPos = 0, cNeg = 0, cRev = 0;
+    int32_t cSum = 0;
+    if (tid == 0) sCarD = base > 0 ? (int)tdir[base - 1] : 0;
+    int64_t r_next = ra;
+    int cs_slot = 0;
+
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t cs = base + c * kChunk;
+        int D[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            int64_t jj = cs + tid * kPerThread + i;
+            D[i] = jj < jend ? (int)tdir[jj] : 0;
+        }
+        if (lane == 31) sWarpD[warp] = D[kPerThread - 1];
+        __syncthreads();
+        int Dp = __shfl_up_sync(0xffffffffu, D[kPerThread - 1], 1);
+        if (lane == 0) Dp = warp == 0 ? sCarD : sWarpD[warp - 1];
+
+        uint32_t lp[kPerThread], ln[kPerThread], lr[kPerThread];
+        int32_t ls[kPerThread];
+        uint32_t ap = 0, an = 0, ar = 0;
+        int32_t as = 0;
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const int64_t jj = cs + tid * kPerThread + i;
+            const int d = D[i];
+            ap += d > 0;
+            an += d < 0;
+            ar += (jj > 0 && d != 0 && d == -Dp) ? 1u : 0u;  // feature_processor.cpp:235
+            as += d;
+            lp[i] = ap; ln[i] = an; lr[i] = ar; ls[i] = as;
+            Dp = d;
+        }
+        uint32_t ip = ap, inn = an, ir = ar;
+        int32_t is = as;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t tp = __shfl_up_sync(0xffffffffu, ip, d), tn = __shfl_up_sync(0xffffffffu, inn, d),
+                           tr = __shfl_up_sync(0xffffffffu, ir, d);
+            const int32_t ts = __shfl_up_sync(0xffffffffu, is, d);
+            if (lane >= d) { ip += tp; inn += tn; ir += tr; is += ts; }
+        }
+        if (lane == 31) { sPos[warp] = ip; sNeg[warp] = inn; sRev[warp] = ir; sSum[warp] = is; }
+        __syncthreads();
+        uint32_t bp = cPos + ip - ap, bn = cNeg + inn - an, br = cRev + ir - ar;
+        int32_t bs = cSum + is - as;
+        uint32_t tp = 0, tn = 0, tr = 0;
+        int32_t ts = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            if (w == warp) { bp += tp; bn += tn; br += tr; bs += ts; }
+            tp += sPos[w]; tn += sNeg[w]; tr += sRev[w]; ts += sSum[w];
+        }
+        if (tid == kThreads - 1) sCarD = D[kPerThread - 1];
+        {
+            int slot = cs_slot + tid * kPerThread;
+            if (slot >= RING) slot -= RING;
+#pragma unroll
+            for (int i = 0; i < kPerThread; ++i) {
+                TrdEntry en;
+                en.pos = bp + lp[i]; en.neg = bn + ln[i]; en.rev = br + lr[i]; en.sum = bs + ls[i];
+                *reinterpret_cast<TrdEntry*>(ring + trd_byte(slot + i)) = en;
+            }
+        }
+        cPos += tp; cNeg += tn; cRev += tr; cSum += ts;
+        __syncthreads();
+
+        auto get = [&](int64_t k) -> TrdEntry {
+            int slot = cs_slot + (int)(k - cs);
+            if (slot < 0) slot += RING;
+            else if (slot >= RING) slot -= RING;
+            return *reinterpret_cast<const TrdEntry*>(ring + trd_byte(slot));
+        };
+        const int64_t ce = (c + 1 == nchunks) ? (int64_t)0x7fffffffffffll : cs + kChunk;
+        while (true) {
+            const int64_t r = r_next + tid;
+            const int64_t je = r < rb ? (int64_t)jcur[r] : (int64_t)0x7fffffffffffffll;
+            const bool q = je <= ce;
+            if (q) {
+                int64_t jb = je - P.dir_window;
+                if (jb < 0) jb = 0;
+                const int64_t nd = je - jb;  // rolling_trade_directions->size()
+                int32_t pos = 0, neg = 0, rev = 0, isum = 0;
+                if (je > 0) {
+                    const TrdEntry H = get(je - 1);
+                    pos = (int32_t)H.pos; neg = (int32_t)H.neg; isum = H.sum;
+                    if (jb > 0) {
+                        const TrdEntry Lo = get(jb - 1);
+                        pos -= (int32_t)Lo.pos; neg -= (int32_t)Lo.neg; isum -= Lo.sum;
+                    }
+                    rev = (int32_t)(H.rev - get(jb).rev);  // pairs (i-1,i) with i in [jb+1, je-1]
+                }
+                const double rr = nd > 1 ? (double)rev / (double)nd : 0.0;  // feature_processor.cpp:239
+                const double ab = (double)isum / (double)nd;                // :246 — 0/0 = NaN with no trades
+                const int tot = pos + neg;                                  // :261-269
+                const double p_pos = tot > 0 ? (double)pos / tot : 0.0;
+                const double p_neg = tot > 0 ? (double)neg / tot : 0.0;
+                double ent = 0.0;
+                ent = entropy_term(ent, p_pos);
+                ent = entropy_term(ent, p_neg);
+                out.raw[(int64_t)MRP_F_REVERSAL_RATE * in.n_rows + r] = rr;
+                out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * in.n_rows + r] = ab;
+                out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * in.n_rows + r] = ent;
+                if (out.counts) {
+                    out.counts[(int64_t)MRP_C_TRADE_POS * in.n_rows + r] = pos;
+                    out.counts[(int64_t)MRP_C_TRADE_NEG * in.n_rows + r] = neg;
+                    out.counts[(int64_t)MRP_C_TRADE_REVERSALS * in.n_rows + r] = rev;
+                    out.counts[(int64_t)MRP_C_TRADE_TOTAL * in.n_rows + r] = (int32_t)nd;
+                    out.counts[(int64_t)MRP_C_TRADE_DIR_SUM * in.n_rows + r] = isum;
+                }
+            }
+            const int nq = __syncthreads_count(q);
+            r_next += nq;
+            if (nq < kThreads) break;
+        }
+        cs_slot += kChunk;
+        if (cs_slot >= RING) cs_slot -= RING;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// book pass: one thread per snapshot row, 256 rows per chunk, chunks walked in time order so that the
+// two EMAs (ofi: 0.2/0.8, liquidity stress: 0.1/0.9) are carried as block scans of y -> a*y + b.
+// A segment that starts mid-stream first walks `ema_warm_rows` halo rows (only what feeds the EMAs
+// and the lag-21 midprice); 0.9^halo is below 1e-17, far under the fp64 noise of the features.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ema_scan(double b, const double* __restrict__ pw, double carry_in, double* sWarp,
+                                           int lane, int warp, double& carry_out) {
+    double v = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = shfl_up_d(v, d);
+        if (lane >= d) v = __ldg(pw + d) * t + v;
+    }
+    if (lane == 31) sWarp[warp] = v;
+    __syncthreads();
+    const double p32 = __ldg(pw + 32);
+    double cw = carry_in, co = carry_in;
+#pragma unroll
+    for (int u = 0; u < kWarps; ++u) {
+        if (u == warp) cw = co;
+        co = p32 * co + sWarp[u];
+    }
+    carry_out = co;
+    return __ldg(pw + lane + 1) * cw + v;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
+    __shared__ double sLM[2][kThreads], sMid[2][kThreads];
+    __shared__ double sWarpLiq[kWarps], sCarLiq;
+    __shared__ double sWOfi[kWarps], sWSt[kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevSegment sg = segs[blockIdx.x];
+    const int64_t ra = sg.row_begin, rb = sg.row_end, sr0 = sg.stream_row0;
+    const int64_t N = in.n_rows;
+    const int L = P.L;
+    int64_t wa = ra - P.ema_warm_rows;
+    if (wa < sr0) wa = sr0;
+    const int back = P.return_lag + 1;  // feature_normalizer.hpp:19-24
+
+    double yOfi = 0.0, ySt = 0.0;
+    if (tid == 0) sCarLiq = 0.0;
+    int buf = 0;
+    __syncthreads();
+
+    for (int64_t c0 = wa; c0 < rb; c0 += kThreads, buf ^= 1) {
+        const int64_t t = c0 + tid;
+        const bool act = t < rb;
+        const bool full = act && t >= ra;       // rows that are written (the rest only warm the EMAs)
+        const bool hasprev = act && t > sr0;    // a previous snapshot exists in this stream
+        const int64_t tc = act ? t : rb - 1;    // clamp loads of idle lanes
+
+        const double bb = in.bid_px[tc], ba = in.ask_px[tc];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
+        const double midp = (ba + bb) / 2;                    // feature_processor.cpp:34,161
+        const double log_mid = log(midp);
+
+        double raw_ofi = 0.0, liq_b = 0.0, liq_a = 0.0;
+        double bid_depth = 0.0, ask_depth = 0.0, bid_lw = 0.0, ask_lw = 0.0;
+        double log_bb = 0.0, log_ba = 0.0;
+        double p0b = 0, p1b = 0, p0a = 0, p1a = 0;
+        int s0b = 0, s1b = 0, s0a = 0, s1a = 0;
+        for (int i = 0; i < L; ++i) {
+            const int64_t o = (int64_t)i * N + tc;
+            const double bp = in.bid_px[o], ap = in.ask_px[o];
+            const int bs = in.bid_sz[o], as = in.ask_sz[o];
+            int pbs = __shfl_up_sync(0xffffffffu, bs, 1), pas = __shfl_up_sync(0xffffffffu, as, 1);
+            if (lane == 0) {
+                pbs = hasprev ? in.bid_sz[o - 1] : 0;  // first snapshot compares with an empty book (order_book.cpp:115,168)
+                pas = hasprev ? in.ask_sz[o - 1] : 0;
+            }
+            if (!hasprev) { pbs = 0; pas = 0; }
+            const int bd = (bs > pbs) - (bs < pbs);    // order_book.cpp:208-239
+            const int ad = (as > pas) - (as < pas);
+            if (full && out.bdir) { out.bdir[o] = (int8_t)bd; out.adir[o] = (int8_t)ad; }
+            const double w = __ldg(P.ofi_weight + i);  // exp(-i*0.5), feature_processor.cpp:121
+            const double bid_contrib = (double)(bd * bs) * w;
+            const double ask_contrib = (double)(ad * as) * w;
+            raw_ofi += bid_contrib - ask_contrib;      // :125
+            if (i < P.stress_levels) {                 // :282-299
+                if (bp > 0.0 && (double)bs >= P.stress_min_size) liq_b += exp(-(bb - bp) * P.stress_distance_decay) * bs;
+                if (ap > 0.0 && (double)as >= P.stress_min_size) liq_a += exp(-(ap - ba) * P.stress_distance_decay) * as;
+            }
+            if (i == 0) { p0b = bp; p0a = ap; s0b = bs; s0a = as; }
+            if (i == 1) { p1b = bp; p1a = ap; s1b = bs; s1a = as; }
+            if (full) {                                // :164-175, :189-200
+                if (i == 0) { log_bb = log(bp); log_ba = log(ap); }
+                if (bp > 0) {
+                    const double dist = fabs(log_mid - (i == 0 ? log_bb : log(bp)));
+                    bid_lw += dist * bs;
+                    bid_depth += bs;
+                }
+                if (ap > 0) {
+                    const double dist = fabs((i == 0 ? log_ba : log(ap)) - log_mid);
+                    ask_lw += dist * as;
+                    ask_depth += as;
+                }
+            }
+        }
+        const double liq = liq_b + liq_a;  // :301
+
+        // neighbours: previous row's liquidity, timestamp; lag-21 midprice through shared memory
+        sLM[buf][tid] = log_mid;
+        sMid[buf][tid] = midp;
+        if (lane == 31) sWarpLiq[warp] = liq;
+        const unsigned long long ts = in.ts[tc];
+        unsigned long long pts = __shfl_up_sync(0xffffffffu, ts, 1);
+        if (lane == 0) pts = hasprev ? in.ts[tc - 1] : 0ull;
+        if (!hasprev) pts = 0ull;
+        __syncthreads();
+        double pliq = shfl_up_d(liq, 1);
+        if (lane == 0) pliq = warp == 0 ? sCarLiq : sWarpLiq[warp - 1];
+        if (!hasprev) pliq = 0.0;  // cache_.prev_liquidity starts at 0 (feature_processor.hpp:27)
+        // lag-(return_lag+1) midprice: read NOW (two barriers separate this read from the next chunk's writes)
+        double old_mid, old_lm;
+        {
+            const int j = tid - back;
+            old_mid = j >= 0 ? sMid[buf][j] : sMid[buf ^ 1][kThreads + j];
+            old_lm = j >= 0 ? sLM[buf][j] : sLM[buf ^ 1][kThreads + j];
+        }
+
+        const double buy = in.buy[tc], sell = in.sell[tc];
+        const double total_volume = buy + sell;                                               // :129
+        const double x_ofi = (total_volume > P.ofi_min_total_vol) ? raw_ofi / total_volume : 0.0;  // :130
+        double raw_stress = 0.0;                                                              // :304-308
+        if (pliq > 0.0) raw_stress = -((liq - pliq) / pliq);
+
+        double coOfi, coSt;
+        const double ofi = ema_scan(act ? P.ofi_alpha * x_ofi : 0.0, P.ofi_pow, yOfi, sWOfi, lane, warp, coOfi);  // :133
+        const double stress = ema_scan(act ? P.stress_alpha * raw_stress : 0.0, P.stress_pow, ySt, sWSt, lane, warp, coSt);  // :311-313
+        yOfi = coOfi;
+        ySt = coSt;
+        if (tid == kThreads - 1) sCarLiq = liq;
+
+        if (full) {
+            // log_return, :37-42: the normaliser deque holds min(t, W) earlier rows when row t asks for index `lag`
+            const int64_t tl = t - sr0;
+            const int64_t have = tl < P.norm_window ? tl : P.norm_window;
+            double log_ret = 0.0;
+            if ((int64_t)P.return_lag < have && old_mid > 0.0) log_ret = log_mid - old_lm;
+            double rate = 0.0;  // :143-151
+            if (pts > 0ull) {
+                const unsigned long long delta_ns = ts - pts;
+                const double seconds = (double)delta_ns * 1e-9;
+                rate = (seconds > 0.0) ? (double)in.adds[tc] / seconds : 0.0;
+            }
+            const double depth = bid_depth + ask_depth;
+            const double bid_slope = (bid_depth > 0.0) ? bid_lw / bid_depth : 0.0;  // :202-204
+            const double ask_slope = (ask_depth > 0.0) ? ask_lw / ask_depth : 0.0;
+            const double gb = (p0b * s0b - p1b * s1b) / (double)(s0b + s1b);        // :207-211
+            const double ga = (p0a * s0a - p1a * s1a) / (double)(s0a + s1a);
+            double* raw = out.raw + t;
+            raw[(int64_t)MRP_F_MIDPRICE * N] = midp;
+            raw[(int64_t)MRP_F_LOG_SPREAD * N] = log_ba - log_bb;                   // :33
+            raw[(int64_t)MRP_F_LOG_RETURN * N] = log_ret;
+            raw[(int64_t)MRP_F_OFI * N] = ofi;
+            raw[(int64_t)MRP_F_SIGNED_VOLUME_PRESSURE * N] = (total_volume > 0.0) ? (buy - sell) / total_volume : 0.0;  // :137-140
+            raw[(int64_t)MRP_F_ORDER_ARRIVAL_RATE * N] = rate;
+            raw[(int64_t)MRP_F_DEPTH_IMBALANCE * N] = (depth > 0.0) ? (bid_depth - ask_depth) / depth : 0.0;  // :181-183
+            raw[(int64_t)MRP_F_MARKET_DEPTH * N] = depth;                           // :178
+            raw[(int64_t)MRP_F_LOB_SLOPE * N] = bid_slope + ask_slope;
+            raw[(int64_t)MRP_F_PRICE_GAP * N] = gb + ga;
+            raw[(int64_t)MRP_F_LIQUIDITY_STRESS * N] = stress;
+        }
+    }
+}
+
+size_t trd_ring_bytes(int ring) { return (size_t)ring * 20u; }
+
+cudaError_t launch_trades(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
+                          const DevParams& P, cudaStream_t st) {
+    const size_t smem = trd_ring_bytes(P.trd_ring);
+    cudaError_t e = cudaFuncSetAttribute(k_trades, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_trades<<<nseg, kThreads, smem, st>>>(in, out, segs, P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
+                        const DevParams& P, cudaStream_t st) {
+    k_book<<<nseg, kThreads, 0, st>>>(in, out, segs, P);
+    return cudaGetLastError();
+}
+
+}  // namespace mrp

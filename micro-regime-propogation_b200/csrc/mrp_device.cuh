@@ -1,0 +1,100 @@
+// mrp_device.cuh — shared device-side types and helpers for the sm_100a feature kernels.
+//
+// Design in one paragraph (details in DESIGN.md): the reference evaluates, per snapshot, O(window)
+// loops over three rolling deques (1800 mids/spreads, 1500 tick directions, 1500 trade directions;
+// feature_processor.cpp:48-108,215-269).  Here every window quantity is a difference of running
+// prefix values along its own axis (tick axis, trade axis), held in a shared-memory ring that covers
+// one window plus one chunk, so each tick / trade is read from HBM once, costs one log, and each
+// snapshot row is finalised from two or three ring look-ups addressed by its cursors.  The time axis
+// of a stream is cut into row segments; one CTA streams through one segment (halo = one window).
+// All arithmetic is fp64, compiled with -fmad=false so a*b+c is rounded exactly as the reference's
+// x86-64 SSE2 code rounds it; explicit fma() is used only inside scan carries where the reference
+// has no counterpart.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mrp_fg.h"
+
+namespace mrp {
+
+struct DevInputs {
+    int64_t n_rows;  // total rows of the batch == level / column stride
+    const uint64_t* ts;
+    const double* bid_px;
+    const double* ask_px;
+    const int32_t* bid_sz;
+    const int32_t* ask_sz;
+    const double* buy;
+    const double* sell;
+    const int32_t* adds;
+    const uint32_t* kcur;
+    const uint32_t* jcur;
+    const double* mid;
+    const double* spread;
+    const int8_t* tdir;
+};
+
+struct DevOutputs {
+    double* raw;     // [19][n_rows]
+    double* norm;    // [19][n_rows]
+    int8_t* bdir;    // [L][n_rows] or null
+    int8_t* adir;    // [L][n_rows] or null
+    int32_t* counts; // [MRP_FG_NUM_COUNTS][n_rows] or null
+};
+
+// One CTA's unit of work on the tick / trade / snapshot axes: rows [row_begin,row_end) of one stream.
+struct DevSegment {
+    int64_t row_begin, row_end;      // global row indices
+    int64_t stream_row0, stream_row1; // the stream's global row range
+    int64_t tick0, n_ticks;          // the stream's ticks: global offset and count
+    int64_t trade0, n_trades;        // the stream's trades
+};
+
+// One CTA's unit of work in the normaliser: a tile of `n` rows starting at global row `row`.
+struct DevTile {
+    int64_t row;          // global first row of the tile
+    int64_t stream_row0;  // global first row of the stream
+    int32_t n;            // rows in this tile (<= tile_rows)
+    int32_t index;        // tile index within the stream
+    int32_t first_id;     // global id of the stream's tile 0
+    int32_t pad;
+};
+
+struct DevParams {
+    int32_t L, mid_window, dir_window, spread_divisor, norm_window, return_lag, stress_levels;
+    int32_t emit_counts;
+    double ewm_alpha, ewm_decay;            // alpha = 2/(span+1), decay = 1-alpha
+    double ofi_alpha, ofi_decay, ofi_min_total_vol;
+    double stress_alpha, stress_decay, stress_min_size, stress_distance_decay;
+    const double* ofi_weight;   // [L]  exp(-i*depth_decay), computed by the host libm
+    const double* ewm_pow;      // [mid_window+1]  decay^n
+    const double* ofi_pow;      // [257]           ofi_decay^n
+    const double* stress_pow;   // [257]           stress_decay^n
+    // ring geometry (entries), computed by the host
+    int32_t ret_ring, spr_ring, trd_ring;
+    int32_t ema_warm_rows;      // halo rows that warm the two row-axis EMAs
+    int32_t tile_rows;          // normaliser tile (divides norm_window, or == norm_window)
+    int32_t tiles_back;         // norm_window / tile_rows
+};
+
+constexpr int kThreads = 256;          // CTA size of the axis passes
+constexpr int kWarps = kThreads / 32;
+constexpr int kPerThread = 4;          // consecutive ticks / trades per thread
+constexpr int kChunk = kThreads * kPerThread;  // 1024 elements per chunk
+constexpr int kChunkShift = 10;
+constexpr int kMaxRingChunks = 12;     // count-base slots
+
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int d) {
+    return __shfl_up_sync(0xffffffffu, v, d);
+}
+__device__ __forceinline__ bool finite_d(double x) { return fabs(x) <= 1.7976931348623157e308; }
+
+// -x*log2(x) terms in the reference's order (feature_processor.cpp:225-228, 265-267).
+__device__ __forceinline__ double entropy_term(double acc, double p) {
+    if (p > 0) acc -= p * log2(p);
+    return acc;
+}
+
+}  // namespace mrp

@@ -1,0 +1,58 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import mrp_b200
+from mrp_b200 import synth
+from oracle import binding as ob
+
+from helpers import (make_host_batch, nan_pattern_equal, norm_check, norm_errors, raw_errors, run_gpu)
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(batch, params=None, z_tol=1e-9, mode="upload"):
+    p = params or mrp_b200.default_params(emit_dirs=1, emit_counts=1)
+    hv, got = run_gpu(batch, p, mode)
+    ref = ob.run_oracle(hv, p)
+    # integer book-delta and count columns: bit-exact
+    assert np.array_equal(got["bid_dir"], ref["bid_dir"])
+    assert np.array_equal(got["ask_dir"], ref["ask_dir"])
+    for i, name in enumerate(mrp_b200.COUNTS):
+        assert np.array_equal(got["counts"][i], ref["counts"][i]), f"count column {name}"
+    # integer-valued feature columns: bit-exact
+    for name in ("midprice", "market_depth"):
+        c = mrp_b200.FEATURES.index(name)
+        assert np.array_equal(got["raw"][c], ref["raw"][c]), name
+    assert nan_pattern_equal(got["raw"], ref["raw"])
+    re = raw_errors(got["raw"], ref["raw"])
+    assert (re <= 1.0).all(), {mrp_b200.FEATURES[i]: re[i] for i in np.nonzero(re > 1.0)[0]}
+    assert nan_pattern_equal(got["norm"], ref["norm"])
+    # z-scores: conditioning-aware, against the exactly-summed definition and against the reference itself
+    wa, wb, drift, frac = norm_check(got["norm"], ref["raw"], ref["norm"], hv.arrays["row_offsets"], p.norm_window, z_tol)
+    assert frac > 0.95
+    assert (wa <= 1.0).all(), {mrp_b200.FEATURES[i]: wa[i] for i in np.nonzero(wa > 1.0)[0]}
+    assert (wb <= 1.0).all(), {mrp_b200.FEATURES[i]: (wb[i], drift[i]) for i in np.nonzero(wb > 1.0)[0]}
+    zr = norm_errors(got["norm"], ref["norm"])
+    print("worst z ratio vs exact %.3g, vs reference %.3g; reference drift %.3g; plain max|dz| vs reference %.3g"
+          % (wa.max(), wb.max(), drift.max(), zr.max()))
+    return got, ref
+
+
+def test_single_stream_default():
+    _check(make_host_batch([synth.SynthSpec(n_rows=6000, seed=11)]))
+
+
+def test_cold_start_variable_cursors():
+    # windows grow from empty; first rows have no trades (aggressor_bias = 0/0 = NaN)
+    _check(make_host_batch([synth.SynthSpec(n_rows=3000, seed=12, warm_ticks=0, warm_trades=0, variable_cursors=True)]))
+
+
+def test_multi_stream_device_pointers():
+    specs = [synth.SynthSpec(n_rows=n, seed=20 + i, variable_cursors=bool(i & 1)) for i, n in enumerate((1, 2, 300, 2500, 1025))]
+    _check(make_host_batch(specs), mode="device")
+
+
+def test_normaliser_window_eviction():
+    # longer than WINDOW_SIZE = 30000 rows so the rolling z-score window evicts
+    _check(make_host_batch([synth.SynthSpec(n_rows=33500, seed=13)]))
