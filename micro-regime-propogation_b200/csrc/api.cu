@@ -176,6 +176,19 @@ int setup_params(mrp_fg_ctx* c) {
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
     const size_t o_s = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.stress_decay, (long double)n));
+    if (tab.size() & 1) tab.push_back(0.0);  // keep the double2 table 16-byte aligned
+    const size_t o_i = tab.size();
+    for (int n = 0; n <= p.norm_window; ++n) {  // 1/n in double-double, so sum*(1/n) rounds like sum/n
+        const long double r = n > 0 ? 1.0L / (long double)n : 0.0L;
+        const double hi = (double)r;
+        tab.push_back(hi);
+        tab.push_back((double)(r - (long double)hi));
+    }
+    const size_t o_h = tab.size();
+    const int hmax = std::max(p.dir_window, p.mid_window) + 1;
+    for (int n = 0; n <= hmax; ++n) tab.push_back(n > 0 ? (double)((long double)n * log2l((long double)n)) : 0.0);
+    const size_t o_c = tab.size();
+    for (int n = 0; n <= p.mid_window + 1; ++n) tab.push_back(n > 0 ? 1.0 / (double)n : 0.0);
     int rc = c->b_tables.ensure(tab.size() * sizeof(double));
     if (rc) return rc;
     CU(cudaMemcpy(c->b_tables.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -184,6 +197,9 @@ int setup_params(mrp_fg_ctx* c) {
     d.ewm_pow = t + o_e;
     d.ofi_pow = t + o_o;
     d.stress_pow = t + o_s;
+    d.inv_n = reinterpret_cast<const double2*>(t + o_i);
+    d.clog2c = t + o_h;
+    d.inv_cnt = t + o_c;
     return MRP_FG_OK;
 }
 

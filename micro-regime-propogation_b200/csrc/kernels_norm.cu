@@ -24,30 +24,53 @@ constexpr int kNormWarps = 10;
 constexpr int kNormThreads = kNormWarps * 32;
 constexpr int kNF = MRP_FG_NUM_FEATURES;
 constexpr int kRowsPerLane = 4;
+constexpr int kStep = 32 * kRowsPerLane;
 
 __device__ __forceinline__ int ld_flag(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// four consecutive doubles of a lane: two 128-bit loads when the column is 16-byte aligned
+__device__ __forceinline__ void load4(const double* __restrict__ p, int i, int n, bool vec, double (&o)[kRowsPerLane]) {
+    if (vec && i + kRowsPerLane <= n) {
+        const double2 a = *reinterpret_cast<const double2*>(p + i), b = *reinterpret_cast<const double2*>(p + i + 2);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRowsPerLane; ++k) o[k] = i + k < n ? p[i + k] : 0.0;
+    }
+}
 
 __global__ void __launch_bounds__(kNormThreads, 2)
 k_normalize(const DevOutputs out, const int64_t N, const DevTile* __restrict__ tiles, double* __restrict__ tile_tot,
             int* __restrict__ flags, unsigned int* __restrict__ ticket, const DevParams P) {
     __shared__ int sId;
-    __shared__ double sHead[2 * kNF];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sId = (int)atomicAdd(ticket, 1u);
     __syncthreads();
     const int id = sId;
     const DevTile T = tiles[id];
     const int n = T.n;
+    // After this point the ten warps of the CTA never meet again: every warp owns whole feature columns.
 
-    // ---- pass 1: this tile's column totals, published before anything is awaited
+    // ---- pass 1: column totals of this tile, published (release) before anything is awaited.
+    //      flags[id] counts the columns published so far; a tile is complete at 19.
     for (int c = warp; c < kNF; c += kNormWarps) {
         const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
-        double s = 0.0, s2 = 0.0;
-        for (int i = lane; i < n; i += 32) {
-            const double v = x[i];
-            s += v;
-            s2 += v * v;
+        const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+        double s = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int i0 = 0; i0 < n; i0 += 2 * kStep) {
+            double a[kRowsPerLane], b[kRowsPerLane];
+            load4(x, i0 + lane * kRowsPerLane, n, vec, a);
+            load4(x, i0 + kStep + lane * kRowsPerLane, n, vec, b);
+#pragma unroll
+            for (int k = 0; k < kRowsPerLane; ++k) {
+                s += a[k];
+                s2 += a[k] * a[k];
+                t1 += b[k];
+                t2 += b[k] * b[k];
+            }
         }
+        s += t1;
+        s2 += t2;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, d);
@@ -56,77 +79,112 @@ k_normalize(const DevOutputs out, const int64_t N, const DevTile* __restrict__ t
         if (lane == 0) {
             tile_tot[(int64_t)id * 2 * kNF + c] = s;
             tile_tot[(int64_t)id * 2 * kNF + kNF + c] = s2;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        atomicExch(flags + id, 1);
-    }
-
-    // ---- totals of the (up to) tiles_back preceding tiles of the same stream, oldest first
-    const int nb = T.index < P.tiles_back ? T.index : P.tiles_back;
-    if (tid < 2 * kNF) {
-        double s = 0.0;
-        for (int j = id - nb; j < id; ++j) {
-            while (ld_flag(flags + j) == 0) { __nanosleep(40); }
             __threadfence();
-            s += __ldcg(tile_tot + (int64_t)j * 2 * kNF + tid);
+            atomicAdd(flags + id, 1);
         }
-        sHead[tid] = s;
     }
-    __syncthreads();
 
-    // ---- pass 2: one warp per feature column; in-tile scans of the current and the lagged tile
+    // ---- pass 2: the window sum slides along the tile:
+    //        sum(t) = [totals of the previous tiles] + sum_{i<=t in tile} (x_i - x_{i-W})
+    //      so one in-tile scan of (x - x_lag, x^2 - x_lag^2) gives every row's window sums.
+    const int nb = T.index < P.tiles_back ? T.index : P.tiles_back;  // preceding tiles inside the window
     const bool has_lag = T.index >= P.tiles_back;
     const int64_t tl0 = (int64_t)T.index * P.tile_rows;  // stream-local index of the tile's first row
+    const double2 invW = __ldg(P.inv_n + P.norm_window);
     for (int c = warp; c < kNF; c += kNormWarps) {
         const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
         const double* __restrict__ xl = x - P.norm_window;
         double* __restrict__ z = out.norm + (int64_t)c * N + T.row;
-        const double H1 = sHead[c], H2 = sHead[kNF + c];
-        double run1 = 0.0, run2 = 0.0, lrun1 = 0.0, lrun2 = 0.0;  // warp-uniform running prefixes
-        for (int i0 = 0; i0 < n; i0 += 32 * kRowsPerLane) {
+        const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((P.norm_window & 1) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+        // first step's loads are in flight while the predecessors' totals are awaited
+        double v[kRowsPerLane], lv[kRowsPerLane];
+        load4(x, lane * kRowsPerLane, n, vec, v);
+        if (has_lag) load4(xl, lane * kRowsPerLane, n, vec, lv);
+        else {
+#pragma unroll
+            for (int k = 0; k < kRowsPerLane; ++k) lv[k] = 0.0;
+        }
+        // totals of the (up to tiles_back) preceding tiles, one lane per predecessor, fixed reduction tree
+        double run1 = 0.0, run2 = 0.0;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+            const int j = id - nb + j0 + lane;
+            double h1 = 0.0, h2 = 0.0;
+            if (j0 + lane < nb) {
+                while (ld_flag(flags + j) < kNF) { __nanosleep(32); }
+                __threadfence();
+                h1 = __ldcg(tile_tot + (int64_t)j * 2 * kNF + c);
+                h2 = __ldcg(tile_tot + (int64_t)j * 2 * kNF + kNF + c);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                h1 += __shfl_xor_sync(0xffffffffu, h1, d);
+                h2 += __shfl_xor_sync(0xffffffffu, h2, d);
+            }
+            run1 += h1;
+            run2 += h2;
+        }
+        for (int i0 = 0; i0 < n; i0 += kStep) {
             const int ib = i0 + lane * kRowsPerLane;
-            double v[kRowsPerLane], p1[kRowsPerLane], p2[kRowsPerLane], q1[kRowsPerLane], q2[kRowsPerLane];
-            double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+            // software pipeline: next step's values are requested before this step's arithmetic
+            double vn[kRowsPerLane], ln[kRowsPerLane];
+            const bool more = i0 + kStep < n;
+            if (more) {
+                load4(x, ib + kStep, n, vec, vn);
+                if (has_lag) load4(xl, ib + kStep, n, vec, ln);
+            }
+            double d1[kRowsPerLane], d2[kRowsPerLane];
+            double a1 = 0.0, a2 = 0.0;
 #pragma unroll
             for (int k = 0; k < kRowsPerLane; ++k) {
-                const bool in_t = ib + k < n;
-                v[k] = in_t ? x[ib + k] : 0.0;
-                const double lv = (in_t && has_lag) ? xl[ib + k] : 0.0;
-                a1 += v[k];
-                a2 += v[k] * v[k];
-                b1 += lv;
-                b2 += lv * lv;
-                p1[k] = a1; p2[k] = a2; q1[k] = b1; q2[k] = b2;
+                d1[k] = v[k] - lv[k];
+                d2[k] = v[k] * v[k] - lv[k] * lv[k];
+                a1 += d1[k];
+                a2 += d2[k];
             }
-            double s1 = a1, s2 = a2, t1 = b1, t2 = b2;
+            double s1 = a1, s2 = a2;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const double u1 = shfl_up_d(s1, d), u2 = shfl_up_d(s2, d), w1 = shfl_up_d(t1, d), w2 = shfl_up_d(t2, d);
-                if (lane >= d) { s1 += u1; s2 += u2; t1 += w1; t2 += w2; }
+                const double u1 = shfl_up_d(s1, d), u2 = shfl_up_d(s2, d);
+                if (lane >= d) { s1 += u1; s2 += u2; }
             }
-            const double e1 = run1 + (s1 - a1), e2 = run2 + (s2 - a2), f1 = lrun1 + (t1 - b1), f2 = lrun2 + (t2 - b2);
+            double e1 = run1 + (s1 - a1), e2 = run2 + (s2 - a2);
+            double zz[kRowsPerLane];
 #pragma unroll
             for (int k = 0; k < kRowsPerLane; ++k) {
-                if (ib + k < n) {
-                    const int64_t tl = tl0 + ib + k;
-                    const int64_t nwin = tl + 1 < P.norm_window ? tl + 1 : P.norm_window;  // window.size(), :71
-                    const double sum = (H1 + (e1 + p1[k])) - (f1 + q1[k]);
-                    const double sum2 = (H2 + (e2 + p2[k])) - (f2 + q2[k]);
-                    const double dn = (double)nwin;
-                    const double mean = sum / dn;                                   // :62
-                    const double variance = (sum2 / dn) - (mean * mean);            // :63
-                    const double stddev = (variance > 0.0) ? sqrt(variance) : 1.0;  // :67
-                    z[ib + k] = (v[k] - mean) / stddev;                             // :68
-                    if (c == 0 && out.counts) out.counts[(int64_t)MRP_C_NORM_N * N + T.row + ib + k] = (int32_t)nwin;
-                }
+                e1 += d1[k];
+                e2 += d2[k];
+                const int64_t tl = tl0 + ib + k;
+                const bool fullw = tl + 1 >= P.norm_window;
+                const int nwin = fullw ? P.norm_window : (int)(tl + 1);  // window.size(), feature_normalizer.cpp:71
+                // sum / n as sum * (1/n) with 1/n in double-double (host table): rounds like the division
+                const double2 inv = (fullw || ib + k >= n) ? invW : __ldg(P.inv_n + nwin);
+                const double m0 = e1 * inv.x;
+                const double mean = m0 + (fma(e1, inv.x, -m0) + e1 * inv.y);      // :62
+                const double q0 = e2 * inv.x;
+                const double ex2 = q0 + (fma(e2, inv.x, -q0) + e2 * inv.y);
+                const double variance = ex2 - (mean * mean);                    // :63
+                const double rstd = (variance > 0.0) ? rsqrt(variance) : 1.0;   // :67 — 1/sqrt, then multiply
+                zz[k] = (v[k] - mean) * rstd;                                   // :68
+                if (c == 0 && out.counts && ib + k < n) out.counts[(int64_t)MRP_C_NORM_N * N + T.row + ib + k] = nwin;
+            }
+            if (vec && ib + kRowsPerLane <= n) {
+                *reinterpret_cast<double2*>(z + ib) = make_double2(zz[0], zz[1]);
+                *reinterpret_cast<double2*>(z + ib + 2) = make_double2(zz[2], zz[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRowsPerLane; ++k)
+                    if (ib + k < n) z[ib + k] = zz[k];
             }
             run1 += __shfl_sync(0xffffffffu, s1, 31);
             run2 += __shfl_sync(0xffffffffu, s2, 31);
-            lrun1 += __shfl_sync(0xffffffffu, t1, 31);
-            lrun2 += __shfl_sync(0xffffffffu, t2, 31);
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < kRowsPerLane; ++k) {
+                    v[k] = vn[k];
+                    lv[k] = has_lag ? ln[k] : 0.0;
+                }
+            }
         }
     }
 }

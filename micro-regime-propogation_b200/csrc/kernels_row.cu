@@ -46,6 +46,8 @@ k_trades(const DevInputs in, const DevOutputs out, const DevSegment* __restrict_
 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t cs = base + c * kChunk;
+        // cursor of the first row this thread may finalise: requested now, consumed after the scan
+        int64_t e_pref = r_next + tid < rb ? (int64_t)jcur[r_next + tid] : (int64_t)0x7fffffffffffffll;
         int D[kPerThread];
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i) {
@@ -113,9 +115,9 @@ k_trades(const DevInputs in, const DevOutputs out, const DevSegment* __restrict_
             return *reinterpret_cast<const TrdEntry*>(ring + trd_byte(slot));
         };
         const int64_t ce = (c + 1 == nchunks) ? (int64_t)0x7fffffffffffll : cs + kChunk;
-        while (true) {
+        for (bool first = true;; first = false) {
             const int64_t r = r_next + tid;
-            const int64_t je = r < rb ? (int64_t)jcur[r] : (int64_t)0x7fffffffffffffll;
+            const int64_t je = first ? e_pref : (r < rb ? (int64_t)jcur[r] : (int64_t)0x7fffffffffffffll);
             const bool q = je <= ce;
             if (q) {
                 int64_t jb = je - P.dir_window;
@@ -134,11 +136,8 @@ k_trades(const DevInputs in, const DevOutputs out, const DevSegment* __restrict_
                 const double rr = nd > 1 ? (double)rev / (double)nd : 0.0;  // feature_processor.cpp:239
                 const double ab = (double)isum / (double)nd;                // :246 — 0/0 = NaN with no trades
                 const int tot = pos + neg;                                  // :261-269
-                const double p_pos = tot > 0 ? (double)pos / tot : 0.0;
-                const double p_neg = tot > 0 ? (double)neg / tot : 0.0;
-                double ent = 0.0;
-                ent = entropy_term(ent, p_pos);
-                ent = entropy_term(ent, p_neg);
+                // binary entropy of (pos, neg) = (T log2 T - pos log2 pos - neg log2 neg) / T, c log2 c tabulated
+                const double ent = tot > 0 ? ((__ldg(P.clog2c + tot) - __ldg(P.clog2c + pos)) - __ldg(P.clog2c + neg)) / (double)tot : 0.0;
                 out.raw[(int64_t)MRP_F_REVERSAL_RATE * in.n_rows + r] = rr;
                 out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * in.n_rows + r] = ab;
                 out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * in.n_rows + r] = ent;
@@ -165,6 +164,29 @@ k_trades(const DevInputs in, const DevOutputs out, const DevSegment* __restrict_
 // A segment that starts mid-stream first walks `ema_warm_rows` halo rows (only what feeds the EMAs
 // and the lag-21 midprice); 0.9^halo is below 1e-17, far under the fp64 noise of the features.
 // ------------------------------------------------------------------------------------------------
+// log(p / m) for a price p near the midprice m: the reference takes |log m - log p| of two rounded logs
+// (feature_processor.cpp:166,171), whose rounding noise (1 ulp of log m ~ 1.8e-15) is ~3e-11 of a one-tick
+// distance.  The Taylor series of log1p((p-m)/m) gives the same quantity to ~3e-16 relative for the cost of a
+// dozen fused multiply-adds instead of a full log; beyond |u| = 2^-6 it falls back to the two-log form.
+__device__ __forceinline__ double log_ratio(double p, double m, double inv_m, double log_m) {
+    const double u = (p - m) * inv_m;
+    if (fabs(u) <= 0.015625) {
+        double q = 1.0 / 11.0;
+        q = fma(q, u, -1.0 / 10.0);
+        q = fma(q, u, 1.0 / 9.0);
+        q = fma(q, u, -1.0 / 8.0);
+        q = fma(q, u, 1.0 / 7.0);
+        q = fma(q, u, -1.0 / 6.0);
+        q = fma(q, u, 1.0 / 5.0);
+        q = fma(q, u, -1.0 / 4.0);
+        q = fma(q, u, 1.0 / 3.0);
+        q = fma(q, u, -0.5);
+        q = fma(q, u, 1.0);
+        return q * u;
+    }
+    return log(p) - log_m;
+}
+
 __device__ __forceinline__ double ema_scan(double b, const double* __restrict__ pw, double carry_in, double* sWarp,
                                            int lane, int warp, double& carry_out) {
     double v = b;
@@ -185,6 +207,8 @@ __device__ __forceinline__ double ema_scan(double b, const double* __restrict__ 
     carry_out = co;
     return __ldg(pw + lane + 1) * cw + v;
 }
+
+constexpr int kLevelGroup = 5;
 
 __global__ void __launch_bounds__(kThreads, 2)
 k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
@@ -213,62 +237,96 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         const bool hasprev = act && t > sr0;    // a previous snapshot exists in this stream
         const int64_t tc = act ? t : rb - 1;    // clamp loads of idle lanes
 
-        const double bb = in.bid_px[tc], ba = in.ask_px[tc];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
-        const double midp = (ba + bb) / 2;                    // feature_processor.cpp:34,161
-        const double log_mid = log(midp);
+        // row scalars first: one batch of independent loads
+        const unsigned long long ts = in.ts[tc];
+        const double buy = in.buy[tc], sell = in.sell[tc];
+        const int adds = in.adds[tc];
+        unsigned long long pts = (lane == 0 && hasprev) ? in.ts[tc - 1] : 0ull;
 
+        double bb = 0.0, ba = 0.0, midp = 0.0, log_mid = 0.0, inv_mid = 0.0;
         double raw_ofi = 0.0, liq_b = 0.0, liq_a = 0.0;
         double bid_depth = 0.0, ask_depth = 0.0, bid_lw = 0.0, ask_lw = 0.0;
-        double log_bb = 0.0, log_ba = 0.0;
         double p0b = 0, p1b = 0, p0a = 0, p1a = 0;
         int s0b = 0, s1b = 0, s0a = 0, s1a = 0;
-        for (int i = 0; i < L; ++i) {
-            const int64_t o = (int64_t)i * N + tc;
-            const double bp = in.bid_px[o], ap = in.ask_px[o];
-            const int bs = in.bid_sz[o], as = in.ask_sz[o];
-            int pbs = __shfl_up_sync(0xffffffffu, bs, 1), pas = __shfl_up_sync(0xffffffffu, as, 1);
-            if (lane == 0) {
-                pbs = hasprev ? in.bid_sz[o - 1] : 0;  // first snapshot compares with an empty book (order_book.cpp:115,168)
-                pas = hasprev ? in.ask_sz[o - 1] : 0;
+        for (int i0 = 0; i0 < L; i0 += kLevelGroup) {
+            // all loads of a group of levels are issued before any is used (the level loop is otherwise
+            // a chain of load -> use stalls: 55 % of the kernel's cycles in the first profile)
+            double bp[kLevelGroup], ap[kLevelGroup];
+            int bs[kLevelGroup], as[kLevelGroup], pbs[kLevelGroup], pas[kLevelGroup];
+#pragma unroll
+            for (int g = 0; g < kLevelGroup; ++g) {
+                const bool lv = i0 + g < L;
+                const int64_t o = (int64_t)(lv ? i0 + g : 0) * N + tc;
+                bp[g] = lv ? in.bid_px[o] : 0.0;
+                ap[g] = lv ? in.ask_px[o] : 0.0;
+                bs[g] = lv ? in.bid_sz[o] : 0;
+                as[g] = lv ? in.ask_sz[o] : 0;
+                // lane 0 fetches the previous row itself; the other lanes get it from their neighbour
+                pbs[g] = (lane == 0 && hasprev && lv) ? in.bid_sz[o - 1] : 0;
+                pas[g] = (lane == 0 && hasprev && lv) ? in.ask_sz[o - 1] : 0;
             }
-            if (!hasprev) { pbs = 0; pas = 0; }
-            const int bd = (bs > pbs) - (bs < pbs);    // order_book.cpp:208-239
-            const int ad = (as > pas) - (as < pas);
-            if (full && out.bdir) { out.bdir[o] = (int8_t)bd; out.adir[o] = (int8_t)ad; }
-            const double w = __ldg(P.ofi_weight + i);  // exp(-i*0.5), feature_processor.cpp:121
-            const double bid_contrib = (double)(bd * bs) * w;
-            const double ask_contrib = (double)(ad * as) * w;
-            raw_ofi += bid_contrib - ask_contrib;      // :125
-            if (i < P.stress_levels) {                 // :282-299
-                if (bp > 0.0 && (double)bs >= P.stress_min_size) liq_b += exp(-(bb - bp) * P.stress_distance_decay) * bs;
-                if (ap > 0.0 && (double)as >= P.stress_min_size) liq_a += exp(-(ap - ba) * P.stress_distance_decay) * as;
+            if (i0 == 0) {
+                bb = bp[0];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
+                ba = ap[0];
+                midp = (ba + bb) / 2;  // feature_processor.cpp:34,161
+                log_mid = log(midp);
+                inv_mid = 1.0 / midp;
             }
-            if (i == 0) { p0b = bp; p0a = ap; s0b = bs; s0a = as; }
-            if (i == 1) { p1b = bp; p1a = ap; s1b = bs; s1a = as; }
-            if (full) {                                // :164-175, :189-200
-                if (i == 0) { log_bb = log(bp); log_ba = log(ap); }
-                if (bp > 0) {
-                    const double dist = fabs(log_mid - (i == 0 ? log_bb : log(bp)));
-                    bid_lw += dist * bs;
-                    bid_depth += bs;
-                }
-                if (ap > 0) {
-                    const double dist = fabs((i == 0 ? log_ba : log(ap)) - log_mid);
-                    ask_lw += dist * as;
-                    ask_depth += as;
+#pragma unroll
+            for (int g = 0; g < kLevelGroup; ++g) {
+                const int i = i0 + g;
+                const int nbs = __shfl_up_sync(0xffffffffu, bs[g], 1), nas = __shfl_up_sync(0xffffffffu, as[g], 1);
+                if (i < L) {
+                    // first snapshot compares with an empty book (order_book.cpp:115,168)
+                    const int qb = hasprev ? (lane == 0 ? pbs[g] : nbs) : 0;
+                    const int qa = hasprev ? (lane == 0 ? pas[g] : nas) : 0;
+                    const int bd = (bs[g] > qb) - (bs[g] < qb);  // order_book.cpp:208-239
+                    const int ad = (as[g] > qa) - (as[g] < qa);
+                    if (full && out.bdir) {
+                        const int64_t o = (int64_t)i * N + tc;
+                        out.bdir[o] = (int8_t)bd;
+                        out.adir[o] = (int8_t)ad;
+                    }
+                    const double w = __ldg(P.ofi_weight + i);  // exp(-i*0.5), feature_processor.cpp:121
+                    const double bid_contrib = (double)(bd * bs[g]) * w;
+                    const double ask_contrib = (double)(ad * as[g]) * w;
+                    raw_ofi += bid_contrib - ask_contrib;      // :125
+                    if (i < P.stress_levels) {                 // :282-299
+                        // exp(-dist*decay): level 0 has dist == 0 exactly (weight 1); on a contiguous book both
+                        // sides share the argument, so one exp serves both
+                        const double xb = -(bb - bp[g]) * P.stress_distance_decay, xa = -(ap[g] - ba) * P.stress_distance_decay;
+                        const double eb = (i == 0) ? 1.0 : exp(xb);
+                        const double ea = (i == 0) ? 1.0 : ((xa == xb) ? eb : exp(xa));
+                        if (bp[g] > 0.0 && (double)bs[g] >= P.stress_min_size) liq_b += eb * bs[g];
+                        if (ap[g] > 0.0 && (double)as[g] >= P.stress_min_size) liq_a += ea * as[g];
+                    }
+                    if (i == 0) { p0b = bp[g]; p0a = ap[g]; s0b = bs[g]; s0a = as[g]; }
+                    if (i == 1) { p1b = bp[g]; p1a = ap[g]; s1b = bs[g]; s1a = as[g]; }
+                    if (full) {                                // :164-175, :189-200
+                        if (bp[g] > 0) {
+                            bid_lw += fabs(log_ratio(bp[g], midp, inv_mid, log_mid)) * bs[g];  // |log mid - log bp|
+                            bid_depth += bs[g];
+                        }
+                        if (ap[g] > 0) {
+                            ask_lw += fabs(log_ratio(ap[g], midp, inv_mid, log_mid)) * as[g];  // |log ap - log mid|
+                            ask_depth += as[g];
+                        }
+                    }
                 }
             }
         }
+        const double log_bb = log(bb), log_ba = log(ba);
         const double liq = liq_b + liq_a;  // :301
 
         // neighbours: previous row's liquidity, timestamp; lag-21 midprice through shared memory
         sLM[buf][tid] = log_mid;
         sMid[buf][tid] = midp;
         if (lane == 31) sWarpLiq[warp] = liq;
-        const unsigned long long ts = in.ts[tc];
-        unsigned long long pts = __shfl_up_sync(0xffffffffu, ts, 1);
-        if (lane == 0) pts = hasprev ? in.ts[tc - 1] : 0ull;
-        if (!hasprev) pts = 0ull;
+        {
+            const unsigned long long nts = __shfl_up_sync(0xffffffffu, ts, 1);
+            if (lane != 0) pts = nts;
+            if (!hasprev) pts = 0ull;
+        }
         __syncthreads();
         double pliq = shfl_up_d(liq, 1);
         if (lane == 0) pliq = warp == 0 ? sCarLiq : sWarpLiq[warp - 1];
@@ -281,7 +339,6 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
             old_lm = j >= 0 ? sLM[buf][j] : sLM[buf ^ 1][kThreads + j];
         }
 
-        const double buy = in.buy[tc], sell = in.sell[tc];
         const double total_volume = buy + sell;                                               // :129
         const double x_ofi = (total_volume > P.ofi_min_total_vol) ? raw_ofi / total_volume : 0.0;  // :130
         double raw_stress = 0.0;                                                              // :304-308
@@ -304,7 +361,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
             if (pts > 0ull) {
                 const unsigned long long delta_ns = ts - pts;
                 const double seconds = (double)delta_ns * 1e-9;
-                rate = (seconds > 0.0) ? (double)in.adds[tc] / seconds : 0.0;
+                rate = (seconds > 0.0) ? (double)adds / seconds : 0.0;
             }
             const double depth = bid_depth + ask_depth;
             const double bid_slope = (bid_depth > 0.0) ? bid_lw / bid_depth : 0.0;  // :202-204

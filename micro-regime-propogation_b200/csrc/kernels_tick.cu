@@ -76,6 +76,8 @@ k_tick_returns(const DevInputs in, const DevOutputs out, const DevSegment* __res
 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t cs = base + c * kChunk;
+        // cursor of the first row this thread may finalise: requested now, consumed after the scan
+        int64_t e_pref = r_next + tid < rb ? (int64_t)kcur[r_next + tid] : (int64_t)0x7fffffffffffffll;
         double M[kPerThread], lm[kPerThread];
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i) M[i] = Mn[i];
@@ -213,9 +215,9 @@ k_tick_returns(const DevInputs in, const DevOutputs out, const DevSegment* __res
             return p;
         };
         const int64_t ce = (c + 1 == nchunks) ? (int64_t)0x7fffffffffffll : cs + kChunk;
-        while (true) {
+        for (bool first = true;; first = false) {
             const int64_t r = r_next + tid;
-            const int64_t e = r < rb ? (int64_t)kcur[r] : (int64_t)0x7fffffffffffffll;
+            const int64_t e = first ? e_pref : (r < rb ? (int64_t)kcur[r] : (int64_t)0x7fffffffffffffll);
             const bool q = e <= ce;
             if (q) {
                 double rv = 0.0, ewm = 0.0, dv = 0.0, tent = 0.0;
@@ -231,7 +233,7 @@ k_tick_returns(const DevInputs in, const DevOutputs out, const DevSegment* __res
                     const double sumU = H.pu - S.pu, sumD = H.pd - S.pd;
                     if (n_valid > 0) {
                         const double tot = sumU + sumD;
-                        rv = tot / (double)n_valid;  // feature_processor.cpp:61
+                        rv = tot * __ldg(P.inv_cnt + n_valid);  // feature_processor.cpp:61 (tabulated 1/count)
                         // EW variance restarted at the window's first valid return f (:64-79).  With the global
                         // recurrence G (same decay, same inputs) the restarted state obeys
                         //   w_k - G_k = decay^(#valid in (f,k]) * (w_f - G_f),  w_f = r_f^2,
@@ -247,8 +249,8 @@ k_tick_returns(const DevInputs in, const DevOutputs out, const DevSegment* __res
                         }
                         ewm = sqrt(w);
                         const uint32_t n_dn = n_valid - n_up;
-                        const double au = n_up > 0 ? sumU / (double)n_up : 0.0;   // :95-98
-                        const double ad = n_dn > 0 ? sumD / (double)n_dn : 0.0;
+                        const double au = sumU * __ldg(P.inv_cnt + n_up);   // :95-98 (inv_cnt[0] = 0 covers the empty side)
+                        const double ad = sumD * __ldg(P.inv_cnt + n_dn);
                         const double diff = au - ad;
                         dv = sqrt(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
                         if (nbad) { rv = ewm = dv = __longlong_as_double(0x7ff8000000000000ll); }
@@ -264,10 +266,10 @@ k_tick_returns(const DevInputs in, const DevOutputs out, const DevSegment* __res
                     }
                     t_tot = (uint32_t)(e - d0);
                     const uint32_t zero = t_tot - t_up - t_dn;
-                    const double total = (double)t_tot;  // feature_processor.cpp:222-229
-                    tent = entropy_term(tent, t_up / total);
-                    tent = entropy_term(tent, t_dn / total);
-                    tent = entropy_term(tent, zero / total);
+                    // feature_processor.cpp:222-229:  -sum p_i log2 p_i with p_i = c_i/T
+                    //   = (T log2 T - sum c_i log2 c_i) / T, with c log2 c tabulated by the host (exact 0 for one bucket)
+                    tent = ((__ldg(P.clog2c + t_tot) - __ldg(P.clog2c + t_up)) - __ldg(P.clog2c + t_dn) - __ldg(P.clog2c + zero)) /
+                           (double)t_tot;
                 }
                 out.raw[(int64_t)MRP_F_EWM_VOLATILITY * in.n_rows + r] = ewm;
                 out.raw[(int64_t)MRP_F_REALIZED_VARIANCE * in.n_rows + r] = rv;
@@ -337,6 +339,8 @@ k_tick_spread(const DevInputs in, const DevOutputs out, const DevSegment* __rest
     }
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t cs = base + c * kChunk;
+        // cursor of the first row this thread may finalise: requested now, consumed after the scan
+        int64_t e_pref = r_next + tid < rb ? (int64_t)kcur[r_next + tid] : (int64_t)0x7fffffffffffffll;
         double l1[kPerThread], l2[kPerThread];
         uint32_t lb[kPerThread];
         double a1 = 0.0, a2 = 0.0;
@@ -405,9 +409,9 @@ k_tick_spread(const DevInputs in, const DevOutputs out, const DevSegment* __rest
             return *reinterpret_cast<const SprEntry*>(ring + spr_byte(slot));
         };
         const int64_t ce = (c + 1 == nchunks) ? (int64_t)0x7fffffffffffll : cs + kChunk;
-        while (true) {
+        for (bool first = true;; first = false) {
             const int64_t r = r_next + tid;
-            const int64_t e = r < rb ? (int64_t)kcur[r] : (int64_t)0x7fffffffffffffll;
+            const int64_t e = first ? e_pref : (r < rb ? (int64_t)kcur[r] : (int64_t)0x7fffffffffffffll);
             const bool q = e <= ce;
             if (q) {
                 double sv = 0.0;

@@ -71,6 +71,9 @@ struct DevParams {
     const double* ewm_pow;      // [mid_window+1]  decay^n
     const double* ofi_pow;      // [257]           ofi_decay^n
     const double* stress_pow;   // [257]           stress_decay^n
+    const double2* inv_n;       // [norm_window+1] 1/n as (hi, lo) double-double; [0] unused
+    const double* clog2c;       // [max(dir_window, mid_window)+2]  c*log2(c), [0] = 0
+    const double* inv_cnt;      // [mid_window+2]  1/n, [0] = 0
     // ring geometry (entries), computed by the host
     int32_t ret_ring, spr_ring, trd_ring;
     int32_t ema_warm_rows;      // halo rows that warm the two row-axis EMAs

@@ -27,6 +27,8 @@ def _check(batch, params=None, z_tol=1e-9, mode="upload"):
     assert nan_pattern_equal(got["raw"], ref["raw"])
     re = raw_errors(got["raw"], ref["raw"])
     assert (re <= 1.0).all(), {mrp_b200.FEATURES[i]: re[i] for i in np.nonzero(re > 1.0)[0]}
+    exact_cols = [mrp_b200.FEATURES[c] for c in range(19) if np.array_equal(got["raw"][c], ref["raw"][c], equal_nan=True)]
+    print("raw: %d/19 columns bit-exact; worst error/tolerance %.3g (%s)" % (len(exact_cols), re.max(), mrp_b200.FEATURES[int(re.argmax())]))
     assert nan_pattern_equal(got["norm"], ref["norm"])
     # z-scores: conditioning-aware, against the exactly-summed definition and against the reference itself
     wa, wb, drift, frac = norm_check(got["norm"], ref["raw"], ref["norm"], hv.arrays["row_offsets"], p.norm_window, z_tol)
