@@ -131,3 +131,33 @@ def norm_check(got_norm, ref_raw, ref_norm, row_offsets, window, z_tol=NORM_TOL)
     db = np.where(ok, np.abs(got_norm - ref_norm) / (tol + 1.5 * dref), 0.0)
     drift = np.where(ok, dref / mag, 0.0)
     return da.max(axis=1), db.max(axis=1), drift.max(axis=1), ok.mean()
+
+
+# ---- golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the compiled reference)
+def golden_cases():
+    import glob
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(here, "*.npz")))
+
+
+def load_golden(name):
+    """Returns (spec, host batch, fixture dict).  Regenerates the inputs from the stored spec and checks
+    their digest, so a drifting generator cannot silently invalidate the fixture."""
+    import hashlib
+    import json
+    import os
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(here, name + ".npz"))
+    spec = synth.SynthSpec(**json.loads(str(z["spec"])))
+    batch = synth.to_numpy(synth.make_batch([spec]))
+    h = hashlib.sha256()
+    for k in sorted(batch):
+        if k == "trade_size":
+            continue
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(batch[k]).tobytes())
+    assert h.hexdigest() == str(z["digest"]), "synthetic generator no longer reproduces the fixture inputs"
+    return spec, batch, {k: z[k] for k in ("rows", "raw", "norm", "bid_dir", "ask_dir")}
