@@ -264,11 +264,12 @@ def main():
     bytes_row = algorithmic_bytes_per_row(LEVELS, m_eff, q)
     # algorithmic bytes per kernel: what each kernel must read + write once
     kb = {
-        "tick_returns": rows * (8 * m_eff + 4 + 4 * 8),          # mids, tick cursor, 4 feature columns
-        "tick_spread": rows * (8 * m_eff + 4 + 8),               # spreads, cursor (re-read), 1 column
-        "trades": rows * (q + 4 + 3 * 8),                        # trade dirs, trade cursor, 3 columns
-        "book": rows * (8 + 24 * LEVELS + 16 + 4 + 11 * 8),      # ts, prices, sizes, buy/sell, adds, 11 columns
-        "normalize": rows * (2 * 19 * 8),                        # raw read once, z written once
+        # mids + spreads + trade dirs + both cursors, 8 feature columns
+        "windows": rows * (16 * m_eff + q + 8 + 8 * 8),
+        # ts, prices, sizes, buy/sell, adds, 11 feature columns
+        "book": rows * (8 + 24 * LEVELS + 16 + 4 + 11 * 8),
+        # raw read once, z written once
+        "normalize": rows * (2 * 19 * 8),
     }
     dom = max(kt, key=kt.get)
     whole_gbs = rows * bytes_row / (ms_per_step * 1e-3) / 1e9

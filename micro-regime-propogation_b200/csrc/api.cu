@@ -13,15 +13,11 @@
 #include "mrp_device.cuh"
 
 namespace mrp {
-cudaError_t launch_tick_returns(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
-cudaError_t launch_tick_spread(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
-cudaError_t launch_trades(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_windows(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
 cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
 cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, const DevParams&, cudaStream_t);
 cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
-size_t ret_ring_bytes(int);
-size_t spr_ring_bytes(int);
-size_t trd_ring_bytes(int);
+size_t win_smem_bytes(int);
 }  // namespace mrp
 
 using namespace mrp;
@@ -44,8 +40,8 @@ int cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
-constexpr int kNumKernels = 5;
-const char* kKernelNames[kNumKernels] = {"tick_returns", "tick_spread", "trades", "book", "normalize"};
+constexpr int kNumKernels = 3;
+const char* kKernelNames[kNumKernels] = {"windows", "book", "normalize"};
 
 struct DevBuf {
     void* p = nullptr;
@@ -136,6 +132,7 @@ int setup_params(mrp_fg_ctx* c) {
     d.emit_counts = p.emit_counts;
     d.ewm_alpha = 2.0 / (p.ewm_span + 1);  // feature_processor.cpp:64
     d.ewm_decay = 1 - d.ewm_alpha;         // :74
+    d.inv_spread_divisor = 1.0 / p.spread_divisor;
     d.ofi_alpha = p.ofi_alpha;
     d.ofi_decay = 1.0 - p.ofi_alpha;       // :133
     d.ofi_min_total_vol = p.ofi_min_total_vol;
@@ -144,15 +141,22 @@ int setup_params(mrp_fg_ctx* c) {
     d.stress_min_size = p.stress_min_size;
     d.stress_distance_decay = p.stress_distance_decay;
 
-    auto round4 = [](int x) { return (x + 3) & ~3; };
+    // window kernel geometry: the ring holds one window plus the new ticks of one chunk
+    if (p.mid_window > 32767 || p.dir_window > 32767) return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window must be <= 32767 (16-bit window counters)");
     const int wmax = std::max(p.mid_window, p.dir_window + 1);
-    d.ret_ring = round4(wmax + kChunk + 4);
-    d.spr_ring = round4(p.mid_window + kChunk + 4);
-    d.trd_ring = round4(p.dir_window + kChunk + 4);
-    const size_t smem_max = 227 * 1024 - 2048;
-    if (ret_ring_bytes(d.ret_ring) > smem_max || spr_ring_bytes(d.spr_ring) > smem_max || trd_ring_bytes(d.trd_ring) > smem_max ||
-        (d.ret_ring + kChunk - 1) / kChunk + 1 > kMaxRingChunks)
-        return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window too large for the on-chip window ring (limit about 5000 ticks)");
+    int ring = 4096;
+    while (ring < 2 * wmax + 16) ring <<= 1;
+    if (ring > 8192)
+        return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window too large for the on-chip window ring (limit about 4000 ticks)");
+    d.win_ring = ring;
+    d.win_span_max = ring - wmax - 8;
+    // the exponentially weighted sum is carried rescaled by decay^-(ticks into the chunk): keep that factor below e^200
+    if (!(d.ewm_decay > 0.0 && d.ewm_decay < 1.0)) return fail(MRP_FG_ERR_INVALID, "ewm_span must be >= 2 (decay = 1 - 2/(span+1) in (0,1))");
+    {
+        const double lim = 200.0 / -std::log(d.ewm_decay);
+        if (lim < (double)d.win_span_max) d.win_span_max = (int)lim;
+        if (d.win_span_max < wmax + 4) return fail(MRP_FG_ERR_INVALID, "ewm_span too small for this mid_window (the rescaled EW sum would overflow)");
+    }
 
     // EMA halo: decay^rows < 1e-17 for the slower of the two EMAs, rounded up to whole chunks; also covers the lag
     const double slow = std::max(d.ofi_decay, d.stress_decay);
@@ -171,7 +175,10 @@ int setup_params(mrp_fg_ctx* c) {
     const size_t o_w = 0;
     for (int i = 0; i < p.depth_levels; ++i) tab.push_back(std::exp(-i * p.ofi_depth_decay));  // feature_processor.cpp:121
     const size_t o_e = tab.size();
-    for (int n = 0; n <= p.mid_window; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
+    for (int n = 0; n <= d.win_ring; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
+    const size_t o_ei = tab.size();
+    for (int n = 0; n <= d.win_ring; ++n)
+        tab.push_back(n <= d.win_span_max + 1 ? (double)powl((long double)d.ewm_decay, -(long double)n) : 0.0);
     const size_t o_o = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
     const size_t o_s = tab.size();
@@ -188,13 +195,14 @@ int setup_params(mrp_fg_ctx* c) {
     const int hmax = std::max(p.dir_window, p.mid_window) + 1;
     for (int n = 0; n <= hmax; ++n) tab.push_back(n > 0 ? (double)((long double)n * log2l((long double)n)) : 0.0);
     const size_t o_c = tab.size();
-    for (int n = 0; n <= p.mid_window + 1; ++n) tab.push_back(n > 0 ? 1.0 / (double)n : 0.0);
+    for (int n = 0; n <= hmax; ++n) tab.push_back(n > 0 ? 1.0 / (double)n : 0.0);
     int rc = c->b_tables.ensure(tab.size() * sizeof(double));
     if (rc) return rc;
     CU(cudaMemcpy(c->b_tables.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     const double* t = static_cast<const double*>(c->b_tables.p);
     d.ofi_weight = t + o_w;
     d.ewm_pow = t + o_e;
+    d.ewm_ipow = t + o_ei;
     d.ofi_pow = t + o_o;
     d.stress_pow = t + o_s;
     d.inv_n = reinterpret_cast<const double2*>(t + o_i);
@@ -472,14 +480,10 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
         c->ev_made = true;
     }
     if (tm) CU(cudaEventRecord(c->ev[0], st));
-    CU(launch_tick_returns(c->in, c->out, segs, c->nseg, c->dp, st));
+    CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, st));
     if (tm) CU(cudaEventRecord(c->ev[1], st));
-    CU(launch_tick_spread(c->in, c->out, segs, c->nseg, c->dp, st));
-    if (tm) CU(cudaEventRecord(c->ev[2], st));
-    CU(launch_trades(c->in, c->out, segs, c->nseg, c->dp, st));
-    if (tm) CU(cudaEventRecord(c->ev[3], st));
     CU(launch_book(c->in, c->out, segs, c->nseg, c->dp, st));
-    if (tm) CU(cudaEventRecord(c->ev[4], st));
+    if (tm) CU(cudaEventRecord(c->ev[2], st));
     CU(launch_normalize(c->out, c->n_rows, static_cast<const DevTile*>(c->b_tiles.p), c->ntiles,
                         static_cast<double*>(c->b_tile_tot.p), static_cast<int*>(c->b_flags.p), c->dp, st));
     c->launches += kNumKernels;
@@ -488,7 +492,7 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
         c->launches += 1;
     }
     if (tm) {
-        CU(cudaEventRecord(c->ev[5], st));
+        CU(cudaEventRecord(c->ev[kNumKernels], st));
         c->have_times = true;
     }
     return MRP_FG_OK;

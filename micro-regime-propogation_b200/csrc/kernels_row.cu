@@ -1,162 +1,11 @@
-// kernels_row.cu — trade-axis pass and snapshot-axis (book) pass.
+// kernels_row.cu — snapshot-axis (book) pass.
 //
-//   k_trades : reversal_rate, aggressor_bias, shannon_entropy
-//              (ref: feature_processor.cpp:231-247 and :254-269 over rolling_trade_directions, feature_engine.cpp:88-93)
 //   k_book   : midprice, log_spread, log_return, ofi, signed_volume_pressure, order_arrival_rate, depth_imbalance,
 //              market_depth, lob_slope, price_gap, liquidity_stress, and the int8 depth-change directions
 //              (ref: feature_processor.cpp:32-43, 111-153, 157-212, 271-317; order_book.cpp:208-239)
 #include "mrp_device.cuh"
 
 namespace mrp {
-
-// ------------------------------------------------------------------------------------------------
-// trade pass: integer prefix counts in a ring, same skeleton as the tick passes
-// ------------------------------------------------------------------------------------------------
-struct __align__(16) TrdEntry {
-    uint32_t pos, neg, rev;  // running counts: dir > 0, dir < 0, reversal pairs (j-1, j)
-    int32_t sum;             // running sum of directions
-};
-__device__ __forceinline__ unsigned trd_byte(int slot) { return (unsigned)slot * 16u + ((unsigned)slot >> 2) * 16u; }
-
-__global__ void __launch_bounds__(kThreads, 4)
-k_trades(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
-    extern __shared__ __align__(16) unsigned char ring[];
-    __shared__ int sWarpD[kWarps];
-    __shared__ int sCarD;
-    __shared__ uint32_t sPos[kWarps], sNeg[kWarps], sRev[kWarps];
-    __shared__ int32_t sSum[kWarps];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DevSegment sg = segs[blockIdx.x];
-    const int64_t ra = sg.row_begin, rb = sg.row_end;
-    const int8_t* __restrict__ tdir = in.tdir + sg.trade0;
-    const uint32_t* __restrict__ jcur = in.jcur;
-    const int RING = P.trd_ring;
-    const int64_t jend = jcur[rb - 1];
-    int64_t base = (int64_t)jcur[ra] - P.dir_window - 2;
-    if (base < 0) base = 0;
-    int64_t nchunks = (jend - base + kChunk - 1) / kChunk;
-    if (nchunks < 1) nchunks = 1;
-
-    uint32_t cPos = 0, cNeg = 0, cRev = 0;
-    int32_t cSum = 0;
-    if (tid == 0) sCarD = base > 0 ? (int)tdir[base - 1] : 0;
-    int64_t r_next = ra;
-    int cs_slot = 0;
-
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t cs = base + c * kChunk;
-        // cursor of the first row this thread may finalise: requested now, consumed after the scan
-        int64_t e_pref = r_next + tid < rb ? (int64_t)jcur[r_next + tid] : (int64_t)0x7fffffffffffffll;
-        int D[kPerThread];
-#pragma unroll
-        for (int i = 0; i < kPerThread; ++i) {
-            int64_t jj = cs + tid * kPerThread + i;
-            D[i] = jj < jend ? (int)tdir[jj] : 0;
-        }
-        if (lane == 31) sWarpD[warp] = D[kPerThread - 1];
-        __syncthreads();
-        int Dp = __shfl_up_sync(0xffffffffu, D[kPerThread - 1], 1);
-        if (lane == 0) Dp = warp == 0 ? sCarD : sWarpD[warp - 1];
-
-        uint32_t lp[kPerThread], ln[kPerThread], lr[kPerThread];
-        int32_t ls[kPerThread];
-        uint32_t ap = 0, an = 0, ar = 0;
-        int32_t as = 0;
-#pragma unroll
-        for (int i = 0; i < kPerThread; ++i) {
-            const int64_t jj = cs + tid * kPerThread + i;
-            const int d = D[i];
-            ap += d > 0;
-            an += d < 0;
-            ar += (jj > 0 && d != 0 && d == -Dp) ? 1u : 0u;  // feature_processor.cpp:235
-            as += d;
-            lp[i] = ap; ln[i] = an; lr[i] = ar; ls[i] = as;
-            Dp = d;
-        }
-        uint32_t ip = ap, inn = an, ir = ar;
-        int32_t is = as;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t tp = __shfl_up_sync(0xffffffffu, ip, d), tn = __shfl_up_sync(0xffffffffu, inn, d),
-                           tr = __shfl_up_sync(0xffffffffu, ir, d);
-            const int32_t ts = __shfl_up_sync(0xffffffffu, is, d);
-            if (lane >= d) { ip += tp; inn += tn; ir += tr; is += ts; }
-        }
-        if (lane == 31) { sPos[warp] = ip; sNeg[warp] = inn; sRev[warp] = ir; sSum[warp] = is; }
-        __syncthreads();
-        uint32_t bp = cPos + ip - ap, bn = cNeg + inn - an, br = cRev + ir - ar;
-        int32_t bs = cSum + is - as;
-        uint32_t tp = 0, tn = 0, tr = 0;
-        int32_t ts = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            if (w == warp) { bp += tp; bn += tn; br += tr; bs += ts; }
-            tp += sPos[w]; tn += sNeg[w]; tr += sRev[w]; ts += sSum[w];
-        }
-        if (tid == kThreads - 1) sCarD = D[kPerThread - 1];
-        {
-            int slot = cs_slot + tid * kPerThread;
-            if (slot >= RING) slot -= RING;
-#pragma unroll
-            for (int i = 0; i < kPerThread; ++i) {
-                TrdEntry en;
-                en.pos = bp + lp[i]; en.neg = bn + ln[i]; en.rev = br + lr[i]; en.sum = bs + ls[i];
-                *reinterpret_cast<TrdEntry*>(ring + trd_byte(slot + i)) = en;
-            }
-        }
-        cPos += tp; cNeg += tn; cRev += tr; cSum += ts;
-        __syncthreads();
-
-        auto get = [&](int64_t k) -> TrdEntry {
-            int slot = cs_slot + (int)(k - cs);
-            if (slot < 0) slot += RING;
-            else if (slot >= RING) slot -= RING;
-            return *reinterpret_cast<const TrdEntry*>(ring + trd_byte(slot));
-        };
-        const int64_t ce = (c + 1 == nchunks) ? (int64_t)0x7fffffffffffll : cs + kChunk;
-        for (bool first = true;; first = false) {
-            const int64_t r = r_next + tid;
-            const int64_t je = first ? e_pref : (r < rb ? (int64_t)jcur[r] : (int64_t)0x7fffffffffffffll);
-            const bool q = je <= ce;
-            if (q) {
-                int64_t jb = je - P.dir_window;
-                if (jb < 0) jb = 0;
-                const int64_t nd = je - jb;  // rolling_trade_directions->size()
-                int32_t pos = 0, neg = 0, rev = 0, isum = 0;
-                if (je > 0) {
-                    const TrdEntry H = get(je - 1);
-                    pos = (int32_t)H.pos; neg = (int32_t)H.neg; isum = H.sum;
-                    if (jb > 0) {
-                        const TrdEntry Lo = get(jb - 1);
-                        pos -= (int32_t)Lo.pos; neg -= (int32_t)Lo.neg; isum -= Lo.sum;
-                    }
-                    rev = (int32_t)(H.rev - get(jb).rev);  // pairs (i-1,i) with i in [jb+1, je-1]
-                }
-                const double rr = nd > 1 ? (double)rev / (double)nd : 0.0;  // feature_processor.cpp:239
-                const double ab = (double)isum / (double)nd;                // :246 — 0/0 = NaN with no trades
-                const int tot = pos + neg;                                  // :261-269
-                // binary entropy of (pos, neg) = (T log2 T - pos log2 pos - neg log2 neg) / T, c log2 c tabulated
-                const double ent = tot > 0 ? ((__ldg(P.clog2c + tot) - __ldg(P.clog2c + pos)) - __ldg(P.clog2c + neg)) / (double)tot : 0.0;
-                out.raw[(int64_t)MRP_F_REVERSAL_RATE * in.n_rows + r] = rr;
-                out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * in.n_rows + r] = ab;
-                out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * in.n_rows + r] = ent;
-                if (out.counts) {
-                    out.counts[(int64_t)MRP_C_TRADE_POS * in.n_rows + r] = pos;
-                    out.counts[(int64_t)MRP_C_TRADE_NEG * in.n_rows + r] = neg;
-                    out.counts[(int64_t)MRP_C_TRADE_REVERSALS * in.n_rows + r] = rev;
-                    out.counts[(int64_t)MRP_C_TRADE_TOTAL * in.n_rows + r] = (int32_t)nd;
-                    out.counts[(int64_t)MRP_C_TRADE_DIR_SUM * in.n_rows + r] = isum;
-                }
-            }
-            const int nq = __syncthreads_count(q);
-            r_next += nq;
-            if (nq < kThreads) break;
-        }
-        cs_slot += kChunk;
-        if (cs_slot >= RING) cs_slot -= RING;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // book pass: one thread per snapshot row, 256 rows per chunk, chunks walked in time order so that the
@@ -382,17 +231,6 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
             raw[(int64_t)MRP_F_LIQUIDITY_STRESS * N] = stress;
         }
     }
-}
-
-size_t trd_ring_bytes(int ring) { return (size_t)ring * 20u; }
-
-cudaError_t launch_trades(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
-                          const DevParams& P, cudaStream_t st) {
-    const size_t smem = trd_ring_bytes(P.trd_ring);
-    cudaError_t e = cudaFuncSetAttribute(k_trades, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_trades<<<nseg, kThreads, smem, st>>>(in, out, segs, P);
-    return cudaGetLastError();
 }
 
 cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,

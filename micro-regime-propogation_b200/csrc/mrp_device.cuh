@@ -2,11 +2,10 @@
 //
 // Design in one paragraph (details in DESIGN.md): the reference evaluates, per snapshot, O(window)
 // loops over three rolling deques (1800 mids/spreads, 1500 tick directions, 1500 trade directions;
-// feature_processor.cpp:48-108,215-269).  Here every window quantity is a difference of running
-// prefix values along its own axis (tick axis, trade axis), held in a shared-memory ring that covers
-// one window plus one chunk, so each tick / trade is read from HBM once, costs one log, and each
-// snapshot row is finalised from two or three ring look-ups addressed by its cursors.  The time axis
-// of a stream is cut into row segments; one CTA streams through one segment (halo = one window).
+// feature_processor.cpp:48-108,215-269).  Here every window quantity slides: snapshot t's value is
+// snapshot t-1's plus the ticks that arrived minus the ticks that left the window, so each tick / trade
+// is read from HBM once (kernels_window.cu).  The time axis of a stream is cut into row segments; one
+// CTA streams through one segment, warmed by a halo of one window.
 // All arithmetic is fp64, compiled with -fmad=false so a*b+c is rounded exactly as the reference's
 // x86-64 SSE2 code rounds it; explicit fma() is used only inside scan carries where the reference
 // has no counterpart.
@@ -65,28 +64,26 @@ struct DevParams {
     int32_t L, mid_window, dir_window, spread_divisor, norm_window, return_lag, stress_levels;
     int32_t emit_counts;
     double ewm_alpha, ewm_decay;            // alpha = 2/(span+1), decay = 1-alpha
+    double inv_spread_divisor;              // 1/spread_divisor
     double ofi_alpha, ofi_decay, ofi_min_total_vol;
     double stress_alpha, stress_decay, stress_min_size, stress_distance_decay;
     const double* ofi_weight;   // [L]  exp(-i*depth_decay), computed by the host libm
-    const double* ewm_pow;      // [mid_window+1]  decay^n
+    const double* ewm_pow;      // [win_ring+1]    decay^n
+    const double* ewm_ipow;     // [win_ring+1]    decay^-n (n <= win_span_max keeps it far from overflow)
     const double* ofi_pow;      // [257]           ofi_decay^n
     const double* stress_pow;   // [257]           stress_decay^n
     const double2* inv_n;       // [norm_window+1] 1/n as (hi, lo) double-double; [0] unused
     const double* clog2c;       // [max(dir_window, mid_window)+2]  c*log2(c), [0] = 0
-    const double* inv_cnt;      // [mid_window+2]  1/n, [0] = 0
-    // ring geometry (entries), computed by the host
-    int32_t ret_ring, spr_ring, trd_ring;
+    const double* inv_cnt;      // [max(mid_window, dir_window)+2]  1/n, [0] = 0
+    // window kernel: shared-memory ring entries (power of two) and the most new ticks one chunk may bring
+    int32_t win_ring, win_span_max;
     int32_t ema_warm_rows;      // halo rows that warm the two row-axis EMAs
     int32_t tile_rows;          // normaliser tile (divides norm_window, or == norm_window)
     int32_t tiles_back;         // norm_window / tile_rows
 };
 
-constexpr int kThreads = 256;          // CTA size of the axis passes
+constexpr int kThreads = 256;          // CTA size of the book pass
 constexpr int kWarps = kThreads / 32;
-constexpr int kPerThread = 4;          // consecutive ticks / trades per thread
-constexpr int kChunk = kThreads * kPerThread;  // 1024 elements per chunk
-constexpr int kChunkShift = 10;
-constexpr int kMaxRingChunks = 12;     // count-base slots
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int d) {

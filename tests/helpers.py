@@ -161,3 +161,25 @@ def load_golden(name):
         h.update(np.ascontiguousarray(batch[k]).tobytes())
     assert h.hexdigest() == str(z["digest"]), "synthetic generator no longer reproduces the fixture inputs"
     return spec, batch, {k: z[k] for k in ("rows", "raw", "norm", "bid_dir", "ask_dir")}
+
+
+# ---- adversarial edits of a synthetic host batch (single stream)
+def drop_rows(batch, lo, hi):
+    """Remove snapshot rows [lo, hi): the next remaining row sees a long jump of its tick / trade cursors."""
+    out = dict(batch)
+    n = len(batch["ts_ns"])
+    keep = np.r_[0:lo, hi:n]
+    for k in ("ts_ns", "buy_vol", "sell_vol", "adds", "tick_cursor", "trade_cursor"):
+        out[k] = np.ascontiguousarray(batch[k][keep])
+    for k in ("bid_px", "ask_px", "bid_sz", "ask_sz"):
+        out[k] = np.ascontiguousarray(batch[k][:, keep])
+    out["row_offsets"] = np.array([0, len(keep)], dtype=np.int64)
+    return out
+
+
+def poke(batch, key, index, value):
+    out = dict(batch)
+    a = np.array(batch[key], copy=True)
+    a[index] = value
+    out[key] = a
+    return out

@@ -1,0 +1,107 @@
+"""GPU parity on the inputs the fast sliding-window formulation cannot represent directly: flagged ticks
+(NaN / zero / negative / infinite midprices, moves beyond the series range, non-finite spreads), snapshots
+that bring more new ticks than the on-chip ring holds, tiny row segments (halo search and restarts), and
+dense / absent trades.  Everything is compared with the oracle exactly like the main parity tests."""
+import os
+
+import numpy as np
+import pytest
+
+import mrp_b200
+from mrp_b200 import synth
+
+from helpers import drop_rows, make_host_batch, poke
+from test_gpu_parity import _check as _check_strict
+
+
+def _check(batch, **kw):
+    # poisoned (NaN) columns are expected here: only require that most cells remain comparable
+    return _check_strict(batch, min_frac=0.5, **kw)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def small_segments(monkeypatch):
+    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "257")
+    yield
+
+
+def test_small_segments_halo_and_restart(small_segments):
+    _check(make_host_batch([synth.SynthSpec(n_rows=5000, seed=31, variable_cursors=True)]))
+
+
+def test_small_segments_cold_start(small_segments):
+    _check(make_host_batch([synth.SynthSpec(n_rows=3000, seed=32, warm_ticks=0, warm_trades=0, variable_cursors=True)]))
+
+
+@pytest.mark.parametrize("kind", ["nan_mid", "zero_mid", "neg_mid", "inf_mid", "jump_mid", "nan_spread", "inf_spread", "many"])
+def test_flagged_ticks(kind, small_segments):
+    b = make_host_batch([synth.SynthSpec(n_rows=4000, seed=33)])
+    K = len(b["mid"])
+    at = [K // 3, K // 3 + 1, K // 2 + 7]
+    if kind == "nan_mid":
+        b = poke(b, "mid", at[:2], np.nan)
+    elif kind == "zero_mid":
+        b = poke(b, "mid", at, 0.0)
+    elif kind == "neg_mid":
+        b = poke(b, "mid", at[:1], -5000.0)
+    elif kind == "inf_mid":
+        b = poke(b, "mid", at[:1], np.inf)
+    elif kind == "jump_mid":
+        b = poke(b, "mid", slice(K // 2, K), b["mid"][K // 2:] * 1.03125)   # a sustained 3 % gap: one out-of-range return
+    elif kind == "nan_spread":
+        b = poke(b, "spread", at, np.nan)
+    elif kind == "inf_spread":
+        b = poke(b, "spread", at[:1], np.inf)
+    else:
+        rng = np.random.default_rng(5)
+        idx = rng.choice(K, size=40, replace=False)
+        b = poke(b, "mid", idx[:20], 0.0)
+        b = poke(b, "spread", idx[20:30], np.nan)
+        b = poke(b, "mid", idx[30:], np.nan)
+    _check(b)
+
+
+def test_flagged_tick_full_segments():
+    b = make_host_batch([synth.SynthSpec(n_rows=9000, seed=34)])
+    K = len(b["mid"])
+    b = poke(b, "mid", [K // 4], 0.0)
+    b = poke(b, "mid", slice(2 * K // 3, K), b["mid"][2 * K // 3:] + 100.0)   # +2 % level shift
+    _check(b)
+
+
+@pytest.mark.parametrize("gap", [400, 1500])
+def test_long_cursor_jump(gap, small_segments):
+    b = make_host_batch([synth.SynthSpec(n_rows=6000, seed=35, variable_cursors=True)])
+    b = drop_rows(b, 2000, 2000 + gap)        # ~4 000 / ~15 000 new ticks in one snapshot: beyond the ring
+    b = drop_rows(b, 900, 1080)               # ~1 800: fits the ring but replaces the whole window
+    _check(b)
+
+
+def test_long_cursor_jump_full_segments():
+    b = make_host_batch([synth.SynthSpec(n_rows=9000, seed=36)])
+    b = drop_rows(b, 5000, 5700)
+    _check(b)
+
+
+def test_dense_and_absent_trades(small_segments):
+    _check(make_host_batch([synth.SynthSpec(n_rows=2500, seed=37, max_trades_per_row=60)]))
+    _check(make_host_batch([synth.SynthSpec(n_rows=1500, seed=38, warm_trades=0, max_trades_per_row=0)]))
+
+
+def test_slow_ticks_and_fast_ticks(small_segments):
+    _check(make_host_batch([synth.SynthSpec(n_rows=2000, seed=39, ticks_per_row=1)]))
+    _check(make_host_batch([synth.SynthSpec(n_rows=1500, seed=40, ticks_per_row=100)]))   # 5 s snapshots: ~22 rows per chunk
+
+
+def test_flat_window_is_exactly_zero():
+    b = make_host_batch([synth.SynthSpec(n_rows=1200, seed=41)])
+    K = len(b["mid"])
+    b = poke(b, "mid", slice(3000, 9000), b["mid"][3000])   # 6000 flat ticks: windows with no moves at all
+    got, ref = _check(b)
+    F = mrp_b200.FEATURES.index
+    flat = ref["raw"][F("realized_variance")] == 0.0
+    assert flat.any()
+    for name in ("realized_variance", "ewm_volatility", "directional_volatility"):
+        assert (got["raw"][F(name)][flat] == 0.0).all(), name

@@ -11,7 +11,7 @@ from helpers import (make_host_batch, nan_pattern_equal, norm_check, norm_errors
 pytestmark = pytest.mark.gpu
 
 
-def _check(batch, params=None, z_tol=1e-9, mode="upload"):
+def _check(batch, params=None, z_tol=1e-9, mode="upload", min_frac=0.95):
     p = params or mrp_b200.default_params(emit_dirs=1, emit_counts=1)
     hv, got = run_gpu(batch, p, mode)
     ref = ob.run_oracle(hv, p)
@@ -32,7 +32,7 @@ def _check(batch, params=None, z_tol=1e-9, mode="upload"):
     assert nan_pattern_equal(got["norm"], ref["norm"])
     # z-scores: conditioning-aware, against the exactly-summed definition and against the reference itself
     wa, wb, drift, frac = norm_check(got["norm"], ref["raw"], ref["norm"], hv.arrays["row_offsets"], p.norm_window, z_tol)
-    assert frac > 0.95
+    assert frac > min_frac
     assert (wa <= 1.0).all(), {mrp_b200.FEATURES[i]: wa[i] for i in np.nonzero(wa > 1.0)[0]}
     assert (wb <= 1.0).all(), {mrp_b200.FEATURES[i]: (wb[i], drift[i]) for i in np.nonzero(wb > 1.0)[0]}
     zr = norm_errors(got["norm"], ref["norm"])
