@@ -33,7 +33,7 @@ namespace mrp {
 
 constexpr int kWinThreads = 256;
 constexpr int kWinRows = 128;            // snapshots per chunk: threads 0..127 add side, 128..255 evict side + trades
-constexpr double kMaxRelMove = 0x1p-10;  // |M_k/M_{k-1} - 1| bound of the log1p series
+// the log1p series covers relative moves below 2^-10 per tick (high word 0x3f500000)
 
 struct __align__(16) WinShared {
     double A[5][kWinRows];      // per-row deltas, then (after the scan) per-row window values
@@ -221,25 +221,51 @@ __device__ __noinline__ void direct_trade_row(const int8_t* __restrict__ tdir, u
     write_trade_row(o, N, r, clog2c, (int)(je - jb), pos, neg, rev, isum);
 }
 
-// One tick: y = +-r^2 (sign set unless the return is > 0) and the flag "the fast formulation cannot represent it".
-__device__ __forceinline__ double tick_y(double Mp, double M, bool neutral, bool& exc) {
-    const double dM = M - Mp;
-    const double u = dM * rcp_pos(Mp);
-    const double r = log1p_small(u);
-    const double x = r * r;
-    exc = !neutral && !(Mp > 0.0 && M > 0.0 && fabs(u) <= kMaxRelMove);
-    return (dM > 0.0 && !neutral) ? x : (neutral ? -0.0 : -x);
+// explicit 32-bit shared-window accessors for the ring (keeps address formation out of the inner loops)
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64_off(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_hi32(uint32_t a) {  // high word of the double at a
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(v) : "r"(a));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f64_off(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
 }
 
-// visit ring slots of the positions [k0, k1) in order; at most one wrap
+// y = +-r^2 of the return log(M / Mprev) = sgn * log1p(sgn * v) written with ONE reciprocal per pair of ticks:
+// v = (M - Mprev) * rcp with rcp = 1/Mprev (sgn = +1) or 1/M (sgn = -1, log(M/Mprev) = -log1p((Mprev - M)/M)).
+// t = Mprev - M; the sign bit of y is set unless the midprice rose (t < 0).
+__device__ __forceinline__ double signed_sq_return(double t, double v_signed) {
+    const double r = log1p_small(v_signed);
+    const double x = r * r;
+    const int hi = __double2hiint(x) | (~__double2hiint(t) & 0x80000000);
+    return __hiloint2double(hi, __double2loint(x));
+}
+__device__ __forceinline__ bool small_mag(double v, uint32_t hi_limit) {  // |v| < the double whose high word is hi_limit; NaN -> false
+    return ((uint32_t)__double2hiint(v) & 0x7fffffffu) < hi_limit;
+}
+
+// visit the ring slots of the positions [k0, k1) in order (at most one wrap): body(shared address, position)
 template <int RING, typename F>
-__device__ __forceinline__ void for_ring(const double* __restrict__ ring, uint32_t k0, uint32_t k1, F&& body) {
+__device__ __forceinline__ void for_ring(uint32_t ring_base, uint32_t k0, uint32_t k1, F&& body) {
     while (k0 < k1) {
         const uint32_t slot = k0 & (RING - 1);
         const uint32_t n = min(k1 - k0, (uint32_t)RING - slot);
-        const double* __restrict__ p = ring + slot;
-#pragma unroll 4
-        for (uint32_t j = 0; j < n; ++j) body(p + j, k0 + j);
+        uint32_t a = ring_base + slot * 8u;
+        const uint32_t aend = a + n * 8u;
+#pragma unroll 1
+        for (; a < aend; a += 8u) body(a);
         k0 += n;
     }
 }
@@ -268,6 +294,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
     extern __shared__ __align__(16) double ring[];  // y: ring[0, RING)   d: ring[RING, 2 RING)
     __shared__ WinShared sh;
     constexpr uint32_t mask = RING - 1;
+    constexpr int kD = RING * 8;  // byte offset of the d ring
+    const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = tid & (kWinRows - 1);
@@ -312,7 +340,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             baseJ = 0;
             if (rs > sr0) {
                 const uint32_t e = kcur[rs], j = jcur[rs];
-                baseK = sub_floor0(e, Wmax + 1);
+                baseK = sub_floor0(e, Wmax + 1) & ~1u;  // even: tick pairs never straddle the base
                 baseJ = sub_floor0(j, Wd + 1);
                 // first row whose cursors lie beyond the bases (cursors are non-decreasing): 256-ary search
                 int64_t lo = sr0, hi = rs;
@@ -378,25 +406,29 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 
         // ------------------------------------------------------------------ tick phase: new ticks -> ring, two per thread
         for (uint32_t k = (Eprev & ~1u) + 2u * tid; k < Elast; k += 2u * kWinThreads) {
+            // ticks a = k (new unless k < Eprev) and b = k + 1 (new unless past the chunk); k is even
             const bool va = k >= Eprev, vb = k + 1u < Elast;
-            const bool na = k == baseK, nb = k + 1u == baseK;
-            double Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
             const double Ma = __ldg(mid + k);
-            if (va && !na) Mp = __ldg(mid + k - 1);
+            double Mp = Ma, Mb = Ma, Sa = pivot, Sb = pivot;  // defaults give flat, unflagged ticks
+            if (k != baseK) Mp = __ldg(mid + k - 1);           // the tick at the base (tick 0) has no return: flat
             if (va) Sa = __ldg(spread + k);
             if (vb) {
                 Mb = __ldg(mid + k + 1);
                 Sb = __ldg(spread + k + 1);
             }
-            bool ea, eb;
-            const double ya = tick_y(Mp, Ma, na, ea), yb = tick_y(Ma, Mb, nb, eb);
+            const double ra = rcp_pos(Ma);
+            const double ta = Mp - Ma, tb = Ma - Mb;
+            const double va_ = ta * ra, vb_ = -tb * ra;        // (Mp-Ma)/Ma and (Mb-Ma)/Ma
+            const double ya = signed_sq_return(ta, va_), yb = signed_sq_return(tb, vb_);
             const double da = Sa - pivot, db = Sb - pivot;
-            ea |= !(fabs(da) <= 1e150);
-            eb |= !(fabs(db) <= 1e150);
-            const uint32_t slot = k & mask;  // k is even: the pair never straddles the wrap
-            if (va) { ring[slot] = ya; ring[RING + slot] = da; }
-            if (vb) { ring[slot + 1] = yb; ring[RING + slot + 1] = db; }
-            if ((va && ea) || (vb && eb)) atomicMax(&sh.excP1, ((vb && eb) ? k + 1u : k) + 1u);
+            // flagged: a midprice that is not a positive normal number, a move beyond the series range, a spread that is
+            // not finite (or absurd).  One flag per pair, attributed to tick b (conservative by one position).
+            const bool ok = (uint32_t)(__double2hiint(Ma) - 0x00100000) < 0x7fe00000u && small_mag(va_, 0x3f500000u) &&
+                            small_mag(vb_, 0x3f500000u) && small_mag(da, 0x5f138d35u) && small_mag(db, 0x5f138d35u);
+            const uint32_t a = ring_base + (k & mask) * 8u;
+            if (va) { sts_f64_off<0>(a, ya); sts_f64_off<kD>(a, da); }
+            if (vb) { sts_f64_off<8>(a, yb); sts_f64_off<kD + 8>(a, db); }
+            if (!ok) atomicMax(&sh.excP1, k + 2u);
         }
         __syncthreads();
         const uint32_t excP1 = sh.excP1;
@@ -438,23 +470,36 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             // ticks that arrive: [e0, e1)
             double sAll = 0.0, sSgn = 0.0, hh = 0.0, d1 = 0.0, d2 = 0.0;
             uint32_t neg = 0, mov = 0, lm = 0;
-            for_ring<RING>(ring, e0, e1, [&](const double* __restrict__ p, uint32_t k) {
-                const double y = p[0], d = p[RING];
-                sAll += fabs(y);
-                sSgn += y;
-                hh = fma(hh, decay, fabs(y));
-                neg += (uint32_t)__double2hiint(y) >> 31;
-                if (fabs(y) > 0.0) { ++mov; lm = k + 1u; }
-                d1 += d;
-                d2 = fma(d, d, d2);
-            });
+            {
+                uint32_t k0 = e0;
+                while (k0 < e1) {
+                    const uint32_t slot = k0 & mask;
+                    const uint32_t n = min(e1 - k0, (uint32_t)RING - slot);
+                    const uint32_t a0 = ring_base + slot * 8u, aend = a0 + n * 8u;
+                    uint32_t am = 0;
+#pragma unroll 1
+                    for (uint32_t a = a0; a < aend; a += 8u) {
+                        const double y = lds_f64(a), d = lds_f64_off<kD>(a);
+                        sAll += fabs(y);
+                        sSgn += y;
+                        hh = fma(hh, decay, fabs(y));
+                        neg += (uint32_t)__double2hiint(y) >> 31;
+                        if (((uint32_t)__double2hiint(y) << 1) != 0u) { ++mov; am = a; }  // r^2 of a move is normal: high word suffices
+                        d1 += d;
+                        d2 = fma(d, d, d2);
+                    }
+                    if (am != 0u) lm = k0 + ((am - a0) >> 3) + 1u;
+                    k0 += n;
+                }
+            }
             // ticks that leave the direction window: [q0, q1)
             const uint32_t q0 = max(baseK, sub_floor0(e0, Wd)), q1 = max(baseK, sub_floor0(e1, Wd));
             uint32_t qneg = 0, qmov = 0;
-            for_ring<RING>(ring, q0, q1, [&](const double* __restrict__ p, uint32_t) {
-                const double y = p[0];
-                qneg += (uint32_t)__double2hiint(y) >> 31;
-                if (fabs(y) > 0.0) ++qmov;
+            for_ring<RING>(ring_base, q0, q1, [&](uint32_t a) {
+                const uint32_t hi = lds_hi32(a);
+                qneg += hi >> 31;
+                // r^2 of a real move is far above 2^-1022: the high word alone tells zero from non-zero
+                if ((hi << 1) != 0u) ++qmov;
             });
             sh.A[0][i] = sAll;
             sh.A[1][i] = sSgn;
@@ -493,8 +538,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             const uint32_t s0 = max(baseK, sub_floor0(e0, Wm)), s1 = max(baseK, sub_floor0(e1, Wm));
             double hE = 0.0;
             uint32_t neg = 0;
-            for_ring<RING>(ring, s0, s1, [&](const double* __restrict__ p, uint32_t) {
-                const double y = p[0], d = p[RING];
+            for_ring<RING>(ring_base, s0, s1, [&](uint32_t a) {
+                const double y = lds_f64(a), d = lds_f64_off<kD>(a);
                 bAll += fabs(y);
                 bSgn += y;
                 hE = fma(hE, decay, fabs(y));
@@ -545,7 +590,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                         const uint32_t s = sub_floor0(e, Wm);
                         cnt = (int)(e - s) - 1;
                         // the sliding sums cover the ticks [s, e); the window's returns are (s, e): take tick s out again
-                        const double ys = ring[s & mask];
+                        const double ys = lds_f64(ring_base + (s & mask) * 8u);
                         const double D1 = sh.A[2][i], D2 = sh.A[3][i];
                         const int dirw = sh.AI[1][i];
                         if (cnt > 0) {
@@ -560,7 +605,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                             if (tot != 0.0) {
                                 // :64-79, see the header: E over (s, e) plus the restart correction of the first return
                                 const double E = sh.A[4][i] * __ldg(P.ewm_pow + (e - E0));
-                                w = E + __ldg(P.ewm_pow + cnt) * (fabs(ring[(s + 1u) & mask]) - P.ewm_alpha * fabs(ys));
+                                w = E + __ldg(P.ewm_pow + cnt) * (fabs(lds_f64(ring_base + ((s + 1u) & mask) * 8u)) - P.ewm_alpha * fabs(ys));
                                 if (!(w > 0.0)) w = 0.0;
                             }
                             ewm = sqrt(w);
