@@ -15,7 +15,8 @@
 namespace mrp {
 cudaError_t launch_windows(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
 cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
-cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, const DevParams&, cudaStream_t);
+cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, void*, const int64_t*, int, const DevParams&, cudaStream_t);
+size_t norm_poison_bytes(int);
 cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
 size_t win_smem_bytes(int);
 }  // namespace mrp
@@ -84,7 +85,7 @@ struct mrp_fg_ctx {
     // outputs
     DevBuf b_raw, b_norm, b_bdir, b_adir, b_counts;
     // tables
-    DevBuf b_segs, b_tiles, b_tile_tot, b_flags, b_tables, b_row_off;
+    DevBuf b_segs, b_tiles, b_tile_tot, b_flags, b_tables, b_row_off, b_poison;
     int nseg = 0, ntiles = 0;
     // timing
     bool timing = false, have_times = false;
@@ -106,14 +107,24 @@ int check_params(const mrp_fg_params& p) {
 }
 
 int pick_tile_rows(int W) {
-    if (W <= 2048) return W;
-    int best = 0;
-    for (int t = 2048; t >= 128; --t)
+    if (const char* e = std::getenv("MRP_FG_NORM_TILE")) {  // experiments
+        const int t = std::atoi(e);
+        if (t >= 4 && W % t == 0) return t;
+    }
+    if (W <= 1024) return W;
+    // a warp sweeps 128 rows per step, 4 per lane: prefer a divisor of W that is a multiple of 4 and wastes
+    // the least of its last step; among equals the one nearest 1000 rows (short look-back, many tiles in flight)
+    int pick = 0;
+    double score = 0.0;
+    for (int t = 256; t <= 1024; t += 4)
         if (W % t == 0) {
-            // prefer tiles around 1000-1500 rows: enough parallel tiles, short look-back (W/t totals)
-            if (best == 0) best = t;
-            if (t <= 1536) return t;
+            const double s = (double)t / (double)(((t + 127) / 128) * 128) - 1e-6 * std::abs(t - 1000);
+            if (s > score) { score = s; pick = t; }
         }
+    if (pick) return pick;
+    int best = 0;
+    for (int t = 2048; t >= 32; --t)
+        if (W % t == 0) { best = t; break; }
     return best;
 }
 
@@ -167,7 +178,7 @@ int setup_params(mrp_fg_ctx* c) {
     d.ema_warm_rows = ((warm + kThreads - 1) / kThreads) * kThreads;
 
     d.tile_rows = pick_tile_rows(p.norm_window);
-    if (d.tile_rows <= 0) return fail(MRP_FG_ERR_INVALID, "norm_window above 2048 needs a divisor in [128,2048]");
+    if (d.tile_rows <= 0) return fail(MRP_FG_ERR_INVALID, "norm_window above 1024 needs a divisor in [32,2048]");
     d.tiles_back = p.norm_window / d.tile_rows;
 
     // constant tables, evaluated by the host libm so that they are bit-identical to the reference's factors
@@ -183,14 +194,8 @@ int setup_params(mrp_fg_ctx* c) {
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
     const size_t o_s = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.stress_decay, (long double)n));
-    if (tab.size() & 1) tab.push_back(0.0);  // keep the double2 table 16-byte aligned
     const size_t o_i = tab.size();
-    for (int n = 0; n <= p.norm_window; ++n) {  // 1/n in double-double, so sum*(1/n) rounds like sum/n
-        const long double r = n > 0 ? 1.0L / (long double)n : 0.0L;
-        const double hi = (double)r;
-        tab.push_back(hi);
-        tab.push_back((double)(r - (long double)hi));
-    }
+    for (int n = 0; n <= p.norm_window; ++n) tab.push_back(n > 0 ? 1.0 / (double)n : 0.0);
     const size_t o_h = tab.size();
     const int hmax = std::max(p.dir_window, p.mid_window) + 1;
     for (int n = 0; n <= hmax; ++n) tab.push_back(n > 0 ? (double)((long double)n * log2l((long double)n)) : 0.0);
@@ -205,7 +210,7 @@ int setup_params(mrp_fg_ctx* c) {
     d.ewm_ipow = t + o_ei;
     d.ofi_pow = t + o_o;
     d.stress_pow = t + o_s;
-    d.inv_n = reinterpret_cast<const double2*>(t + o_i);
+    d.inv_cnt_norm = t + o_i;
     d.clog2c = t + o_h;
     d.inv_cnt = t + o_c;
     return MRP_FG_OK;
@@ -300,6 +305,7 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
             t.n = (int32_t)std::min<int64_t>(TR, r1 - a);
             t.index = idx;
             t.first_id = first;
+            t.stream = s;
             tiles.push_back(t);
         }
     }
@@ -310,6 +316,7 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     if ((rc = c->b_tile_tot.ensure(tiles.size() * 2 * MRP_FG_NUM_FEATURES * sizeof(double)))) return rc;
     if ((rc = c->b_flags.ensure((tiles.size() + 1) * sizeof(int)))) return rc;
     if ((rc = c->b_row_off.ensure((S + 1) * sizeof(int64_t)))) return rc;
+    if ((rc = c->b_poison.ensure(norm_poison_bytes(S)))) return rc;
     if (!segs.empty()) CU(cudaMemcpy(c->b_segs.p, segs.data(), segs.size() * sizeof(DevSegment), cudaMemcpyHostToDevice));
     if (!tiles.empty()) CU(cudaMemcpy(c->b_tiles.p, tiles.data(), tiles.size() * sizeof(DevTile), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->b_row_off.p, c->row_off.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -379,7 +386,7 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->b_ts, &c->b_bpx, &c->b_apx, &c->b_bsz, &c->b_asz, &c->b_buy, &c->b_sell, &c->b_adds, &c->b_kcur,
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
-                      &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off};
+                      &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison};
     for (DevBuf* b : bufs) b->release();
     if (c->ev_made)
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -485,8 +492,9 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
     CU(launch_book(c->in, c->out, segs, c->nseg, c->dp, st));
     if (tm) CU(cudaEventRecord(c->ev[2], st));
     CU(launch_normalize(c->out, c->n_rows, static_cast<const DevTile*>(c->b_tiles.p), c->ntiles,
-                        static_cast<double*>(c->b_tile_tot.p), static_cast<int*>(c->b_flags.p), c->dp, st));
-    c->launches += kNumKernels;
+                        static_cast<double*>(c->b_tile_tot.p), static_cast<int*>(c->b_flags.p), c->b_poison.p,
+                        static_cast<const int64_t*>(c->b_row_off.p), c->n_streams, c->dp, st));
+    c->launches += kNumKernels + 1;  // + the (normally empty) non-finite fix-up pass
     if (c->p.norm_mode == MRP_NORM_FAITHFUL) {
         CU(launch_normalize_faithful(c->out, c->n_rows, static_cast<const int64_t*>(c->b_row_off.p), c->n_streams, c->dp, st));
         c->launches += 1;

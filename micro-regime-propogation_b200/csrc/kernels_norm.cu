@@ -1,4 +1,4 @@
-// kernels_norm.cu — the rolling z-score (FeatureNormalizer) and its fused write epilogue.
+// kernels_norm.cu — the rolling z-score (FeatureNormalizer) and its write epilogue.
 //
 // Reference (feature_normalizer.cpp:32-83): running sum / sum-of-squares per feature, add the new row,
 // evict the row 30 000 back, z = (x - sum/n) / sqrt(sum2/n - (sum/n)^2) (std = 1 when the variance is not
@@ -6,13 +6,20 @@
 //
 // k_normalize evaluates the SAME window sums without any long-lived accumulator.  The row axis of a stream
 // is cut into tiles of `tile_rows` rows, tile_rows dividing norm_window (30 000 = 30 x 1000).  For a row t
-// in tile T (offset o in the stream), with l = t - norm_window in tile T-30:
-//      window sum(t) = [totals of tiles T-30 .. T-1] + prefix_T(t) - prefix_{T-30}(l)
-// so a CTA needs 30 small totals of its predecessors plus two in-tile scans.  Tiles are handed out by an
-// atomic ticket in time order; each CTA first publishes its own totals (release flag), only then waits for
-// its predecessors' flags — predecessors hold smaller tickets, hence are already resident: no deadlock,
-// no serial carry chain.  The lagged tile was streamed by a CTA ~30 tickets earlier and is still in the
+// in tile T:
+//      window sum(t) = [totals of tiles T-30 .. T-1] + sum_{i <= t in tile} (x_i - x_{i-W})
+// so a warp needs 30 small totals of the tile's predecessors plus one in-tile scan of (x - x_lag, x^2 - x_lag^2).
+// Tiles are handed out by an atomic ticket in time order; each warp first publishes its own column total,
+// only then waits for the predecessors' totals of the same column — predecessors hold smaller tickets, hence
+// are resident: no deadlock, no serial carry chain.  The lagged tile was streamed ~30 tickets earlier and is still in the
 // 126 MB L2, so HBM sees each raw value once (read) and each z-score once (write).
+// After the ticket is taken the ten warps of a CTA never meet again: every warp owns whole columns, a lane owns
+// four consecutive rows per 128-row step (one 256-bit access: the warp touches 1 KB contiguously), and the only
+// cross-lane traffic is one warp scan per step.
+//
+// Non-finite raw values follow the reference's own arithmetic (a NaN poisons the running sums for ever, an
+// infinity until it is evicted and then for ever): k_normalize records where each column first goes
+// non-finite, and k_norm_poison — which returns at once on clean data — rewrites the affected rows.
 //
 // k_normalize_faithful re-enacts the reference's add-then-evict chain in its exact rounding order
 // (one thread per stream x feature; serial, for validation only).
@@ -23,169 +30,280 @@ namespace mrp {
 constexpr int kNormWarps = 10;
 constexpr int kNormThreads = kNormWarps * 32;
 constexpr int kNF = MRP_FG_NUM_FEATURES;
-constexpr int kRowsPerLane = 4;
-constexpr int kStep = 32 * kRowsPerLane;
+constexpr int kRPL = 4;               // consecutive rows per lane: one 256-bit access, a warp covers 1 KB contiguously
+constexpr int kStep = 32 * kRPL;      // rows per warp step
 
-__device__ __forceinline__ int ld_flag(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+// A tile total doubles as its own "published" flag: the table is preset to an all-ones pattern (a NaN no
+// arithmetic produces), a total is one aligned 8-byte store, and a reader polls the value itself — no separate
+// flag, no fences on either side.
+constexpr unsigned long long kUnpublished = 0xffffffffffffffffull;
+__device__ __forceinline__ unsigned long long peek_total(const double* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ double poll_total(const double* p, unsigned long long u) {  // u: an earlier peek of *p
+    while (u == kUnpublished) {
+        __nanosleep(20);
+        u = peek_total(p);
+    }
+    return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ double publishable(double s) {  // keep computed NaNs distinguishable from "unpublished"
+    return s == s ? s : __longlong_as_double(0x7ff8000000000000ll);
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// four consecutive doubles of a lane: two 128-bit loads when the column is 16-byte aligned
-__device__ __forceinline__ void load4(const double* __restrict__ p, int i, int n, bool vec, double (&o)[kRowsPerLane]) {
-    if (vec && i + kRowsPerLane <= n) {
+// 1/sqrt(v) for a positive normal v: the seed plus one third-order step (the library's own fast path)
+__device__ __forceinline__ double rsqrt_pos(double v) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    const double e = fma(-v * r, r, 1.0);           // 1 - v r^2
+    const double p = fma(e, 0.375, 0.5);
+    return fma(p, e * r, r);                         // r (1 + e/2 + 3 e^2/8)
+}
+
+// Four consecutive doubles of a lane.  ALIGN = 32: one 256-bit access (sm_100 LDG.256 / STG.256: the warp's 32 lanes
+// touch 8 full lines); ALIGN = 16: two 128-bit accesses; otherwise scalar.
+template <int ALIGN>
+__device__ __forceinline__ void load4(const double* __restrict__ p, int i, int n, double (&o)[kRPL]) {
+    if (ALIGN == 32 && i + kRPL <= n) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p + i));
+    } else if (ALIGN == 16 && i + kRPL <= n) {
         const double2 a = *reinterpret_cast<const double2*>(p + i), b = *reinterpret_cast<const double2*>(p + i + 2);
         o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
     } else {
 #pragma unroll
-        for (int k = 0; k < kRowsPerLane; ++k) o[k] = i + k < n ? p[i + k] : 0.0;
+        for (int k = 0; k < kRPL; ++k) o[k] = i + k < n ? p[i + k] : 0.0;
+    }
+}
+template <int ALIGN>
+__device__ __forceinline__ void store4(double* __restrict__ p, int i, int n, const double (&o)[kRPL]) {
+    if (ALIGN == 32 && i + kRPL <= n) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + i), "d"(o[0]), "d"(o[1]), "d"(o[2]), "d"(o[3]) : "memory");
+    } else if (ALIGN == 16 && i + kRPL <= n) {
+        *reinterpret_cast<double2*>(p + i) = make_double2(o[0], o[1]);
+        *reinterpret_cast<double2*>(p + i + 2) = make_double2(o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRPL; ++k)
+            if (i + k < n) p[i + k] = o[k];
+    }
+}
+__device__ __forceinline__ int common_align(const void* a, const void* b, int w_rows) {
+    const uintptr_t m = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | ((uintptr_t)w_rows * 8u);
+    return (m & 31) == 0 ? 32 : ((m & 15) == 0 ? 16 : 8);
+}
+
+// non-finite bookkeeping, per (stream, column): first stream-local row holding NaN / +inf / -inf
+struct NormPoison {
+    unsigned int first_nan, first_pinf, first_ninf;
+};
+
+// ---- pass 1 of one (tile, column): the tile total, published as soon as the column has been read once
+template <int ALIGN>
+__device__ __forceinline__ void tile_total(const double* __restrict__ x, const int n, const int64_t tl0, double* __restrict__ tot,
+                                           NormPoison* __restrict__ q, int* __restrict__ any_poison, const int lane) {
+    double s = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
+    unsigned int fn = 0xffffffffu, fp = 0xffffffffu, fm = 0xffffffffu;
+    for (int i0 = 0; i0 < n; i0 += 2 * kStep) {
+        const int ia = i0 + lane * kRPL, ib = ia + kStep;
+        double a[kRPL], b[kRPL];
+        load4<ALIGN>(x, ia, n, a);
+        load4<ALIGN>(x, ib, n, b);
+        uint32_t m = 0u;  // largest |high word|: >= 0x7ff00000 means an infinity or a NaN
+#pragma unroll
+        for (int k = 0; k < kRPL; ++k) {
+            s += a[k];
+            s2 = fma(a[k], a[k], s2);
+            t1 += b[k];
+            t2 = fma(b[k], b[k], t2);
+            m = max(m, max((uint32_t)__double2hiint(a[k]) & 0x7fffffffu, (uint32_t)__double2hiint(b[k]) & 0x7fffffffu));
+        }
+        if (m >= 0x7ff00000u) {  // rare: record where the column first goes non-finite (stream-local rows)
+#pragma unroll
+            for (int k = 0; k < 2 * kRPL; ++k) {
+                const double y = k < kRPL ? a[k] : b[k - kRPL];
+                const int i = (k < kRPL ? ia : ib) + (k & (kRPL - 1));
+                if (i >= n) continue;
+                const unsigned int r = (unsigned int)(tl0 + i);
+                if (y != y) fn = min(fn, r);
+                else if (y == __longlong_as_double(0x7ff0000000000000ll)) fp = min(fp, r);
+                else if (y == __longlong_as_double(0xfff0000000000000ll)) fm = min(fm, r);
+            }
+        }
+    }
+    if ((fn & fp & fm) != 0xffffffffu) {
+        if (fn != 0xffffffffu) atomicMin(&q->first_nan, fn);
+        if (fp != 0xffffffffu) atomicMin(&q->first_pinf, fp);
+        if (fm != 0xffffffffu) atomicMin(&q->first_ninf, fm);
+        *any_poison = 1;
+    }
+    s += t1;
+    s2 += t2;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) {
+        __stcg(tot, publishable(s));
+        __stcg(tot + kNF, publishable(s2));
     }
 }
 
-__global__ void __launch_bounds__(kNormThreads, 2)
+// ---- pass 2 of one (tile, column): the window sum slides along the tile
+//        sum(t) = [totals of the preceding tiles inside the window] + sum_{i<=t in tile} (x_i - x_{i-W})
+template <int ALIGN>
+__device__ __forceinline__ void tile_zscores(const double* __restrict__ x, double* __restrict__ z, const int n, const bool has_lag,
+                                             const int W, const int64_t tl0, const double* __restrict__ pred_tot, const int nb,
+                                             const double* __restrict__ inv_n, int32_t* __restrict__ cnt_out, const int lane) {
+    const double* __restrict__ xl = x - W;
+    // the first step's values are in flight while the predecessors' totals are collected
+    double v[kRPL], l[kRPL] = {0.0, 0.0, 0.0, 0.0};
+    load4<ALIGN>(x, lane * kRPL, n, v);
+    if (has_lag) load4<ALIGN>(xl, lane * kRPL, n, l);
+    double run1 = 0.0, run2 = 0.0;
+    {
+        double h1 = 0.0, h2 = 0.0;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+            if (j0 + lane < nb) {
+                const double* __restrict__ tp = pred_tot + (int64_t)(j0 + lane) * 2 * kNF;
+                const unsigned long long ua = peek_total(tp), ub = peek_total(tp + kNF);  // both in flight together
+                h1 += poll_total(tp, ua);
+                h2 += poll_total(tp + kNF, ub);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            h1 += __shfl_xor_sync(0xffffffffu, h1, d);
+            h2 += __shfl_xor_sync(0xffffffffu, h2, d);
+        }
+        run1 = h1;
+        run2 = h2;
+    }
+    const double invW = __ldg(inv_n + W);
+    for (int i0 = 0; i0 < n; i0 += kStep) {
+        const int ib = i0 + lane * kRPL;
+        double vn[kRPL] = {0.0, 0.0, 0.0, 0.0}, ln[kRPL] = {0.0, 0.0, 0.0, 0.0};
+        if (i0 + kStep < n) {  // next step's values: in flight during this step's arithmetic
+            load4<ALIGN>(x, ib + kStep, n, vn);
+            if (has_lag) load4<ALIGN>(xl, ib + kStep, n, ln);
+        }
+        double p1[kRPL], p2[kRPL];
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kRPL; ++k) {
+            a1 += v[k] - l[k];
+            a2 += fma(v[k], v[k], -(l[k] * l[k]));
+            p1[k] = a1;
+            p2[k] = a2;
+        }
+        double s1 = a1, s2 = a2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double u1 = shfl_up_d(s1, d), u2 = shfl_up_d(s2, d);
+            if (lane >= d) { s1 += u1; s2 += u2; }
+        }
+        const double b1 = run1 + (s1 - a1), b2 = run2 + (s2 - a2);
+        double zz[kRPL];
+#pragma unroll
+        for (int k = 0; k < kRPL; ++k) {
+            const double e1 = b1 + p1[k], e2 = b2 + p2[k];
+            double inv = invW;
+            if (!has_lag) {  // the window is still filling: n = rows so far (feature_normalizer.cpp:71)
+                const int64_t tl = tl0 + ib + k;
+                inv = __ldg(inv_n + (tl + 1 >= W ? W : (int)(tl + 1)));
+            }
+            const double mean = e1 * inv;                       // :62
+            const double variance = e2 * inv - mean * mean;     // :63
+            // :67 — std = 1 unless the variance is positive.  Fast path: positive, normal, far from the range ends
+            double rstd;
+            if ((uint32_t)(__double2hiint(variance) - 0x03000000) < 0x79000000u) rstd = rsqrt_pos(variance);
+            else rstd = variance > 0.0 ? rsqrt(variance) : 1.0;
+            zz[k] = (v[k] - mean) * rstd;                       // :68
+        }
+        store4<ALIGN>(z, ib, n, zz);
+        if (cnt_out) {
+#pragma unroll
+            for (int k = 0; k < kRPL; ++k)
+                if (ib + k < n) {
+                    const int64_t tl = tl0 + ib + k;
+                    cnt_out[ib + k] = tl + 1 >= W ? W : (int)(tl + 1);
+                }
+        }
+        run1 += __shfl_sync(0xffffffffu, s1, 31);
+        run2 += __shfl_sync(0xffffffffu, s2, 31);
+#pragma unroll
+        for (int k = 0; k < kRPL; ++k) { v[k] = vn[k]; l[k] = ln[k]; }
+    }
+}
+
+// One CTA per tile (atomic ticket, time order), ten warps, each owning the columns w and w + 10.  All of the
+// CTA's column totals are published first (one read of the tile), then the z-scores are produced from a second read
+// that the L2 serves; after the ticket the warps never meet again.
+__global__ void __launch_bounds__(kNormThreads, 3)
 k_normalize(const DevOutputs out, const int64_t N, const DevTile* __restrict__ tiles, double* __restrict__ tile_tot,
-            int* __restrict__ flags, unsigned int* __restrict__ ticket, const DevParams P) {
+            int* __restrict__ flags, unsigned int* __restrict__ ticket, NormPoison* __restrict__ poison, int* __restrict__ any_poison,
+            const DevParams P) {
     __shared__ int sId;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sId = (int)atomicAdd(ticket, 1u);
     __syncthreads();
     const int id = sId;
     const DevTile T = tiles[id];
-    const int n = T.n;
-    // After this point the ten warps of the CTA never meet again: every warp owns whole feature columns.
-
-    // ---- pass 1: column totals of this tile, published (release) before anything is awaited.
-    //      flags[id] counts the columns published so far; a tile is complete at 19.
+    const int n = T.n, W = P.norm_window;
+    const int64_t tl0 = (int64_t)T.index * P.tile_rows;  // stream-local index of the tile's first row
     for (int c = warp; c < kNF; c += kNormWarps) {
         const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
-        const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-        double s = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int i0 = 0; i0 < n; i0 += 2 * kStep) {
-            double a[kRowsPerLane], b[kRowsPerLane];
-            load4(x, i0 + lane * kRowsPerLane, n, vec, a);
-            load4(x, i0 + kStep + lane * kRowsPerLane, n, vec, b);
-#pragma unroll
-            for (int k = 0; k < kRowsPerLane; ++k) {
-                s += a[k];
-                s2 += a[k] * a[k];
-                t1 += b[k];
-                t2 += b[k] * b[k];
-            }
-        }
-        s += t1;
-        s2 += t2;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, d);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-        }
-        if (lane == 0) {
-            tile_tot[(int64_t)id * 2 * kNF + c] = s;
-            tile_tot[(int64_t)id * 2 * kNF + kNF + c] = s2;
-            __threadfence();
-            atomicAdd(flags + id, 1);
-        }
+        double* tot = tile_tot + (int64_t)id * 2 * kNF + c;
+        NormPoison* q = poison + (int64_t)T.stream * kNF + c;
+        const int al = common_align(x, x, 0);
+        if (al == 32) tile_total<32>(x, n, tl0, tot, q, any_poison, lane);
+        else if (al == 16) tile_total<16>(x, n, tl0, tot, q, any_poison, lane);
+        else tile_total<8>(x, n, tl0, tot, q, any_poison, lane);
     }
-
-    // ---- pass 2: the window sum slides along the tile:
-    //        sum(t) = [totals of the previous tiles] + sum_{i<=t in tile} (x_i - x_{i-W})
-    //      so one in-tile scan of (x - x_lag, x^2 - x_lag^2) gives every row's window sums.
     const int nb = T.index < P.tiles_back ? T.index : P.tiles_back;  // preceding tiles inside the window
     const bool has_lag = T.index >= P.tiles_back;
-    const int64_t tl0 = (int64_t)T.index * P.tile_rows;  // stream-local index of the tile's first row
-    const double2 invW = __ldg(P.inv_n + P.norm_window);
     for (int c = warp; c < kNF; c += kNormWarps) {
         const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
-        const double* __restrict__ xl = x - P.norm_window;
         double* __restrict__ z = out.norm + (int64_t)c * N + T.row;
-        const bool vec = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((P.norm_window & 1) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
-        // first step's loads are in flight while the predecessors' totals are awaited
-        double v[kRowsPerLane], lv[kRowsPerLane];
-        load4(x, lane * kRowsPerLane, n, vec, v);
-        if (has_lag) load4(xl, lane * kRowsPerLane, n, vec, lv);
-        else {
-#pragma unroll
-            for (int k = 0; k < kRowsPerLane; ++k) lv[k] = 0.0;
-        }
-        // totals of the (up to tiles_back) preceding tiles, one lane per predecessor, fixed reduction tree
-        double run1 = 0.0, run2 = 0.0;
-        for (int j0 = 0; j0 < nb; j0 += 32) {
-            const int j = id - nb + j0 + lane;
-            double h1 = 0.0, h2 = 0.0;
-            if (j0 + lane < nb) {
-                while (ld_flag(flags + j) < kNF) { __nanosleep(32); }
-                __threadfence();
-                h1 = __ldcg(tile_tot + (int64_t)j * 2 * kNF + c);
-                h2 = __ldcg(tile_tot + (int64_t)j * 2 * kNF + kNF + c);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                h1 += __shfl_xor_sync(0xffffffffu, h1, d);
-                h2 += __shfl_xor_sync(0xffffffffu, h2, d);
-            }
-            run1 += h1;
-            run2 += h2;
-        }
-        for (int i0 = 0; i0 < n; i0 += kStep) {
-            const int ib = i0 + lane * kRowsPerLane;
-            // software pipeline: next step's values are requested before this step's arithmetic
-            double vn[kRowsPerLane], ln[kRowsPerLane];
-            const bool more = i0 + kStep < n;
-            if (more) {
-                load4(x, ib + kStep, n, vec, vn);
-                if (has_lag) load4(xl, ib + kStep, n, vec, ln);
-            }
-            double d1[kRowsPerLane], d2[kRowsPerLane];
-            double a1 = 0.0, a2 = 0.0;
-#pragma unroll
-            for (int k = 0; k < kRowsPerLane; ++k) {
-                d1[k] = v[k] - lv[k];
-                d2[k] = v[k] * v[k] - lv[k] * lv[k];
-                a1 += d1[k];
-                a2 += d2[k];
-            }
-            double s1 = a1, s2 = a2;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double u1 = shfl_up_d(s1, d), u2 = shfl_up_d(s2, d);
-                if (lane >= d) { s1 += u1; s2 += u2; }
-            }
-            double e1 = run1 + (s1 - a1), e2 = run2 + (s2 - a2);
-            double zz[kRowsPerLane];
-#pragma unroll
-            for (int k = 0; k < kRowsPerLane; ++k) {
-                e1 += d1[k];
-                e2 += d2[k];
-                const int64_t tl = tl0 + ib + k;
-                const bool fullw = tl + 1 >= P.norm_window;
-                const int nwin = fullw ? P.norm_window : (int)(tl + 1);  // window.size(), feature_normalizer.cpp:71
-                // sum / n as sum * (1/n) with 1/n in double-double (host table): rounds like the division
-                const double2 inv = (fullw || ib + k >= n) ? invW : __ldg(P.inv_n + nwin);
-                const double m0 = e1 * inv.x;
-                const double mean = m0 + (fma(e1, inv.x, -m0) + e1 * inv.y);      // :62
-                const double q0 = e2 * inv.x;
-                const double ex2 = q0 + (fma(e2, inv.x, -q0) + e2 * inv.y);
-                const double variance = ex2 - (mean * mean);                    // :63
-                const double rstd = (variance > 0.0) ? rsqrt(variance) : 1.0;   // :67 — 1/sqrt, then multiply
-                zz[k] = (v[k] - mean) * rstd;                                   // :68
-                if (c == 0 && out.counts && ib + k < n) out.counts[(int64_t)MRP_C_NORM_N * N + T.row + ib + k] = nwin;
-            }
-            if (vec && ib + kRowsPerLane <= n) {
-                *reinterpret_cast<double2*>(z + ib) = make_double2(zz[0], zz[1]);
-                *reinterpret_cast<double2*>(z + ib + 2) = make_double2(zz[2], zz[3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < kRowsPerLane; ++k)
-                    if (ib + k < n) z[ib + k] = zz[k];
-            }
-            run1 += __shfl_sync(0xffffffffu, s1, 31);
-            run2 += __shfl_sync(0xffffffffu, s2, 31);
-            if (more) {
-#pragma unroll
-                for (int k = 0; k < kRowsPerLane; ++k) {
-                    v[k] = vn[k];
-                    lv[k] = has_lag ? ln[k] : 0.0;
-                }
-            }
-        }
+        const double* pred = tile_tot + (int64_t)(id - nb) * 2 * kNF + c;
+        int32_t* cnt_out = (c == 0 && out.counts) ? out.counts + (int64_t)MRP_C_NORM_N * N + T.row : nullptr;
+        const int al = common_align(x, z, W);
+        if (al == 32) tile_zscores<32>(x, z, n, has_lag, W, tl0, pred, nb, P.inv_cnt_norm, cnt_out, lane);
+        else if (al == 16) tile_zscores<16>(x, z, n, has_lag, W, tl0, pred, nb, P.inv_cnt_norm, cnt_out, lane);
+        else tile_zscores<8>(x, z, n, has_lag, W, tl0, pred, nb, P.inv_cnt_norm, cnt_out, lane);
+    }
+}
+
+// Rewrites the z-scores of columns that went non-finite, following the reference's running-sum arithmetic
+// (feature_normalizer.cpp:37-51,61-69):  a NaN makes sum / sum2 NaN for ever; an infinity makes sum = +-inf and
+// sum2 = +inf (variance NaN -> std 1 -> z = x - (+-inf)) until a NaN, an infinity of the other sign or its own
+// eviction W rows later turns the sums into NaN for ever.  One CTA per (stream, column); exits at once when clean.
+__global__ void k_norm_poison(const DevOutputs out, const int64_t N, const int64_t* __restrict__ row_off, const NormPoison* __restrict__ poison,
+                              const int* __restrict__ any_poison, const DevParams P) {
+    if (*any_poison == 0) return;
+    const int sidx = blockIdx.x / kNF, c = blockIdx.x % kNF;
+    const NormPoison q = poison[(int64_t)sidx * kNF + c];
+    const unsigned int none = 0xffffffffu;
+    if ((q.first_nan & q.first_pinf & q.first_ninf) == none) return;
+    const int64_t r0 = row_off[sidx], r1 = row_off[sidx + 1];
+    const int64_t n = r1 - r0;
+    const int64_t tN = q.first_nan == none ? n : q.first_nan;
+    const int64_t tP = q.first_pinf == none ? n : q.first_pinf, tM = q.first_ninf == none ? n : q.first_ninf;
+    const int64_t tI = tP < tM ? tP : tM;                 // first infinity
+    const int64_t tO = tP < tM ? tM : tP;                 // first infinity of the other sign (n if none)
+    int64_t tZ = tN;                                      // sums are NaN from here on
+    if (tI < n) {
+        if (tO < tZ) tZ = tO;
+        if (tI + P.norm_window < tZ) tZ = tI + P.norm_window;
+    }
+    const double sig_inf = tP < tM ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0xfff0000000000000ll);
+    const double* __restrict__ x = out.raw + (int64_t)c * N + r0;
+    double* __restrict__ z = out.norm + (int64_t)c * N + r0;
+    const int64_t start = tI < tZ ? tI : tZ;
+    for (int64_t t = start + threadIdx.x; t < n; t += blockDim.x) {
+        if (t >= tZ) z[t] = __longlong_as_double(0x7ff8000000000000ll);
+        else z[t] = x[t] - sig_inf;                       // mean = +-inf, std = 1
     }
 }
 
@@ -218,13 +336,26 @@ __global__ void k_normalize_faithful(const DevOutputs out, const int64_t N, cons
     }
 }
 
-cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* tiles, int ntiles, double* tile_tot,
-                             int* flags, const DevParams& P, cudaStream_t st) {
-    // flags[0..ntiles) + the ticket counter at flags[ntiles]
-    cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)ntiles + 1), st);
+size_t norm_poison_bytes(int n_streams) { return (size_t)n_streams * kNF * sizeof(NormPoison) + 16; }
+
+cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* tiles, int ntiles, double* tile_tot, int* flags,
+                             void* poison, const int64_t* row_off, int n_streams, const DevParams& P, cudaStream_t st) {
+    // the ticket counter at flags[ntiles]; tile totals preset to "unpublished"; poison table preset to "none" + the any-flag
+    cudaError_t e = cudaMemsetAsync(flags + ntiles, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_normalize<<<ntiles, kNormThreads, 0, st>>>(out, N, tiles, tile_tot, flags,
-                                                 reinterpret_cast<unsigned int*>(flags + ntiles), P);
+    e = cudaMemsetAsync(tile_tot, 0xff, (size_t)ntiles * 2 * kNF * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    const size_t pb = (size_t)n_streams * kNF * sizeof(NormPoison);
+    e = cudaMemsetAsync(poison, 0xff, pb, st);
+    if (e != cudaSuccess) return e;
+    int* any = reinterpret_cast<int*>(static_cast<unsigned char*>(poison) + pb);
+    e = cudaMemsetAsync(any, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    k_normalize<<<ntiles, kNormThreads, 0, st>>>(out, N, tiles, tile_tot, flags, reinterpret_cast<unsigned int*>(flags + ntiles),
+                                                    static_cast<NormPoison*>(poison), any, P);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_norm_poison<<<n_streams * kNF, 256, 0, st>>>(out, N, row_off, static_cast<const NormPoison*>(poison), any, P);
     return cudaGetLastError();
 }
 

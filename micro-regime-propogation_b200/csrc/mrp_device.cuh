@@ -57,7 +57,7 @@ struct DevTile {
     int32_t n;            // rows in this tile (<= tile_rows)
     int32_t index;        // tile index within the stream
     int32_t first_id;     // global id of the stream's tile 0
-    int32_t pad;
+    int32_t stream;       // stream index within the batch
 };
 
 struct DevParams {
@@ -72,7 +72,7 @@ struct DevParams {
     const double* ewm_ipow;     // [win_ring+1]    decay^-n (n <= win_span_max keeps it far from overflow)
     const double* ofi_pow;      // [257]           ofi_decay^n
     const double* stress_pow;   // [257]           stress_decay^n
-    const double2* inv_n;       // [norm_window+1] 1/n as (hi, lo) double-double; [0] unused
+    const double* inv_cnt_norm; // [norm_window+1] 1/n, [0] = 0
     const double* clog2c;       // [max(dir_window, mid_window)+2]  c*log2(c), [0] = 0
     const double* inv_cnt;      // [max(mid_window, dir_window)+2]  1/n, [0] = 0
     // window kernel: shared-memory ring entries (power of two) and the most new ticks one chunk may bring
