@@ -185,6 +185,7 @@ int setup_params(mrp_fg_ctx* c) {
     std::vector<double> tab;
     const size_t o_w = 0;
     for (int i = 0; i < p.depth_levels; ++i) tab.push_back(std::exp(-i * p.ofi_depth_decay));  // feature_processor.cpp:121
+    for (int i = 0; i < kOfiWeights; ++i) d.ofi_w[i] = std::exp(-i * p.ofi_depth_decay);
     const size_t o_e = tab.size();
     for (int n = 0; n <= d.win_ring; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
     const size_t o_ei = tab.size();

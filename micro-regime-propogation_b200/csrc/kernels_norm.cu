@@ -203,7 +203,9 @@ __device__ __forceinline__ void tile_zscores(const double* __restrict__ x, doubl
             const double u1 = shfl_up_d(s1, d), u2 = shfl_up_d(s2, d);
             if (lane >= d) { s1 += u1; s2 += u2; }
         }
-        const double b1 = run1 + (s1 - a1), b2 = run2 + (s2 - a2);
+        // exclusive offsets by shuffle, not by subtraction: a NaN in this lane's rows must not reach the rows before it
+        const double x1 = shfl_up_d(s1, 1), x2 = shfl_up_d(s2, 1);
+        const double b1 = run1 + (lane ? x1 : 0.0), b2 = run2 + (lane ? x2 : 0.0);
         double zz[kRPL];
 #pragma unroll
         for (int k = 0; k < kRPL; ++k) {

@@ -13,27 +13,37 @@ namespace mrp {
 // A segment that starts mid-stream first walks `ema_warm_rows` halo rows (only what feeds the EMAs
 // and the lag-21 midprice); 0.9^halo is below 1e-17, far under the fp64 noise of the features.
 // ------------------------------------------------------------------------------------------------
-// log(p / m) for a price p near the midprice m: the reference takes |log m - log p| of two rounded logs
-// (feature_processor.cpp:166,171), whose rounding noise (1 ulp of log m ~ 1.8e-15) is ~3e-11 of a one-tick
-// distance.  The Taylor series of log1p((p-m)/m) gives the same quantity to ~3e-16 relative for the cost of a
-// dozen fused multiply-adds instead of a full log; beyond |u| = 2^-6 it falls back to the two-log form.
-__device__ __forceinline__ double log_ratio(double p, double m, double inv_m, double log_m) {
-    const double u = (p - m) * inv_m;
-    if (fabs(u) <= 0.015625) {
-        double q = 1.0 / 11.0;
-        q = fma(q, u, -1.0 / 10.0);
-        q = fma(q, u, 1.0 / 9.0);
-        q = fma(q, u, -1.0 / 8.0);
-        q = fma(q, u, 1.0 / 7.0);
-        q = fma(q, u, -1.0 / 6.0);
-        q = fma(q, u, 1.0 / 5.0);
-        q = fma(q, u, -1.0 / 4.0);
-        q = fma(q, u, 1.0 / 3.0);
-        q = fma(q, u, -0.5);
-        q = fma(q, u, 1.0);
-        return q * u;
+// log(1 + u) by its Taylor series for |u| <= 2^-7 (truncation below 1e-16 relative).  The reference takes
+// differences of two rounded logs of nearby prices (feature_processor.cpp:33,38,166,171), whose own rounding
+// noise (1 ulp of log 5000 ~ 1.8e-15) is ~4e-11 of a one-tick distance; the series gives the exact quantity for a
+// handful of fused multiply-adds instead of two ~90-instruction logs.  Callers fall back to the two-log form
+// whenever the argument is out of range (empty side, price 0, NaN, a deep level far from the touch).
+constexpr double kSeriesMax = 0x1p-7;
+__device__ __forceinline__ double log1p_series(double u) {
+    double q = -1.0 / 8.0;
+    q = fma(q, u, 1.0 / 7.0);
+    q = fma(q, u, -1.0 / 6.0);
+    q = fma(q, u, 1.0 / 5.0);
+    q = fma(q, u, -1.0 / 4.0);
+    q = fma(q, u, 1.0 / 3.0);
+    q = fma(q, u, -0.5);
+    q = fma(q, u, 1.0);
+    return q * u;
+}
+// The row's size-weighted log distances in the reference's own form (feature_processor.cpp:164-175,186-200), for rows
+// where some level lies outside the series range (rare: empty side, NaN, a level > 0.78 % from the midprice).
+__device__ __noinline__ void lob_sums_direct(const double* __restrict__ bid_px, const double* __restrict__ ask_px,
+                                             const int32_t* __restrict__ bid_sz, const int32_t* __restrict__ ask_sz, int64_t N, int64_t r,
+                                             int L, double midp, double* bid_lw, double* ask_lw) {
+    const double log_mid = log(midp);
+    double bl = 0.0, al = 0.0;
+    for (int i = 0; i < L; ++i) {
+        const double bp = bid_px[(int64_t)i * N + r], ap = ask_px[(int64_t)i * N + r];
+        if (bp > 0) bl += fabs(log_mid - log(bp)) * bid_sz[(int64_t)i * N + r];
+        if (ap > 0) al += fabs(log(ap) - log_mid) * ask_sz[(int64_t)i * N + r];
     }
-    return log(p) - log_m;
+    *bid_lw = bl;
+    *ask_lw = al;
 }
 
 __device__ __forceinline__ double ema_scan(double b, const double* __restrict__ pw, double carry_in, double* sWarp,
@@ -57,11 +67,13 @@ __device__ __forceinline__ double ema_scan(double b, const double* __restrict__ 
     return __ldg(pw + lane + 1) * cw + v;
 }
 
-constexpr int kLevelGroup = 5;
+constexpr int kStressCache = 4;  // levels 1..4 keep their last exp(-distance*decay) per thread
 
+// LG = levels per load batch; it divides the depth L, so the level loop carries no bounds predicates.
+template <int LG>
 __global__ void __launch_bounds__(kThreads, 2)
 k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
-    __shared__ double sLM[2][kThreads], sMid[2][kThreads];
+    __shared__ double sInv[2][kThreads], sMid[2][kThreads];
     __shared__ double sWarpLiq[kWarps], sCarLiq;
     __shared__ double sWOfi[kWarps], sWSt[kWarps];
 
@@ -73,8 +85,13 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     int64_t wa = ra - P.ema_warm_rows;
     if (wa < sr0) wa = sr0;
     const int back = P.return_lag + 1;  // feature_normalizer.hpp:19-24
+    const bool want_dirs = out.bdir != nullptr;
 
     double yOfi = 0.0, ySt = 0.0;
+    // exp(-distance*decay) of the near-touch levels: on a regular tick grid the arguments repeat row after row
+    double cx[kStressCache], ce[kStressCache];
+#pragma unroll
+    for (int j = 0; j < kStressCache; ++j) { cx[j] = 0.0; ce[j] = 1.0; }
     if (tid == 0) sCarLiq = 0.0;
     int buf = 0;
     __syncthreads();
@@ -85,90 +102,122 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         const bool full = act && t >= ra;       // rows that are written (the rest only warm the EMAs)
         const bool hasprev = act && t > sr0;    // a previous snapshot exists in this stream
         const int64_t tc = act ? t : rb - 1;    // clamp loads of idle lanes
+        const bool own_prev = lane == 0 && hasprev;  // lane 0 fetches the previous row itself; the others ask their neighbour
 
         // row scalars first: one batch of independent loads
         const unsigned long long ts = in.ts[tc];
         const double buy = in.buy[tc], sell = in.sell[tc];
         const int adds = in.adds[tc];
-        unsigned long long pts = (lane == 0 && hasprev) ? in.ts[tc - 1] : 0ull;
+        unsigned long long pts = own_prev ? in.ts[tc - 1] : 0ull;
 
-        double bb = 0.0, ba = 0.0, midp = 0.0, log_mid = 0.0, inv_mid = 0.0;
+        double bb = 0.0, ba = 0.0, midp = 0.0, inv_mid = 0.0;
         double raw_ofi = 0.0, liq_b = 0.0, liq_a = 0.0;
         double bid_depth = 0.0, ask_depth = 0.0, bid_lw = 0.0, ask_lw = 0.0;
+        bool oor = false;  // some level outside the log1p series range
         double p0b = 0, p1b = 0, p0a = 0, p1a = 0;
         int s0b = 0, s1b = 0, s0a = 0, s1a = 0;
-        for (int i0 = 0; i0 < L; i0 += kLevelGroup) {
-            // all loads of a group of levels are issued before any is used (the level loop is otherwise
-            // a chain of load -> use stalls: 55 % of the kernel's cycles in the first profile)
-            double bp[kLevelGroup], ap[kLevelGroup];
-            int bs[kLevelGroup], as[kLevelGroup], pbs[kLevelGroup], pas[kLevelGroup];
+        const double* __restrict__ pbp = in.bid_px + tc;
+        const double* __restrict__ pap = in.ask_px + tc;
+        const int32_t* __restrict__ pbs = in.bid_sz + tc;
+        const int32_t* __restrict__ pas = in.ask_sz + tc;
+        int8_t* __restrict__ obd = out.bdir + tc;
+        int8_t* __restrict__ oad = out.adir + tc;
+        for (int i0 = 0; i0 < L; i0 += LG) {
+            // all loads of a batch of levels are issued before any is used
+            double bp[LG], ap[LG];
+            int bs[LG], as[LG], qbs[LG], qas[LG];
 #pragma unroll
-            for (int g = 0; g < kLevelGroup; ++g) {
-                const bool lv = i0 + g < L;
-                const int64_t o = (int64_t)(lv ? i0 + g : 0) * N + tc;
-                bp[g] = lv ? in.bid_px[o] : 0.0;
-                ap[g] = lv ? in.ask_px[o] : 0.0;
-                bs[g] = lv ? in.bid_sz[o] : 0;
-                as[g] = lv ? in.ask_sz[o] : 0;
-                // lane 0 fetches the previous row itself; the other lanes get it from their neighbour
-                pbs[g] = (lane == 0 && hasprev && lv) ? in.bid_sz[o - 1] : 0;
-                pas[g] = (lane == 0 && hasprev && lv) ? in.ask_sz[o - 1] : 0;
+            for (int g = 0; g < LG; ++g) {
+                const int64_t o = (int64_t)g * N;
+                bp[g] = pbp[o];
+                ap[g] = pap[o];
+                bs[g] = pbs[o];
+                as[g] = pas[o];
+                qbs[g] = own_prev ? pbs[o - 1] : 0;
+                qas[g] = own_prev ? pas[o - 1] : 0;
             }
             if (i0 == 0) {
                 bb = bp[0];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
                 ba = ap[0];
                 midp = (ba + bb) / 2;  // feature_processor.cpp:34,161
-                log_mid = log(midp);
                 inv_mid = 1.0 / midp;
             }
 #pragma unroll
-            for (int g = 0; g < kLevelGroup; ++g) {
+            for (int g = 0; g < LG; ++g) {
                 const int i = i0 + g;
+                // first snapshot compares with an empty book (order_book.cpp:115,168)
                 const int nbs = __shfl_up_sync(0xffffffffu, bs[g], 1), nas = __shfl_up_sync(0xffffffffu, as[g], 1);
-                if (i < L) {
-                    // first snapshot compares with an empty book (order_book.cpp:115,168)
-                    const int qb = hasprev ? (lane == 0 ? pbs[g] : nbs) : 0;
-                    const int qa = hasprev ? (lane == 0 ? pas[g] : nas) : 0;
-                    const int bd = (bs[g] > qb) - (bs[g] < qb);  // order_book.cpp:208-239
-                    const int ad = (as[g] > qa) - (as[g] < qa);
-                    if (full && out.bdir) {
-                        const int64_t o = (int64_t)i * N + tc;
-                        out.bdir[o] = (int8_t)bd;
-                        out.adir[o] = (int8_t)ad;
-                    }
-                    const double w = __ldg(P.ofi_weight + i);  // exp(-i*0.5), feature_processor.cpp:121
-                    const double bid_contrib = (double)(bd * bs[g]) * w;
-                    const double ask_contrib = (double)(ad * as[g]) * w;
-                    raw_ofi += bid_contrib - ask_contrib;      // :125
-                    if (i < P.stress_levels) {                 // :282-299
-                        // exp(-dist*decay): level 0 has dist == 0 exactly (weight 1); on a contiguous book both
-                        // sides share the argument, so one exp serves both
+                const int qb = hasprev ? (lane == 0 ? qbs[g] : nbs) : 0;
+                const int qa = hasprev ? (lane == 0 ? qas[g] : nas) : 0;
+                const int bd = (bs[g] > qb) - (bs[g] < qb);  // order_book.cpp:208-239
+                const int ad = (as[g] > qa) - (as[g] < qa);
+                if (want_dirs && full) {
+                    obd[(int64_t)g * N] = (int8_t)bd;
+                    oad[(int64_t)g * N] = (int8_t)ad;
+                }
+                const double w = i < kOfiWeights ? P.ofi_w[i < kOfiWeights ? i : 0] : __ldg(P.ofi_weight + i);  // exp(-i*0.5), :121
+                const double bid_contrib = (double)(bd * bs[g]) * w;   // (int8 * int) * double, as the reference
+                const double ask_contrib = (double)(ad * as[g]) * w;
+                raw_ofi += bid_contrib - ask_contrib;      // :125
+                const double fbs = (double)bs[g], fas = (double)as[g];
+                if (i < P.stress_levels && (i == 0 || i > kStressCache || i0 != 0)) {   // :282-299 (levels 1..kStressCache of
+                    const bool ub = bp[g] > 0.0 && fbs >= P.stress_min_size;              //  the first batch: cached, below)
+                    const bool ua = ap[g] > 0.0 && fas >= P.stress_min_size;
+                    if (i == 0) {  // distance 0 exactly: weight 1
+                        if (ub) liq_b += fbs;
+                        if (ua) liq_a += fas;
+                    } else {
                         const double xb = -(bb - bp[g]) * P.stress_distance_decay, xa = -(ap[g] - ba) * P.stress_distance_decay;
-                        const double eb = (i == 0) ? 1.0 : exp(xb);
-                        const double ea = (i == 0) ? 1.0 : ((xa == xb) ? eb : exp(xa));
-                        if (bp[g] > 0.0 && (double)bs[g] >= P.stress_min_size) liq_b += eb * bs[g];
-                        if (ap[g] > 0.0 && (double)as[g] >= P.stress_min_size) liq_a += ea * as[g];
+                        if (ub) liq_b += exp(xb) * fbs;
+                        if (ua) liq_a += exp(xa) * fas;
                     }
-                    if (i == 0) { p0b = bp[g]; p0a = ap[g]; s0b = bs[g]; s0a = as[g]; }
-                    if (i == 1) { p1b = bp[g]; p1a = ap[g]; s1b = bs[g]; s1a = as[g]; }
-                    if (full) {                                // :164-175, :189-200
-                        if (bp[g] > 0) {
-                            bid_lw += fabs(log_ratio(bp[g], midp, inv_mid, log_mid)) * bs[g];  // |log mid - log bp|
-                            bid_depth += bs[g];
+                }
+                if (i == 0) { p0b = bp[g]; p0a = ap[g]; s0b = bs[g]; s0a = as[g]; }
+                if (i == 1) { p1b = bp[g]; p1a = ap[g]; s1b = bs[g]; s1a = as[g]; }
+                {   // :164-175, :189-200 — branch-free: out-of-range arguments only raise the row's flag
+                    const double ub_ = (bp[g] - midp) * inv_mid, ua_ = (ap[g] - midp) * inv_mid;
+                    const bool hb = bp[g] > 0, ha = ap[g] > 0;
+                    oor |= (hb && !(fabs(ub_) <= kSeriesMax)) || (ha && !(fabs(ua_) <= kSeriesMax));
+                    const double lb = fabs(log1p_series(ub_)), la = fabs(log1p_series(ua_));
+                    bid_lw += hb ? lb * fbs : 0.0;   // |log mid - log bp| * size
+                    ask_lw += ha ? la * fas : 0.0;   // |log ap - log mid| * size
+                    bid_depth += hb ? fbs : 0.0;
+                    ask_depth += ha ? fas : 0.0;
+                }
+            }
+            if (i0 == 0) {
+                // near-touch liquidity weights exp(-distance*decay) of levels 1..kStressCache (:282-299): on a regular tick
+                // grid the arguments repeat row after row, so each thread remembers its last bid-side argument per level
+                // and the ask side shares it when the book is symmetric
+#pragma unroll
+                for (int j = 0; j < kStressCache; ++j) {
+                    constexpr int kTop = LG - 1;
+                    const int g = j + 1 < kTop ? j + 1 : kTop;   // == j + 1 whenever the level exists in this batch
+                    if (j + 1 < LG && j + 1 < P.stress_levels) {
+                        const double fbs = (double)bs[g], fas = (double)as[g];
+                        const bool ub = bp[g] > 0.0 && fbs >= P.stress_min_size;
+                        const bool ua = ap[g] > 0.0 && fas >= P.stress_min_size;
+                        const double xb = -(bb - bp[g]) * P.stress_distance_decay, xa = -(ap[g] - ba) * P.stress_distance_decay;
+                        if (ub) {
+                            if (xb != cx[j]) { cx[j] = xb; ce[j] = exp(xb); }
+                            liq_b += ce[j] * fbs;
                         }
-                        if (ap[g] > 0) {
-                            ask_lw += fabs(log_ratio(ap[g], midp, inv_mid, log_mid)) * as[g];  // |log ap - log mid|
-                            ask_depth += as[g];
-                        }
+                        if (ua) liq_a += ((xa == cx[j]) ? ce[j] : exp(xa)) * fas;
                     }
                 }
             }
+            pbp += (int64_t)LG * N;
+            pap += (int64_t)LG * N;
+            pbs += (int64_t)LG * N;
+            pas += (int64_t)LG * N;
+            obd += (int64_t)LG * N;
+            oad += (int64_t)LG * N;
         }
-        const double log_bb = log(bb), log_ba = log(ba);
+        if (oor && full) lob_sums_direct(in.bid_px, in.ask_px, in.bid_sz, in.ask_sz, N, tc, L, midp, &bid_lw, &ask_lw);
         const double liq = liq_b + liq_a;  // :301
 
         // neighbours: previous row's liquidity, timestamp; lag-21 midprice through shared memory
-        sLM[buf][tid] = log_mid;
+        sInv[buf][tid] = inv_mid;
         sMid[buf][tid] = midp;
         if (lane == 31) sWarpLiq[warp] = liq;
         {
@@ -181,11 +230,11 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         if (lane == 0) pliq = warp == 0 ? sCarLiq : sWarpLiq[warp - 1];
         if (!hasprev) pliq = 0.0;  // cache_.prev_liquidity starts at 0 (feature_processor.hpp:27)
         // lag-(return_lag+1) midprice: read NOW (two barriers separate this read from the next chunk's writes)
-        double old_mid, old_lm;
+        double old_mid, old_inv;
         {
             const int j = tid - back;
             old_mid = j >= 0 ? sMid[buf][j] : sMid[buf ^ 1][kThreads + j];
-            old_lm = j >= 0 ? sLM[buf][j] : sLM[buf ^ 1][kThreads + j];
+            old_inv = j >= 0 ? sInv[buf][j] : sInv[buf ^ 1][kThreads + j];
         }
 
         const double total_volume = buy + sell;                                               // :129
@@ -201,11 +250,21 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         if (tid == kThreads - 1) sCarLiq = liq;
 
         if (full) {
+            // log_spread = log(ask0) - log(bid0), :33
+            double log_spread;
+            {
+                const double u = (ba - bb) / bb;
+                if (bb > 0.0 && fabs(u) <= kSeriesMax) log_spread = log1p_series(u);
+                else log_spread = log(ba) - log(bb);
+            }
             // log_return, :37-42: the normaliser deque holds min(t, W) earlier rows when row t asks for index `lag`
             const int64_t tl = t - sr0;
             const int64_t have = tl < P.norm_window ? tl : P.norm_window;
             double log_ret = 0.0;
-            if ((int64_t)P.return_lag < have && old_mid > 0.0) log_ret = log_mid - old_lm;
+            if ((int64_t)P.return_lag < have && old_mid > 0.0) {
+                const double u = (midp - old_mid) * old_inv;
+                log_ret = fabs(u) <= kSeriesMax ? log1p_series(u) : log(midp) - log(old_mid);
+            }
             double rate = 0.0;  // :143-151
             if (pts > 0ull) {
                 const unsigned long long delta_ns = ts - pts;
@@ -219,7 +278,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
             const double ga = (p0a * s0a - p1a * s1a) / (double)(s0a + s1a);
             double* raw = out.raw + t;
             raw[(int64_t)MRP_F_MIDPRICE * N] = midp;
-            raw[(int64_t)MRP_F_LOG_SPREAD * N] = log_ba - log_bb;                   // :33
+            raw[(int64_t)MRP_F_LOG_SPREAD * N] = log_spread;
             raw[(int64_t)MRP_F_LOG_RETURN * N] = log_ret;
             raw[(int64_t)MRP_F_OFI * N] = ofi;
             raw[(int64_t)MRP_F_SIGNED_VOLUME_PRESSURE * N] = (total_volume > 0.0) ? (buy - sell) / total_volume : 0.0;  // :137-140
@@ -235,7 +294,11 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
 
 cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
                         const DevParams& P, cudaStream_t st) {
-    k_book<<<nseg, kThreads, 0, st>>>(in, out, segs, P);
+    const int L = P.L;
+    if (L % 5 == 0) k_book<5><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
+    else if (L % 4 == 0) k_book<4><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
+    else if (L % 2 == 0) k_book<2><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
+    else k_book<1><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
     return cudaGetLastError();
 }
 

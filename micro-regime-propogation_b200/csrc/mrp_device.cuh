@@ -60,6 +60,8 @@ struct DevTile {
     int32_t stream;       // stream index within the batch
 };
 
+constexpr int kOfiWeights = 16;
+
 struct DevParams {
     int32_t L, mid_window, dir_window, spread_divisor, norm_window, return_lag, stress_levels;
     int32_t emit_counts;
@@ -68,6 +70,7 @@ struct DevParams {
     double ofi_alpha, ofi_decay, ofi_min_total_vol;
     double stress_alpha, stress_decay, stress_min_size, stress_distance_decay;
     const double* ofi_weight;   // [L]  exp(-i*depth_decay), computed by the host libm
+    double ofi_w[kOfiWeights];  // the first weights again, as kernel-parameter constants
     const double* ewm_pow;      // [win_ring+1]    decay^n
     const double* ewm_ipow;     // [win_ring+1]    decay^-n (n <= win_span_max keeps it far from overflow)
     const double* ofi_pow;      // [257]           ofi_decay^n
