@@ -55,7 +55,10 @@ def build_host(force: bool = False) -> str:
     """C++20 host adaptor + validation tool (links against libmrp_fg.so)."""
     mk = os.path.join(HOST, "Makefile")
     if os.path.exists(mk):
-        subprocess.run(["make", "-C", HOST] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL)
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        subprocess.run(["make", "-C", HOST] + (["-B"] if force else []), check=True, stdout=subprocess.DEVNULL, env=env)
     return HOST
 
 

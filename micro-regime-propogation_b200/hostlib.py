@@ -1,0 +1,61 @@
+"""ctypes view of host/libmrp_host.so — the C++20 adaptor (GpuFeatureProcessor, CsvWriter) driven from Python by
+the tests and the validation harness.  The library itself is the product's host side; this file adds nothing to it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .cabi import HostView, SoaView
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(HERE, "host", "libmrp_host.so")
+
+_lib = None
+
+
+def load_host() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} not found: build it with `make -C micro-regime-propogation_b200/host`")
+        lib = C.CDLL(HOST_LIB_PATH)
+        lib.mrp_host_last_error.restype = C.c_char_p
+        lib.mrp_host_write_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int]
+        lib.mrp_host_features_to_csv.argtypes = [C.POINTER(SoaView), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64,
+                                                 C.c_uint64, C.c_int, C.c_int]
+        _lib = lib
+    return _lib
+
+
+def csv_directory(project_root: str, interval_ns: int, date: str, window: int = 30000, events: int = 1500) -> str:
+    return os.path.join(project_root, "data", "output_Snapshot%f_Window%d_Events%d" % (interval_ns / 1e9, window, events), date)
+
+
+def write_csv(project_root: str, base_filename: str, interval_ns: int, date: str, instrument: str, grid_ts: np.ndarray,
+              raw: np.ndarray, norm: np.ndarray, row_ts: Optional[np.ndarray] = None, bulk: bool = False) -> str:
+    lib = load_host()
+    grid_ts = np.ascontiguousarray(grid_ts, dtype=np.uint64)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    norm = np.ascontiguousarray(norm, dtype=np.float64)
+    rts = np.ascontiguousarray(row_ts, dtype=np.uint64) if row_ts is not None else None
+    rc = lib.mrp_host_write_csv(project_root.encode(), base_filename.encode(), interval_ns, date.encode(), instrument.encode(),
+                                raw.shape[1], grid_ts.ctypes.data, rts.ctypes.data if rts is not None else None,
+                                raw.ctypes.data, norm.ctypes.data, int(bulk))
+    if rc != 0:
+        raise RuntimeError(lib.mrp_host_last_error().decode())
+    return csv_directory(project_root, interval_ns, date)
+
+
+def features_to_csv(hv: HostView, project_root: str, base_filename: str, date: str, instrument: str, first_grid_ns: int,
+                    interval_ns: int, device: int = 0, bulk: bool = False) -> str:
+    """Stage one stream through microregime::GpuFeatureProcessor (ticks, trades and snapshots in event order), run the
+    GPU pass and write the reference-layout CSV files.  Raises when no GPU is present (no CPU fallback)."""
+    lib = load_host()
+    rc = lib.mrp_host_features_to_csv(C.byref(hv.view), project_root.encode(), base_filename.encode(), date.encode(),
+                                      instrument.encode(), first_grid_ns, interval_ns, device, int(bulk))
+    if rc != 0:
+        raise RuntimeError(lib.mrp_host_last_error().decode())
+    return csv_directory(project_root, interval_ns, date)

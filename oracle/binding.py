@@ -23,7 +23,10 @@ REF_L50_SO = os.path.join(HERE, "_ref", "libmrp_ref_L50.so")
 
 def build(quiet: bool = True) -> None:
     """(Re)build the checkers with oracle/Makefile (reference part only if /root/reference exists)."""
-    subprocess.run(["make", "-C", HERE, "all"], check=True,
+    env = dict(os.environ)
+    env.pop("CC", None)   # the image's CC/CXX wrappers lack libgomp: the Makefile names the PATH compilers itself
+    env.pop("CXX", None)
+    subprocess.run(["make", "-C", HERE, "all"], check=True, env=env,
                    stdout=subprocess.DEVNULL if quiet else None)
 
 
@@ -96,3 +99,37 @@ def run_reference(hv: HostView, trade_size: Optional[np.ndarray] = None, use_boo
     if rc != 0:
         raise RuntimeError(f"mrp_ref_run failed ({rc})")
     return out
+
+
+# ---- the reference's own CsvWriter (oracle/_ref/libmrp_refcsv.so, built from features_to_csv.cpp where it lies)
+REF_CSV_SO = os.path.join(HERE, "_ref", "libmrp_refcsv.so")
+
+
+def ref_csv_available() -> bool:
+    return os.path.exists(REF_CSV_SO)
+
+
+def ref_write_csv(project_root: str, base_filename: str, interval_ns: int, date: str, instrument: str,
+                  grid_ts: np.ndarray, row_ts: np.ndarray, raw: np.ndarray, norm: np.ndarray) -> str:
+    """Format rows with the UNMODIFIED reference CsvWriter; returns the directory it wrote into."""
+    lib = C.CDLL(REF_CSV_SO)
+    lib.mrp_ref_write_csv.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int64] + [C.c_void_p] * 4
+    grid_ts = np.ascontiguousarray(grid_ts, dtype=np.uint64)
+    row_ts = np.ascontiguousarray(row_ts, dtype=np.uint64)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    norm = np.ascontiguousarray(norm, dtype=np.float64)
+    n = raw.shape[1]
+    old = os.environ.get("MRP_REF_PROJECT_ROOT")
+    os.environ["MRP_REF_PROJECT_ROOT"] = project_root
+    try:
+        rc = lib.mrp_ref_write_csv(base_filename.encode(), interval_ns, date.encode(), instrument.encode(), n,
+                                   _ptr(grid_ts), _ptr(row_ts), _ptr(raw), _ptr(norm))
+    finally:
+        if old is None:
+            os.environ.pop("MRP_REF_PROJECT_ROOT", None)
+        else:
+            os.environ["MRP_REF_PROJECT_ROOT"] = old
+    if rc != 0:
+        raise RuntimeError(f"mrp_ref_write_csv failed ({rc})")
+    secs = "%f" % (interval_ns / 1e9)
+    return os.path.join(project_root, "data", f"output_Snapshot{secs}_Window30000_Events1500", date)

@@ -23,4 +23,8 @@ def _built():
         b.build_cuda()
     if not os.path.exists(ob.ORACLE_SO):
         ob.build()
+    from mrp_b200 import hostlib
+
+    if not os.path.exists(hostlib.HOST_LIB_PATH):
+        b.build_host()
     yield

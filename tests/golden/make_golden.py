@@ -69,5 +69,35 @@ def main():
         print(name, spec.n_rows, "rows ->", len(idx), "kept;", os.path.getsize(os.path.join(HERE, name + ".npz")) >> 10, "KiB")
 
 
+def main_csv():
+    """Golden CSV files: the reference's own CsvWriter (features_to_csv.cpp) formatting the reference's own features."""
+    import shutil
+    import tempfile
+
+    spec = synth.SynthSpec(n_rows=64, seed=105, warm_trades=0, max_trades_per_row=1, warm_ticks=3)
+    batch = synth.to_numpy(synth.make_batch([spec]))
+    hv = mrp_b200.HostView(batch)
+    ref = ob.run_reference(hv, batch["trade_size"], use_book=True)
+    raw, norm = ref["raw"].copy(), ref["norm"].copy()
+    # a few special values the formatter must spell like the reference's stream does
+    raw[7, 5], raw[7, 6], raw[8, 5], raw[9, 5], raw[10, 5] = np.inf, -np.inf, -0.0, 4.9e-324, 1.7976931348623157e308
+    raw[11, 6], raw[12, 6] = np.nan, np.copysign(np.nan, -1.0)
+    norm[3, 9], norm[4, 9] = np.copysign(np.nan, -1.0), 1e-300
+    grid = (1_746_453_700_000_000_000 + np.arange(spec.n_rows, dtype=np.uint64) * np.uint64(500_000_000)).astype(np.uint64)
+    out = os.path.join(HERE, "csv")
+    os.makedirs(out, exist_ok=True)
+    tmp = tempfile.mkdtemp()
+    try:
+        d = ob.ref_write_csv(tmp, "base_SYN", 500_000_000, "20250505", "SYN", grid, batch["ts_ns"], raw, norm)
+        for f in ("base_SYN_raw.csv", "base_SYN_norm.csv"):
+            shutil.copy(os.path.join(d, f), os.path.join(out, f))
+        np.savez_compressed(os.path.join(out, "values.npz"), raw=raw, norm=norm, grid=grid, row_ts=batch["ts_ns"],
+                            rel_dir=os.path.relpath(d, tmp))
+        print("csv golden:", os.path.relpath(d, tmp), os.path.getsize(os.path.join(out, "base_SYN_raw.csv")), "bytes")
+    finally:
+        shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
     main()
+    main_csv()
