@@ -41,6 +41,15 @@ def algorithmic_bytes_per_row(levels: int, m: int, q: float) -> float:
     return 340 + 24 * levels + 16 * m + q
 
 
+def ncu_traffic_per_row():
+    """DRAM bytes per row and kernel from the committed `ncu --set full` captures (profiles/ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -177,7 +186,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=FULL_ROWS, help="snapshot rows per GPU (default: the 50 M-row config)")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows for the host-buffer end-to-end leg (0 = same as --rows if host memory allows)")
-    ap.add_argument("--ref-rows", type=int, default=12000, help="rows per stream of the CPU sample")
+    ap.add_argument("--ref-rows", type=int, default=200000, help="rows per stream of the CPU sample (about 15 s per host thread)")
+    ap.add_argument("--timeshard", action="store_true", help="BASELINE.json configs[4]: ONE stream of rows*N snapshots split by time across the N ranks (halo over NVLink)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -205,16 +215,69 @@ def main():
 
     # ---- synthetic instrument-day, generated on the device (never crosses PCIe)
     rows = args.rows
-    spec = synth.SynthSpec(n_rows=rows, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + rank)
-    batch = synth.make_batch([spec], device=dev)
+    step_pre = None   # per-step work ahead of the kernels (time-sharded mode: the halo exchange)
+    skip = 0
+    if args.timeshard and world > 1:
+        # ONE stream of rows*world snapshots; every rank keeps only its time slice (+ the halo its left neighbour sends)
+        from mrp_b200 import timeshard as tsh
+
+        total = rows * world
+        if total > 120_000_000:
+            raise SystemExit("--timeshard generates the whole stream on every rank before slicing it: use --rows <= 120e6 / N")
+        spec = synth.SynthSpec(n_rows=total, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED)
+        full = synth.make_batch([spec], device=dev)
+        full.pop("trade_size", None)
+        r0, r1 = tsh.shard_bounds(total, world, rank)
+        shard = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in tsh.shard_of(full, r0, r1).items()}
+        del full
+        torch.cuda.empty_cache()
+        H = tsh.halo_rows()
+        halo = tsh.exchange_halo(shard, rank, world, H)
+        batch, skip = tsh.extend(shard, halo)
+        tail = tsh.tail_for_right(shard, H) if rank + 1 < world else None
+        hk, hj = (halo["mid"].shape[0], halo["trade_dir"].shape[0]) if halo is not None else (0, 0)
+        t_base, j_base = (halo["tick0"], halo["trade0"]) if halo is not None else (0, 0)
+        del shard, halo
+
+        def step_pre():
+            # the per-step exchange: pack the tail, NVLink P2P, unpack into the front of the extended arrays
+            ops, tmp = [], {}
+            if tail is not None:
+                for k in tsh._ALL:
+                    ops.append(dist.P2POp(dist.isend, tail[k], rank + 1))
+            if rank > 0:
+                for k in tsh._ALL:
+                    n = hk if k in tsh.TICK_KEYS else (hj if k in tsh.TRADE_KEYS else skip)
+                    shape = (LEVELS, n) if k in tsh.ROW_KEYS_2D else (n,)
+                    tmp[k] = torch.empty(shape, dtype=batch[k].dtype, device=dev)
+                    ops.append(dist.P2POp(dist.irecv, tmp[k], rank - 1))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            for k, v in tmp.items():
+                if k == "tick_cursor":
+                    v = (v.to(torch.int64) - t_base).to(batch[k].dtype)
+                elif k == "trade_cursor":
+                    v = (v.to(torch.int64) - j_base).to(batch[k].dtype)
+                batch[k][..., :v.shape[-1]].copy_(v)
+    else:
+        spec = synth.SynthSpec(n_rows=rows, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + rank)
+        batch = synth.make_batch([spec], device=dev)
     n_ticks, n_trades = batch["tick_offsets"][-1], batch["trade_offsets"][-1]
-    q = n_trades / rows
-    m_eff = n_ticks / rows
+    q = n_trades / (batch["row_offsets"][-1])
+    m_eff = n_ticks / (batch["row_offsets"][-1])
     torch.cuda.synchronize()
 
     eng = mrp_b200.Engine(mrp_b200.default_params(), device=local_rank)
     eng.bind_device(batch)
     stream = torch.cuda.current_stream().cuda_stream
+    _run = eng.run
+
+    def run_step(st):
+        if step_pre is not None:
+            step_pre()
+        _run(st)
+
+    eng.run = run_step
 
     def barrier():
         if world > 1:
@@ -254,7 +317,7 @@ def main():
     value = rows * world / (ms_per_step * 1e-3)
 
     # ---- the one collective on this path: global column moments (19 x {n, sum, sum^2})
-    mom = torch.from_numpy(eng.moments(stream)).to(dev)
+    mom = torch.from_numpy(eng.moments(stream)).to(dev)   # (time-sharded mode: halo rows are counted twice; diagnostic only)
     if world > 1:
         dist.all_reduce(mom, op=dist.ReduceOp.SUM)
     mom = mom.cpu().numpy()
@@ -273,9 +336,13 @@ def main():
     }
     dom = max(kt, key=kt.get)
     whole_gbs = rows * bytes_row / (ms_per_step * 1e-3) / 1e9
+    tr = ncu_traffic_per_row()
+    traffic = tr["dram_bytes_per_row"][dom] * rows if tr and dom in tr.get("dram_bytes_per_row", {}) else None
     roof = {
         "bound": "hbm", "kernel": dom, "achieved": kb[dom] / (kt[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": kb[dom] / (kt[dom] * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "frac": kb[dom] / (kt[dom] * 1e-3) / 1e9 / peak, "traffic": traffic,
+        "traffic_source": (tr["source"] + " (per-row DRAM bytes of that capture x rows of this run)") if traffic else None,
+        "algorithmic_bytes": kb[dom], "peak_source": peak_src,
         "whole_pass": {"bytes_per_row": bytes_row, "achieved": whole_gbs, "frac": whole_gbs / peak},
         "kernels_ms": kt,
         "kernels_gbs": {k: kb[k] / (kt[k] * 1e-3) / 1e9 for k in kt},
@@ -283,7 +350,7 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not (args.timeshard and world > 1):
         e2e_rows = args.e2e_rows or rows
         try:
             import psutil
@@ -360,7 +427,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"single instrument-day per GPU, {rows} snapshots x {LEVELS} levels, {m_eff:.2f} ticks and {q:.2f} trades per snapshot"
                                    + (" (BASELINE.json configs[1])" if rows == FULL_ROWS else " (REDUCED rows: not the headline config)"),
-                       "rows_per_gpu": rows, "levels": LEVELS, "sharding": "instrument-day per GPU, no data-path collective",
+                       "rows_per_gpu": rows, "levels": LEVELS,
+                       "sharding": ("ONE stream split by time; per step each rank sends its last %d rows (+ window of ticks / trades) to its right "
+                                    "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % skip)
+                       if (args.timeshard and world > 1) else "instrument-day per GPU, no data-path collective",
                        "l2": "inputs (>= 20 GB at 50 M rows) far exceed the 126 MB L2; no explicit flush"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "global_moments_midprice": [float(x) for x in mom[0]],

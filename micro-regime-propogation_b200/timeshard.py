@@ -1,0 +1,150 @@
+"""Time-sharding of ONE long stream across ranks (BASELINE.json configs[4]: a 400 M-snapshot stream over 8 B200).
+
+Rank g owns the snapshot rows [r0, r1) of the stream and the ticks / trades that arrive during those rows.  Every state
+of the feature path has finite memory (30 000 rows for the z-score window, 21 rows for the log return,
+1 row for the book-delta directions and the arrival rate, 1800 ticks, 1500 trades, EMAs that forget to < 1e-17 in 372 rows),
+so a rank reproduces its rows exactly from its own slice plus a HALO taken from its left neighbour:
+
+    rows   : the last  H = norm_window + ema_warm + 32  rows of the neighbour (inputs, not features: recomputing the
+             neighbour's last 30 000 raw feature rows costs 0.06 % extra work at 50 M rows per GPU and needs no second
+             exchange step and no extra kernel entry point)
+    ticks  : from (tick cursor of the halo's first row) - max(mid_window, dir_window + 1) - 2
+    trades : from (trade cursor of the halo's first row) - dir_window - 2
+
+The halo travels peer to peer (torch.distributed send / recv: NCCL over NVLink on the GPU box, gloo in the CPU tests);
+the extended slice is then handed to the engine as an ordinary stream whose cursors are rebased to the slice, and the
+first `skip` rows of the outputs are dropped.  The only collective is the all-reduce of the global column moments.
+This module is host-side plumbing: it contains no feature arithmetic.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+ROW_KEYS_1D = ("ts_ns", "buy_vol", "sell_vol", "adds", "tick_cursor", "trade_cursor")
+ROW_KEYS_2D = ("bid_px", "ask_px", "bid_sz", "ask_sz")
+TICK_KEYS = ("mid", "spread")
+TRADE_KEYS = ("trade_dir",)
+
+
+def ema_warm_rows(ofi_alpha: float = 0.2, stress_alpha: float = 0.1, return_lag: int = 20) -> int:
+    """Rows after which both EMAs have forgotten their start (decay^rows < 1e-17), as the kernels size their own halo."""
+    slow = max(1.0 - ofi_alpha, 1.0 - stress_alpha)
+    warm = max(int(math.ceil(math.log(1e-17) / math.log(slow))), return_lag + 1)
+    return ((warm + 255) // 256) * 256
+
+
+def halo_rows(norm_window: int = 30000, ofi_alpha: float = 0.2, stress_alpha: float = 0.1, return_lag: int = 20) -> int:
+    return norm_window + ema_warm_rows(ofi_alpha, stress_alpha, return_lag) + 32
+
+
+def shard_bounds(n_rows: int, world: int, rank: int):
+    """Contiguous, near-equal row ranges."""
+    base, rem = divmod(n_rows, world)
+    r0 = rank * base + min(rank, rem)
+    return r0, r0 + base + (1 if rank < rem else 0)
+
+
+def shard_of(batch: Dict[str, object], r0: int, r1: int) -> Dict[str, object]:
+    """Cut the rows [r0, r1) of a single-stream batch (global cursors kept) together with the ticks / trades that
+    arrive during those rows.  Used by the tests and the benchmark to play the role of "what this rank holds"."""
+    kc, jc = batch["tick_cursor"], batch["trade_cursor"]
+    n = int(kc.shape[0])
+    t0 = int(kc[r0 - 1]) if r0 > 0 else 0
+    j0 = int(jc[r0 - 1]) if r0 > 0 else 0
+    t1 = int(kc[r1 - 1]) if r1 < n else int(batch["mid"].shape[0])
+    j1 = int(jc[r1 - 1]) if r1 < n else int(batch["trade_dir"].shape[0])
+    out: Dict[str, object] = {"row0": r0, "tick0": t0, "trade0": j0, "n_rows_total": n}
+    for k in ROW_KEYS_1D:
+        out[k] = batch[k][r0:r1]
+    for k in ROW_KEYS_2D:
+        out[k] = batch[k][:, r0:r1]
+    for k in TICK_KEYS:
+        out[k] = batch[k][t0:t1]
+    for k in TRADE_KEYS:
+        out[k] = batch[k][j0:j1]
+    return out
+
+
+def tail_for_right(shard: Dict[str, object], H: int, mid_window: int = 1800, dir_window: int = 1500) -> Dict[str, object]:
+    """What this rank sends to its right neighbour: its last H rows and the ticks / trades those rows can see."""
+    n = int(shard["tick_cursor"].shape[0])
+    if n < H:
+        raise ValueError(f"a time shard must hold at least {H} rows (has {n}): the halo comes from ONE neighbour")
+    a = n - H
+    wmax = max(mid_window, dir_window + 1)
+    t_need = max(0, int(shard["tick_cursor"][a]) - wmax - 2)
+    j_need = max(0, int(shard["trade_cursor"][a]) - dir_window - 2)
+    if (t_need < shard["tick0"] and shard["tick0"] > 0) or (j_need < shard["trade0"] and shard["trade0"] > 0):
+        raise ValueError("the shard does not hold enough ticks / trades before its halo rows; use longer shards")
+    t_need, j_need = max(t_need, shard["tick0"]), max(j_need, shard["trade0"])
+    out: Dict[str, object] = {"row0": shard["row0"] + a, "tick0": t_need, "trade0": j_need}
+    for k in ROW_KEYS_1D:
+        out[k] = shard[k][a:].contiguous()
+    for k in ROW_KEYS_2D:
+        out[k] = shard[k][:, a:].contiguous()
+    for k in TICK_KEYS:
+        out[k] = shard[k][t_need - shard["tick0"]:].contiguous()
+    for k in TRADE_KEYS:
+        out[k] = shard[k][j_need - shard["trade0"]:].contiguous()
+    return out
+
+
+def extend(shard: Dict[str, object], halo: Optional[Dict[str, object]]):
+    """halo + shard as ONE engine stream: cursors rebased to the slice, host offsets, and the rows to skip on output."""
+    if halo is None:
+        ext = dict(shard)
+        skip = 0
+    else:
+        assert halo["row0"] + int(halo["tick_cursor"].shape[0]) == shard["row0"], "halo and shard rows are not adjacent"
+        ext = {"row0": halo["row0"], "tick0": halo["tick0"], "trade0": halo["trade0"]}
+        for k in ROW_KEYS_1D:
+            ext[k] = torch.cat([halo[k], shard[k]])
+        for k in ROW_KEYS_2D:
+            ext[k] = torch.cat([halo[k], shard[k]], dim=1).contiguous()
+        for k in TICK_KEYS + TRADE_KEYS:
+            ext[k] = torch.cat([halo[k], shard[k]])
+        skip = int(halo["tick_cursor"].shape[0])
+    out = {k: ext[k] for k in ROW_KEYS_1D + ROW_KEYS_2D + TICK_KEYS + TRADE_KEYS}
+    out["tick_cursor"] = (ext["tick_cursor"].to(torch.int64) - ext["tick0"]).to(ext["tick_cursor"].dtype)
+    out["trade_cursor"] = (ext["trade_cursor"].to(torch.int64) - ext["trade0"]).to(ext["trade_cursor"].dtype)
+    out["row_offsets"] = [0, int(out["tick_cursor"].shape[0])]
+    out["tick_offsets"] = [0, int(out["mid"].shape[0])]
+    out["trade_offsets"] = [0, int(out["trade_dir"].shape[0])]
+    return out, skip
+
+
+_META = ("row0", "tick0", "trade0")
+_ALL = ROW_KEYS_1D + ROW_KEYS_2D + TICK_KEYS + TRADE_KEYS
+
+
+def exchange_halo(shard: Dict[str, object], rank: int, world: int, H: int, mid_window: int = 1800, dir_window: int = 1500):
+    """Neighbour exchange: every rank but the last sends its tail to rank + 1; every rank but the first receives.
+    Returns the received halo (None on rank 0).  Uses the default process group (NCCL -> NVLink P2P, or gloo)."""
+    import torch.distributed as dist
+
+    dev = shard["mid"].device
+    ops, recv = [], None
+    if rank + 1 < world:
+        tail = tail_for_right(shard, H, mid_window, dir_window)
+        meta = torch.tensor([tail[m] for m in _META] + [tail[k].shape[-1] for k in _ALL], dtype=torch.int64, device=dev)
+        dist.send(meta, rank + 1)
+        for k in _ALL:
+            ops.append(dist.P2POp(dist.isend, tail[k], rank + 1))
+    if rank > 0:
+        meta = torch.empty(len(_META) + len(_ALL), dtype=torch.int64, device=dev)
+        dist.recv(meta, rank - 1)
+        meta = [int(x) for x in meta.tolist()]
+        recv = {m: meta[i] for i, m in enumerate(_META)}
+        L = shard["bid_px"].shape[0]
+        for i, k in enumerate(_ALL):
+            n = meta[len(_META) + i]
+            shape = (L, n) if k in ROW_KEYS_2D else (n,)
+            recv[k] = torch.empty(shape, dtype=shard[k].dtype, device=dev)
+            ops.append(dist.P2POp(dist.irecv, recv[k], rank - 1))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return recv
