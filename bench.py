@@ -429,7 +429,7 @@ def main():
                                    + (" (BASELINE.json configs[1])" if rows == FULL_ROWS else " (REDUCED rows: not the headline config)"),
                        "rows_per_gpu": rows, "levels": LEVELS,
                        "sharding": ("ONE stream split by time; per step each rank sends its last %d rows (+ window of ticks / trades) to its right "
-                                    "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % skip)
+                                    "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % tsh.halo_rows())
                        if (args.timeshard and world > 1) else "instrument-day per GPU, no data-path collective",
                        "l2": "inputs (>= 20 GB at 50 M rows) far exceed the 126 MB L2; no explicit flush"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -1,0 +1,53 @@
+"""GPU against the committed golden outputs of the UNMODIFIED reference (tests/golden/*.npz), and the deep-book
+configuration (L = 50, BASELINE.json configs[3]) against the oracle / the L = 50 build of the reference."""
+import numpy as np
+import pytest
+
+import mrp_b200
+from mrp_b200 import synth
+from oracle import binding as ob
+
+from helpers import golden_cases, load_golden, norm_errors, raw_errors, run_gpu
+from test_gpu_parity import _check
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_gpu_matches_reference_golden(name):
+    spec, batch, gold = load_golden(name)
+    p = mrp_b200.default_params(depth_levels=spec.levels, emit_dirs=1, emit_counts=1)
+    hv, got = run_gpu(batch, p)
+    rows = gold["rows"]
+    assert np.array_equal(got["bid_dir"][:, rows], gold["bid_dir"]) and np.array_equal(got["ask_dir"][:, rows], gold["ask_dir"])
+    for col in ("midprice", "market_depth"):
+        c = mrp_b200.FEATURES.index(col)
+        assert np.array_equal(got["raw"][c, rows], gold["raw"][c]), col
+    re = raw_errors(got["raw"][:, rows], gold["raw"])
+    assert (re <= 1.0).all(), re
+    # z-scores of the first 30 000 rows: the window sums are short and well conditioned except for near-constant windows
+    ze = norm_errors(got["norm"][:, rows], gold["norm"])
+    assert np.nanmax(ze) < 1e-6, ze
+
+
+def test_deep_book_50_levels():
+    p = mrp_b200.default_params(depth_levels=50, emit_dirs=1, emit_counts=1)
+    batch = synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=5000, levels=50, seed=51, variable_cursors=True)]))
+    got, ref = _check(batch, params=p)
+    if ob.ref_available(50):   # the reference itself, compiled with DEPTH_LEVELS = 50
+        r = ob.run_reference(mrp_b200.HostView(batch), batch["trade_size"], use_book=False)
+        assert np.array_equal(r["raw"], ref["raw"], equal_nan=True)
+
+
+@pytest.mark.parametrize("levels", [2, 3, 4, 7, 16])
+def test_odd_depths(levels):
+    p = mrp_b200.default_params(depth_levels=levels, stress_levels=min(5, levels), emit_dirs=1, emit_counts=1)
+    _check(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=1500, levels=levels, seed=60 + levels)])), params=p)
+
+
+def test_other_window_parameters():
+    p = mrp_b200.default_params(mid_window=900, dir_window=700, spread_divisor=700, ewm_span=300, norm_window=1200, return_lag=7,
+                                emit_dirs=1, emit_counts=1)
+    _check(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=4000, seed=71, dir_window=700, variable_cursors=True)])), params=p)
+    p = mrp_b200.default_params(mid_window=3000, dir_window=2500, norm_window=500, emit_dirs=1, emit_counts=1)   # 8192-entry ring
+    _check(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=3000, seed=72, dir_window=2500, warm_ticks=4000, warm_trades=3000)])), params=p)
