@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 1
+#define MRP_FG_ABI_VERSION 2
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -174,6 +174,15 @@ int mrp_fg_bind_inputs(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view);
  * device buffers, asynchronously on `stream`, and bind them.  Buffers are reused across calls
  * when the shape allows. */
 int mrp_fg_upload(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, void* stream);
+
+/* Host-resident data in, host-resident features out (what a pipeline holding pinned host arrays calls): every stream
+ * of the HOST view is cut into time chunks of `chunk_rows` snapshots (0 = default, 4 Mi rows) that are uploaded,
+ * computed and downloaded on two alternating device buffer sets / CUDA streams, so PCIe runs in both directions while
+ * the SMs compute.  A chunk is preceded by a halo (norm_window + EMA warm-up rows, one window of ticks / trades)
+ * re-read from the host; results equal the single-shot upload / run / download sequence to within the EMA warm-up
+ * (< 1e-17 of the column scale).  raw, norm: HOST double [19][n_rows] (pinned memory recommended).  Synchronous.
+ * Replaces, for every row: FeatureProcessor::GetRawFeatureSet + GetProcessedFeatureSet (feature_processor.cpp:11-29). */
+int mrp_fg_process_host(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, double* raw, double* norm, int64_t chunk_rows);
 
 /* Enqueue the whole feature pass (raw features, then rolling z-scores) for every bound stream.
  * Replaces, for every row: FeatureProcessor::GetRawFeatureSet + GetProcessedFeatureSet

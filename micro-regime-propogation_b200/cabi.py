@@ -134,6 +134,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_bind_inputs.argtypes = [vp, PV]
     lib.mrp_fg_upload.argtypes = [vp, PV, vp]
     lib.mrp_fg_run.argtypes = [vp, vp]
+    lib.mrp_fg_process_host.argtypes = [vp, PV, vp, vp, i64]
     lib.mrp_fg_outputs.argtypes = [vp] + [C.POINTER(vp)] * 5
     lib.mrp_fg_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.mrp_fg_moments.argtypes = [vp, vp, vp]
@@ -194,6 +195,18 @@ class Engine:
         self._keep = hv
         self.n_rows = hv.n_rows
         self._check(self.lib.mrp_fg_upload(self.ctx, C.byref(hv.view), C.c_void_p(stream)))
+
+    # -- host in, host out, pipelined over PCIe (mrp_fg_process_host)
+    def process_host(self, hv: HostView, raw: Optional[np.ndarray] = None, norm: Optional[np.ndarray] = None, chunk_rows: int = 0,
+                     raw_ptr: int = 0, norm_ptr: int = 0):
+        """raw / norm: numpy [19, n] outputs (allocated when omitted), or raw_ptr / norm_ptr: addresses of pinned buffers."""
+        n = hv.n_rows
+        if not raw_ptr:
+            raw = raw if raw is not None else np.empty((NUM_FEATURES, n), np.float64)
+            norm = norm if norm is not None else np.empty((NUM_FEATURES, n), np.float64)
+            raw_ptr, norm_ptr = raw.ctypes.data, norm.ctypes.data
+        self._check(self.lib.mrp_fg_process_host(self.ctx, C.byref(hv.view), C.c_void_p(raw_ptr), C.c_void_p(norm_ptr), chunk_rows))
+        return raw, norm
 
     # -- compute
     def run(self, stream: int = 0):

@@ -92,6 +92,12 @@ struct mrp_fg_ctx {
     cudaEvent_t ev[kNumKernels + 1] = {};
     bool ev_made = false;
     int64_t launches = 0;
+    // mrp_fg_process_host: two child contexts (device buffer sets), each with its own non-blocking stream
+    mrp_fg_ctx* lane[2] = {nullptr, nullptr};
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_done[2] = {nullptr, nullptr};
+    uint32_t* lane_cursors[2] = {nullptr, nullptr};   // pinned: rebased tick / trade cursors of the chunk in flight
+    size_t lane_cursor_cap[2] = {0, 0};
 };
 
 namespace {
@@ -389,6 +395,12 @@ int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out) {
 int mrp_fg_destroy(mrp_fg_ctx* c) {
     if (!c) return MRP_FG_OK;
     cudaSetDevice(c->device);
+    for (int i = 0; i < 2; ++i) {
+        if (c->lane[i]) mrp_fg_destroy(c->lane[i]);
+        if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
+        if (c->lane_done[i]) cudaEventDestroy(c->lane_done[i]);
+        if (c->lane_cursors[i]) cudaFreeHost(c->lane_cursors[i]);
+    }
     DevBuf* bufs[] = {&c->b_ts, &c->b_bpx, &c->b_apx, &c->b_bsz, &c->b_asz, &c->b_buy, &c->b_sell, &c->b_adds, &c->b_kcur,
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
                       &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison};
@@ -425,40 +437,52 @@ int mrp_fg_bind_inputs(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     return MRP_FG_OK;
 }
 
-int mrp_fg_upload(mrp_fg_ctx* c, const mrp_fg_soa_view* v, void* stream) {
-    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
-    int rc = check_view(c, v, MRP_MEM_HOST);
-    if (rc) return rc;
+}  // extern "C"
+
+namespace {
+
+// Copy a HOST view into the context's device buffers and bind them.  `level_stride` = elements between consecutive
+// levels of the level-major host arrays (== n_rows for a self-contained view; larger when the view is a row slice of a
+// bigger batch, mrp_fg_process_host).
+int upload_impl(mrp_fg_ctx* c, const mrp_fg_soa_view* v, int64_t level_stride, cudaStream_t st, bool validate) {
+    int rc;
     CU(cudaSetDevice(c->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     c->bound = false;
-    // the cursors are on the host here: validate what the kernels rely on
-    const int S = v->n_streams;
-    for (int s = 0; s < S; ++s) {
-        const int64_t K = v->tick_offsets[s + 1] - v->tick_offsets[s], T = v->trade_offsets[s + 1] - v->trade_offsets[s];
-        uint32_t pk = 0, pj = 0;
-        for (int64_t r = v->row_offsets[s]; r < v->row_offsets[s + 1]; ++r) {
-            const uint32_t k = v->tick_cursor[r], j = v->trade_cursor[r];
-            if (k < pk || j < pj) return fail(MRP_FG_ERR_INVALID, "cursors must be non-decreasing within a stream");
-            if ((int64_t)k > K || (int64_t)j > T) return fail(MRP_FG_ERR_INVALID, "a cursor points past the end of its stream's tick / trade arrays");
-            pk = k;
-            pj = j;
+    if (validate) {
+        // the cursors are on the host here: validate what the kernels rely on
+        const int S = v->n_streams;
+        for (int s = 0; s < S; ++s) {
+            const int64_t K = v->tick_offsets[s + 1] - v->tick_offsets[s], T = v->trade_offsets[s + 1] - v->trade_offsets[s];
+            uint32_t pk = 0, pj = 0;
+            for (int64_t r = v->row_offsets[s]; r < v->row_offsets[s + 1]; ++r) {
+                const uint32_t k = v->tick_cursor[r], j = v->trade_cursor[r];
+                if (k < pk || j < pj) return fail(MRP_FG_ERR_INVALID, "cursors must be non-decreasing within a stream");
+                if ((int64_t)k > K || (int64_t)j > T) return fail(MRP_FG_ERR_INVALID, "a cursor points past the end of its stream's tick / trade arrays");
+                pk = k;
+                pj = j;
+            }
         }
     }
     if ((rc = setup_shape(c, v))) return rc;
     const int64_t N = c->n_rows, K = c->n_ticks, T = c->n_trades;
     const int L = c->p.depth_levels;
-    struct Copy { DevBuf* b; const void* src; size_t bytes; };
+    struct Copy { DevBuf* b; const void* src; size_t elem; int64_t count; bool levels; };
     const Copy copies[] = {
-        {&c->b_ts, v->ts_ns, (size_t)N * 8},       {&c->b_bpx, v->bid_px, (size_t)N * L * 8}, {&c->b_apx, v->ask_px, (size_t)N * L * 8},
-        {&c->b_bsz, v->bid_sz, (size_t)N * L * 4}, {&c->b_asz, v->ask_sz, (size_t)N * L * 4}, {&c->b_buy, v->buy_vol, (size_t)N * 8},
-        {&c->b_sell, v->sell_vol, (size_t)N * 8},  {&c->b_adds, v->adds, (size_t)N * 4},      {&c->b_kcur, v->tick_cursor, (size_t)N * 4},
-        {&c->b_jcur, v->trade_cursor, (size_t)N * 4}, {&c->b_mid, v->mid, (size_t)K * 8},     {&c->b_spread, v->spread, (size_t)K * 8},
-        {&c->b_tdir, v->trade_dir, (size_t)T},
+        {&c->b_ts, v->ts_ns, 8, N, false},        {&c->b_bpx, v->bid_px, 8, N, true},     {&c->b_apx, v->ask_px, 8, N, true},
+        {&c->b_bsz, v->bid_sz, 4, N, true},       {&c->b_asz, v->ask_sz, 4, N, true},     {&c->b_buy, v->buy_vol, 8, N, false},
+        {&c->b_sell, v->sell_vol, 8, N, false},   {&c->b_adds, v->adds, 4, N, false},     {&c->b_kcur, v->tick_cursor, 4, N, false},
+        {&c->b_jcur, v->trade_cursor, 4, N, false}, {&c->b_mid, v->mid, 8, K, false},     {&c->b_spread, v->spread, 8, K, false},
+        {&c->b_tdir, v->trade_dir, 1, T, false},
     };
     for (const Copy& cp : copies) {
-        if ((rc = cp.b->ensure(cp.bytes))) return rc;
-        if (cp.bytes) CU(cudaMemcpyAsync(cp.b->p, cp.src, cp.bytes, cudaMemcpyHostToDevice, st));
+        const size_t bytes = (size_t)cp.count * cp.elem * (cp.levels ? (size_t)L : 1u);
+        if ((rc = cp.b->ensure(bytes))) return rc;
+        if (!bytes) continue;
+        if (cp.levels && level_stride != N)
+            CU(cudaMemcpy2DAsync(cp.b->p, (size_t)N * cp.elem, cp.src, (size_t)level_stride * cp.elem, (size_t)N * cp.elem, (size_t)L,
+                                 cudaMemcpyHostToDevice, st));
+        else
+            CU(cudaMemcpyAsync(cp.b->p, cp.src, bytes, cudaMemcpyHostToDevice, st));
     }
     DevInputs& in = c->in;
     in.n_rows = N;
@@ -476,6 +500,120 @@ int mrp_fg_upload(mrp_fg_ctx* c, const mrp_fg_soa_view* v, void* stream) {
     in.spread = static_cast<const double*>(c->b_spread.p);
     in.tdir = static_cast<const int8_t*>(c->b_tdir.p);
     c->bound = true;
+    return MRP_FG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrp_fg_upload(mrp_fg_ctx* c, const mrp_fg_soa_view* v, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    int rc = check_view(c, v, MRP_MEM_HOST);
+    if (rc) return rc;
+    return upload_impl(c, v, v->row_offsets[v->n_streams], static_cast<cudaStream_t>(stream), true);
+}
+
+// Host-resident data in, host-resident features out, with PCIe busy in both directions while the SMs compute: every
+// stream is cut into time chunks; chunk i is uploaded (with a halo of norm_window + EMA warm-up rows and one window of
+// ticks / trades in front, re-read from the host: < 1 % extra traffic at the default chunk size), computed and downloaded on
+// one of two lanes (device buffer set + non-blocking stream) while chunk i+1 travels on the other.  Every state of the
+// path has finite memory, so a chunk's own rows are exact (EMAs agree to < 1e-17 of their scale).
+int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, double* norm, int64_t chunk_rows) {
+    if (!c || !raw || !norm) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    int rc = check_view(c, v, MRP_MEM_HOST);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    const int S = v->n_streams, L = c->p.depth_levels;
+    const int64_t NT = v->row_offsets[S];
+    if (NT == 0) return MRP_FG_OK;
+    const int64_t H = (int64_t)c->p.norm_window + c->dp.ema_warm_rows + 32;
+    if (chunk_rows <= 0) chunk_rows = 4 << 20;
+    const int64_t wmax = std::max(c->p.mid_window, c->p.dir_window + 1);
+    for (int i = 0; i < 2; ++i) {
+        if (!c->lane[i]) {
+            mrp_fg_params p = c->p;
+            p.emit_dirs = p.emit_counts = 0;
+            p.norm_mode = c->p.norm_mode;
+            if ((rc = mrp_fg_create(&p, c->device, &c->lane[i]))) return rc;
+            CU(cudaStreamCreateWithFlags(&c->lane_stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&c->lane_done[i], cudaEventDisableTiming));
+        }
+    }
+    bool busy[2] = {false, false};
+    int li = 0;
+    for (int s = 0; s < S; ++s) {
+        const int64_t r0 = v->row_offsets[s], r1 = v->row_offsets[s + 1];
+        const int64_t k0 = v->tick_offsets[s], K = v->tick_offsets[s + 1] - k0;
+        const int64_t j0 = v->trade_offsets[s], T = v->trade_offsets[s + 1] - j0;
+        for (int64_t a = r0; a < r1; a += chunk_rows, li ^= 1) {
+            const int64_t b = std::min(a + chunk_rows, r1);
+            const int64_t e0 = std::max(r0, a - H);           // first halo row
+            const int64_t n = b - e0;
+            int64_t tb = 0, jb = 0;                            // tick / trade bases: the slice's "stream start"
+            if (e0 > r0) {
+                tb = std::max<int64_t>(0, (int64_t)v->tick_cursor[e0] - wmax - 2);
+                jb = std::max<int64_t>(0, (int64_t)v->trade_cursor[e0] - c->p.dir_window - 2);
+            }
+            const int64_t t1 = v->tick_cursor[b - 1], j1 = v->trade_cursor[b - 1];
+            if (t1 > K || j1 > T || tb > t1 || jb > j1) return fail(MRP_FG_ERR_INVALID, "a cursor points past the end of its stream's tick / trade arrays");
+            if (busy[li]) CU(cudaEventSynchronize(c->lane_done[li]));   // the lane's buffers (device and pinned) are free again
+            if (c->lane_cursor_cap[li] < (size_t)n * 2) {
+                if (c->lane_cursors[li]) cudaFreeHost(c->lane_cursors[li]);
+                c->lane_cursors[li] = nullptr;
+                c->lane_cursor_cap[li] = 0;
+                CU(cudaMallocHost(reinterpret_cast<void**>(&c->lane_cursors[li]), sizeof(uint32_t) * (size_t)n * 2));
+                c->lane_cursor_cap[li] = (size_t)n * 2;
+            }
+            uint32_t* kc = c->lane_cursors[li];
+            uint32_t* jc = kc + n;
+            {
+                uint32_t pk = 0, pj = 0;
+                for (int64_t i = 0; i < n; ++i) {
+                    const int64_t k = (int64_t)v->tick_cursor[e0 + i] - tb, j = (int64_t)v->trade_cursor[e0 + i] - jb;
+                    if (k < (int64_t)pk || j < (int64_t)pj) return fail(MRP_FG_ERR_INVALID, "cursors must be non-decreasing within a stream");
+                    kc[i] = pk = (uint32_t)k;
+                    jc[i] = pj = (uint32_t)j;
+                }
+            }
+            const int64_t ro[2] = {0, n}, to[2] = {0, t1 - tb}, tro[2] = {0, j1 - jb};
+            mrp_fg_soa_view sub{};
+            sub.n_streams = 1;
+            sub.memory = MRP_MEM_HOST;
+            sub.row_offsets = ro;
+            sub.tick_offsets = to;
+            sub.trade_offsets = tro;
+            sub.ts_ns = v->ts_ns + e0;
+            sub.bid_px = v->bid_px + e0;
+            sub.ask_px = v->ask_px + e0;
+            sub.bid_sz = v->bid_sz + e0;
+            sub.ask_sz = v->ask_sz + e0;
+            sub.buy_vol = v->buy_vol + e0;
+            sub.sell_vol = v->sell_vol + e0;
+            sub.adds = v->adds + e0;
+            sub.tick_cursor = kc;
+            sub.trade_cursor = jc;
+            sub.mid = v->mid + k0 + tb;
+            sub.spread = v->spread + k0 + tb;
+            sub.trade_dir = v->trade_dir + j0 + jb;
+            mrp_fg_ctx* ln = c->lane[li];
+            cudaStream_t st = c->lane_stream[li];
+            if ((rc = upload_impl(ln, &sub, NT, st, false))) return rc;
+            if ((rc = mrp_fg_run(ln, st))) return rc;
+            const int64_t skip = a - e0, own = b - a;
+            CU(cudaMemcpy2DAsync(raw + a, (size_t)NT * 8, ln->out.raw + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
+                                 cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpy2DAsync(norm + a, (size_t)NT * 8, ln->out.norm + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
+                                 cudaMemcpyDeviceToHost, st));
+            CU(cudaEventRecord(c->lane_done[li], st));
+            busy[li] = true;
+            c->launches += kNumKernels + 1;
+        }
+    }
+    for (int i = 0; i < 2; ++i)
+        if (busy[i]) CU(cudaEventSynchronize(c->lane_done[i]));
+    CU(cudaGetLastError());
+    (void)L;
     return MRP_FG_OK;
 }
 

@@ -93,10 +93,8 @@ void GpuFeatureProcessor::run(std::vector<double>& raw, std::vector<double>& nor
     v.mid = mid_.data();
     v.spread = spread_.data();
     v.trade_dir = tdir_.data();
-    if (mrp_fg_upload(ctx_, &v, nullptr) != MRP_FG_OK) fail("mrp_fg_upload");
-    if (mrp_fg_run(ctx_, nullptr) != MRP_FG_OK) fail("mrp_fg_run");
-    if (mrp_fg_download(ctx_, raw.data(), norm.data(), nullptr, nullptr, nullptr, nullptr) != MRP_FG_OK) fail("mrp_fg_download");
-    if (mrp_fg_sync(ctx_, nullptr) != MRP_FG_OK) fail("mrp_fg_sync");
+    // host arrays in, host features out: chunks of the day are uploaded / computed / downloaded on two alternating lanes
+    if (mrp_fg_process_host(ctx_, &v, raw.data(), norm.data(), 0) != MRP_FG_OK) fail("mrp_fg_process_host");
 }
 
 void GpuFeatureProcessor::flush_columns(std::vector<double>& raw, std::vector<double>& norm, std::vector<std::uint64_t>& grid_ts) {
