@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=200000, help="rows per stream of the CPU sample (about 15 s per host thread)")
     ap.add_argument("--timeshard", action="store_true", help="BASELINE.json configs[4]: ONE stream of rows*N snapshots split by time across the N ranks (halo over NVLink)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="rows per pipelined chunk of the end-to-end leg (0 = library default)")
+    ap.add_argument("--levels", type=int, default=LEVELS, help="book depth (50 = the deep-book config, BASELINE.json configs[3])")
+    ap.add_argument("--days", type=int, default=1, help="instrument-days per GPU in one batch (BASELINE.json configs[2]: 32 days over the ranks, round-robin)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -261,14 +263,19 @@ def main():
                     v = (v.to(torch.int64) - j_base).to(batch[k].dtype)
                 batch[k][..., :v.shape[-1]].copy_(v)
     else:
-        spec = synth.SynthSpec(n_rows=rows, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + rank)
-        batch = synth.make_batch([spec], device=dev)
+        # `--days D`: D independent instrument-days of `rows` snapshots each in one batch on this rank (day d of the job's
+        # D*world days lives on rank d mod world, scripts/multidate_feature_to_csv.sh:24 -> one GPU per instrument-day)
+        specs = [synth.SynthSpec(n_rows=rows, levels=args.levels, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + rank + world * d)
+                 for d in range(args.days)]
+        spec = specs[0]
+        batch = synth.make_batch(specs, device=dev)
+        rows = rows * args.days
     n_ticks, n_trades = batch["tick_offsets"][-1], batch["trade_offsets"][-1]
     q = n_trades / (batch["row_offsets"][-1])
     m_eff = n_ticks / (batch["row_offsets"][-1])
     torch.cuda.synchronize()
 
-    eng = mrp_b200.Engine(mrp_b200.default_params(), device=local_rank)
+    eng = mrp_b200.Engine(mrp_b200.default_params(depth_levels=args.levels), device=local_rank)
     eng.bind_device(batch)
     stream = torch.cuda.current_stream().cuda_stream
     _run = eng.run
@@ -325,13 +332,13 @@ def main():
 
     # ---- roofline of the dominant kernel (live CUDA events on the launching stream, last timed step)
     peak, peak_src = measured_peaks()
-    bytes_row = algorithmic_bytes_per_row(LEVELS, m_eff, q)
+    bytes_row = algorithmic_bytes_per_row(args.levels, m_eff, q)
     # algorithmic bytes per kernel: what each kernel must read + write once
     kb = {
         # mids + spreads + trade dirs + both cursors, 8 feature columns
         "windows": rows * (16 * m_eff + q + 8 + 8 * 8),
         # ts, prices, sizes, buy/sell, adds, 11 feature columns
-        "book": rows * (8 + 24 * LEVELS + 16 + 4 + 11 * 8),
+        "book": rows * (8 + 24 * args.levels + 16 + 4 + 11 * 8),
         # raw read once, z written once
         "normalize": rows * (2 * 19 * 8),
     }
@@ -351,7 +358,7 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
-    if not args.no_e2e and not (args.timeshard and world > 1):
+    if not args.no_e2e and not (args.timeshard and world > 1) and args.days == 1 and args.levels == LEVELS:
         e2e_rows = args.e2e_rows or rows
         try:
             import psutil
@@ -419,16 +426,16 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(LEVELS, args.ref_rows)
+        cpu = cpu_baseline(args.levels, args.ref_rows)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"single instrument-day per GPU, {rows} snapshots x {LEVELS} levels, {m_eff:.2f} ticks and {q:.2f} trades per snapshot"
-                                   + (" (BASELINE.json configs[1])" if rows == FULL_ROWS else " (REDUCED rows: not the headline config)"),
-                       "rows_per_gpu": rows, "levels": LEVELS,
+            "config": {"workload": f"{args.days} instrument-day(s) per GPU, {rows // args.days} snapshots x {args.levels} levels each, {m_eff:.2f} ticks and {q:.2f} trades per snapshot"
+                                   + (" (BASELINE.json configs[1])" if (rows == FULL_ROWS and args.days == 1 and args.levels == LEVELS) else " (not the headline config)"),
+                       "rows_per_gpu": rows, "levels": args.levels, "days_per_gpu": args.days,
                        "sharding": ("ONE stream split by time; per step each rank sends its last %d rows (+ window of ticks / trades) to its right "
                                     "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % tsh.halo_rows())
                        if (args.timeshard and world > 1) else "instrument-day per GPU, no data-path collective",
