@@ -34,6 +34,8 @@
  *     rolling_tick_directions             = tick dirs [max(0,k-dir_window), k)    (cap 1500)
  *     rolling_trade_directions            = trades [max(0,j-dir_window), j)       (cap 1500)
  *   Per-level book arrays are level-major: element (level i, row r) at [i * n_rows + r].
+ *   Limits: a stream holds at most 2^32 - 65536 ticks and trades (uint32 cursors; longer streams are split by time),
+ *   mid_window and dir_window <= about 4000 (on-chip ring), depth_levels in [2, 1024].
  *   The per-level depth-change directions (ref: data_ingestion/src/core/order_book.cpp:208-239,
  *   both branches reduce to sign(new_size - old_size)) are derived on the device from the
  *   sizes of rows t and t-1 (row 0 compares with an all-zero book, order_book.cpp:115,168).

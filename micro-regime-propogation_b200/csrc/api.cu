@@ -236,8 +236,9 @@ int check_view(const mrp_fg_ctx* c, const mrp_fg_soa_view* v, int want_memory) {
     for (int s = 0; s < S; ++s) {
         if (v->row_offsets[s + 1] < v->row_offsets[s] || v->tick_offsets[s + 1] < v->tick_offsets[s] || v->trade_offsets[s + 1] < v->trade_offsets[s])
             return fail(MRP_FG_ERR_INVALID, "offsets must be non-decreasing");
-        if (v->tick_offsets[s + 1] - v->tick_offsets[s] > 0xfffffff0ll || v->trade_offsets[s + 1] - v->trade_offsets[s] > 0xfffffff0ll)
-            return fail(MRP_FG_ERR_INVALID, "a stream may hold at most 2^32-16 ticks / trades (cursors are uint32)");
+        // cursors are uint32 and the kernels step positions by up to 2048 before comparing: keep a margin below 2^32
+        if (v->tick_offsets[s + 1] - v->tick_offsets[s] > 0xffff0000ll || v->trade_offsets[s + 1] - v->trade_offsets[s] > 0xffff0000ll)
+            return fail(MRP_FG_ERR_INVALID, "a stream may hold at most 2^32-65536 ticks / trades (cursors are uint32); split longer streams by time (timeshard)");
     }
     const int64_t N = v->row_offsets[S];
     if (N > 0 && (!v->ts_ns || !v->bid_px || !v->ask_px || !v->bid_sz || !v->ask_sz || !v->buy_vol || !v->sell_vol || !v->adds ||

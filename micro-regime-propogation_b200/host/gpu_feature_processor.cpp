@@ -33,7 +33,7 @@ void GpuFeatureProcessor::on_tick(double midprice, double spread) {
 void GpuFeatureProcessor::on_trade(std::int8_t direction) { tdir_.push_back(direction); }
 
 void GpuFeatureProcessor::stage(const FeatureInputSnapshot& s, std::uint64_t grid_timestamp_ns) {
-    if (mid_.size() > 0xfffffff0ull || tdir_.size() > 0xfffffff0ull) throw std::runtime_error("GpuFeatureProcessor: more than 2^32-16 ticks / trades in one stream");
+    if (mid_.size() > 0xffff0000ull || tdir_.size() > 0xffff0000ull) throw std::runtime_error("GpuFeatureProcessor: more than 2^32-65536 ticks / trades in one stream");
     ts_.push_back(s.timestamp_ns);
     grid_.push_back(grid_timestamp_ns);
     instrument_.push_back(s.instrument);
