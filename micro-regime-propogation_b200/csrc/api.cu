@@ -170,6 +170,8 @@ int setup_params(mrp_fg_ctx* c) {
     if (ring > 8192)
         return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window too large for the on-chip window ring (limit about 4000 ticks)");
     d.win_ring = ring;
+    d.win_pipeline = 1;
+    if (const char* e = std::getenv("MRP_FG_WIN_PIPELINE")) d.win_pipeline = std::atoi(e) != 0;
     d.win_span_max = ring - wmax - 8;
     // the exponentially weighted sum is carried rescaled by decay^-(ticks into the chunk): keep that factor below e^200
     if (!(d.ewm_decay > 0.0 && d.ewm_decay < 1.0)) return fail(MRP_FG_ERR_INVALID, "ewm_span must be >= 2 (decay = 1 - 2/(span+1) in (0,1))");

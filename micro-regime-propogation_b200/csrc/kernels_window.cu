@@ -288,11 +288,378 @@ __device__ __forceinline__ void scan128_max(uint32_t* __restrict__ a, uint32_t& 
     carry = __shfl_sync(0xffffffffu, v.w, 31);
 }
 
+// One snapshot's five tick-axis features from its window values.  The sliding sums cover the ticks [s, e) of the mid window
+// (SA = sum |y|, SS = sum y, D1 / D2 = sums of d and d^2, Eall = exponentially weighted sum, negs = sign-set count) and [d0, e) of
+// the direction window (dirw = sign-set | moved << 16); ys / yf are the ring entries of ticks s and s + 1; lm = 1 + position
+// of the last tick that moved the midprice.
+__device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int64_t N, const int64_t row, const DevParams& P,
+                                                const uint32_t e, const double pivot, const double SAall, const double SSall,
+                                                const double D1, const double D2, const double Eall, const int negs, const int dirw,
+                                                const uint32_t lm, const double ys, const double yf) {
+    double ewm = 0.0, rv = 0.0, dv = 0.0, sv = 0.0, tent = 0.0;
+    int cnt = 0, nUp = 0, t_up = 0, t_dn = 0, t_tot = 0;
+    if (e > 0u) {
+        const uint32_t s = sub_floor0(e, (uint32_t)P.mid_window);
+        cnt = (int)(e - s) - 1;
+        if (cnt > 0) {
+            // the window's returns are (s, e): take tick s out of the sums again
+            const double SA = SAall - fabs(ys), SS = SSall - ys;
+            nUp = cnt - (negs - (int)((uint32_t)__double2hiint(ys) >> 31));
+            // a window of flat ticks only is exactly zero in the reference; do not let rounding residue of the sliding sums
+            // through the square roots
+            const bool moved = lm > s + 1u;
+            const double tot = (SA > 0.0 && moved) ? SA : 0.0;
+            rv = tot * __ldg(P.inv_cnt + cnt);  // feature_processor.cpp:61 (tabulated 1/count)
+            double w = 0.0;
+            if (tot != 0.0) {
+                // :64-79, see the file header: E over (s, e) plus the restart correction of the first return
+                w = Eall + __ldg(P.ewm_pow + cnt) * (fabs(yf) - P.ewm_alpha * fabs(ys));
+                if (!(w > 0.0)) w = 0.0;
+            }
+            ewm = sqrt(w);
+            double sumU = 0.5 * (SA + SS), sumD = 0.5 * (SA - SS);
+            if (!(sumU > 0.0) || !moved) sumU = 0.0;
+            if (!(sumD > 0.0) || !moved) sumD = 0.0;
+            const double au = sumU * __ldg(P.inv_cnt + nUp);          // :95-98 (inv_cnt[0] = 0: empty side)
+            const double ad = sumD * __ldg(P.inv_cnt + (cnt - nUp));
+            const double diff = au - ad;
+            dv = sqrt(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
+        }
+        {   // :101-107 with s_k = pivot + d_k: mean = (sum s)/1500, var = sum (s_k - mean)^2 / 1500
+            const double n = (double)(e - s);
+            const double mean = (D1 + n * pivot) * P.inv_spread_divisor;
+            const double delta = mean - pivot;
+            double ss = D2 - 2.0 * delta * D1 + n * delta * delta;
+            if (!(ss > 0.0)) ss = 0.0;
+            sv = sqrt(ss * P.inv_spread_divisor);
+        }
+        const uint32_t d0 = sub_floor0(e, (uint32_t)P.dir_window);
+        t_tot = (int)(e - d0);
+        const int negd = dirw & 0xffff, movd = (dirw >> 16) & 0xffff;
+        t_up = t_tot - negd;            // sign clear <=> the midprice rose
+        t_dn = negd + movd - t_tot;     // sign set and moved
+        const int zero = t_tot - movd;
+        // :222-229: -sum p log2 p = (T log2 T - sum c log2 c) / T, c*log2(c) tabulated by the host
+        tent = ((__ldg(P.clog2c + t_tot) - __ldg(P.clog2c + t_up)) - __ldg(P.clog2c + t_dn) - __ldg(P.clog2c + zero)) *
+               __ldg(P.inv_cnt + t_tot);
+        if (cnt < 0) cnt = 0;
+    }
+    write_tick_row(out, N, row, ewm, rv, dv, sv, tent, cnt, nUp, t_up, t_dn, t_tot);
+}
+
+// ================================================================================================
+// Pipelined chunk loop for clean data: warps 4-7 (producers) fetch the cursors, run the tick phase and the trade deltas
+// of chunk q+1 while warps 0-3 (consumers) run the row loops, the scans and the finalisation of chunk q.  The global-load
+// latency of the tick phase is thereby hidden behind shared-memory / ALU work instead of stalling the whole CTA at a
+// barrier.  Two chunks of new ticks must fit the ring next to one window, so a pipelined chunk holds at most 112 rows.
+// Anything irregular — a flagged tick, a snapshot with more new ticks than fit — makes the producers publish BAIL; the
+// kernel then continues from that row with the sequential chunk loop below, which owns all the special cases.
+// Named barriers: 1 producers, 2 consumers, 3/4 "descriptor b is full", 5/6 "descriptor b is free again".
+// ================================================================================================
+constexpr int kPipeRows = 112;
+enum { PIPE_RUN = 0, PIPE_END = 1, PIPE_BAIL = 2 };
+
+struct __align__(16) PipeDesc {
+    int TD[2][kWinRows];        // trade deltas of the chunk's rows, scanned in place by the consumers
+    uint32_t E[kWinRows + 1];   // clamped tick cursors, E[0] = the previous chunk's last
+    uint32_t J[kWinRows];       // clamped trade cursor of each row
+    long long c0;               // first row of the chunk
+    uint32_t Elast;
+    int nr, mode;
+};
+struct __align__(16) PipeShared {
+    double A[5][kWinRows];
+    int AI[2][kWinRows];
+    uint32_t LM[kWinRows];
+    PipeDesc d[2];
+    uint32_t exc;
+    int cnt[4];
+};
+
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// returns (through ps.d[..]) the first row it did not process; called by all 256 threads with a freshly restarted state
+template <int RING>
+__device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32_t ring_base, const DevInputs& in, const DevOutputs& out,
+                                                    const DevSegment& sg, const DevParams& P, int64_t c0, const int64_t out_from,
+                                                    uint32_t Eprev, uint32_t Jprev, const uint32_t baseK, const uint32_t baseJ,
+                                                    const double pivot) {
+    constexpr uint32_t mask = RING - 1;
+    constexpr int kD = RING * 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t rb = sg.row_end, N = in.n_rows;
+    const double* __restrict__ mid = in.mid + sg.tick0;
+    const double* __restrict__ spread = in.spread + sg.tick0;
+    const int8_t* __restrict__ tdir = in.tdir + sg.trade0;
+    const uint32_t Wm = (uint32_t)P.mid_window, Wd = (uint32_t)P.dir_window;
+    const uint32_t Wmax = max(Wm, Wd + 1);
+    const uint32_t span_pipe = ((uint32_t)RING - Wmax - 8u) / 2u;
+    const double decay = P.ewm_decay;
+    if (tid == 0) ps.exc = 0u;
+    __syncthreads();
+
+    if (warp >= 4) {
+        // ------------------------------------------------------------------------------------ producers
+        const int pt = tid - kWinRows, pw = warp - 4;
+        int q = 0, published = 0;
+        // the cursors of a round are requested one round ahead
+        uint32_t nce = 0xffffffffu, ncj = 0xffffffffu;
+        if (c0 + pt < rb && pt < kPipeRows) {
+            nce = __ldg(in.kcur + c0 + pt);
+            ncj = __ldg(in.jcur + c0 + pt);
+        }
+        for (;; ++q) {
+            const int b = q & 1;
+            PipeDesc& D = ps.d[b];
+            if (q >= 2) bar_sync_n(5 + b, kWinThreads);   // the consumers have released this descriptor (chunk q-2)
+            int mode = PIPE_RUN, nr = 0;
+            uint32_t Elast = Eprev;
+            if (c0 >= rb) mode = PIPE_END;
+            else {
+                const int64_t row = c0 + pt;
+                uint32_t ce = 0xffffffffu, cj = 0xffffffffu;
+                if (row < rb && pt < kPipeRows) {
+                    ce = max(nce, baseK);
+                    cj = max(ncj, baseJ);
+                }
+                const bool fits = row < rb && pt < kPipeRows && ce - Eprev <= span_pipe;   // monotone in pt
+                const unsigned bal = __ballot_sync(0xffffffffu, fits);
+                if (lane == 0) ps.cnt[pw] = __popc(bal);
+                D.E[pt + 1] = ce;
+                D.J[pt] = cj;
+                if (pt == 0) D.E[0] = Eprev;
+                bar_sync_n(1, kWinRows);
+                nr = ps.cnt[0] + ps.cnt[1] + ps.cnt[2] + ps.cnt[3];
+                if (nr == 0) mode = PIPE_BAIL;
+                else {
+                    Elast = D.E[nr];
+                    {   // next round's cursors: in flight during this round's work
+                        const int64_t nrow = c0 + nr + pt;
+                        nce = ncj = 0xffffffffu;
+                        if (nrow < rb && pt < kPipeRows) {
+                            nce = __ldg(in.kcur + nrow);
+                            ncj = __ldg(in.jcur + nrow);
+                        }
+                    }
+                    // trade window boundaries of this thread's row: requested before the tick phase, used after it
+                    const uint32_t j0 = pt > 0 ? D.J[pt - 1] : Jprev, j1 = cj;
+                    uint32_t q0 = 0, q1 = 0;
+                    int dprev = 0, dq = 0;
+                    if (pt < nr) {
+                        q0 = max(baseJ, sub_floor0(j0, Wd));
+                        q1 = max(baseJ, sub_floor0(j1, Wd));
+                        if (j0 > baseJ) dprev = (int)tdir[j0 - 1];   // the trade at the base (trade 0) closes no pair
+                        if (q1 > q0) dq = (int)tdir[q0];
+                    }
+                    // tick phase: new ticks -> ring, two per thread (see the sequential loop for the derivation)
+                    // the next pair's five values are requested before the current pair is worked on
+                    uint32_t k = (Eprev & ~1u) + 2u * pt;
+                    double Ma = 1.0, Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
+                    auto fetch = [&](uint32_t kk, double& fMa, double& fMp, double& fMb, double& fSa, double& fSb) {
+                        if (kk < Elast) {
+                            fMa = __ldg(mid + kk);
+                            fMp = fMb = fMa;
+                            fSa = fSb = pivot;
+                            if (kk != baseK) fMp = __ldg(mid + kk - 1);
+                            if (kk >= Eprev) fSa = __ldg(spread + kk);
+                            if (kk + 1u < Elast) {
+                                fMb = __ldg(mid + kk + 1);
+                                fSb = __ldg(spread + kk + 1);
+                            }
+                        }
+                    };
+                    fetch(k, Ma, Mp, Mb, Sa, Sb);
+                    while (k < Elast) {
+                        double nMa = 1.0, nMp = 1.0, nMb = 1.0, nSa = pivot, nSb = pivot;
+                        fetch(k + 2u * kWinRows, nMa, nMp, nMb, nSa, nSb);
+                        const bool va = k >= Eprev, vb = k + 1u < Elast;
+                        if (k == baseK) Mp = Ma;
+                        if (!vb) Mb = Ma;
+                        const double ra = rcp_pos(Ma);
+                        const double ta = Mp - Ma, tb = Ma - Mb;
+                        const double va_ = ta * ra, vb_ = -tb * ra;
+                        const double ya = signed_sq_return(ta, va_), yb = signed_sq_return(tb, vb_);
+                        const double da = Sa - pivot, db = Sb - pivot;
+                        const bool ok = (uint32_t)(__double2hiint(Ma) - 0x00100000) < 0x7fe00000u && small_mag(va_, 0x3f500000u) &&
+                                        small_mag(vb_, 0x3f500000u) && small_mag(da, 0x5f138d35u) && small_mag(db, 0x5f138d35u);
+                        const uint32_t a = ring_base + (k & mask) * 8u;
+                        if (va) { sts_f64_off<0>(a, ya); sts_f64_off<kD>(a, da); }
+                        if (vb) { sts_f64_off<8>(a, yb); sts_f64_off<kD + 8>(a, db); }
+                        if (!ok) ps.exc = 1u;
+                        k += 2u * kWinRows;
+                        Ma = nMa; Mp = nMp; Mb = nMb; Sa = nSa; Sb = nSb;
+                    }
+                    // trade deltas of this chunk's rows, read straight from global memory
+                    int w0 = 0, w1 = 0;
+                    if (pt < nr) {
+                        for (uint32_t j = j0; j < j1; ++j) {
+                            const int d = tdir[j];
+                            w0 += (d > 0 ? 1 : 0) + (d < 0 ? 65536 : 0);
+                            w1 += ((d != 0 && d == -dprev) ? 1 : 0) + (d << 16);   // feature_processor.cpp:235
+                            dprev = d;
+                        }
+                        int d = dq;
+                        for (uint32_t j = q0; j < q1; ++j) {
+                            const int dn = tdir[j + 1];
+                            w0 -= (d > 0 ? 1 : 0) + (d < 0 ? 65536 : 0);
+                            w1 -= ((dn != 0 && dn == -d) ? 1 : 0) + (d << 16);   // the pair (j, j+1) leaves with trade j
+                            d = dn;
+                        }
+                    }
+                    D.TD[0][pt] = w0;
+                    D.TD[1][pt] = w1;
+                    bar_sync_n(1, kWinRows);
+                    if (ps.exc != 0u) mode = PIPE_BAIL;   // a flagged tick: the sequential loop takes over from this chunk
+                }
+            }
+            if (pt == 0) {
+                D.c0 = c0;
+                D.Elast = Elast;
+                D.nr = nr;
+                D.mode = mode;
+            }
+            __threadfence_block();
+            bar_arrive_n(3 + b, kWinThreads);
+            if (mode != PIPE_RUN) break;
+            ++published;
+            const uint32_t jn = D.J[nr - 1];
+            bar_sync_n(1, kWinRows);      // everybody has read what it needs from D before the next round may overwrite its twin
+            Eprev = Elast;
+            Jprev = jn;
+            c0 += nr;
+        }
+        // drain: the "free again" arrival of the last processed chunk has no later round to consume it
+        if (published >= 1) bar_sync_n(5 + ((q - 1) & 1), kWinThreads);
+    } else {
+        // ------------------------------------------------------------------------------------ consumers
+        const int ct = tid;
+        // scan ownership: warp 0: A0, A4, TD0 | warp 1: A1, AI0, TD1 | warp 2: A2, AI1 | warp 3: A3, LM
+        double carry_a = 0.0, carry_b = 0.0;
+        int carry_i = 0, carry_t = 0;
+        uint32_t carry_lm = 0;
+        for (int q = 0;; ++q) {
+            const int b = q & 1;
+            PipeDesc& D = ps.d[b];
+            bar_sync_n(3 + b, kWinThreads);
+            if (D.mode != PIPE_RUN) break;
+            const int nr = D.nr;
+            const int64_t row = D.c0 + ct;
+            const uint32_t E0 = D.E[0], Elast = D.Elast;
+            uint32_t e0 = 0, e1 = 0;
+            if (ct < nr) { e0 = D.E[ct]; e1 = D.E[ct + 1]; }
+            {   // ticks that arrive: [e0, e1)
+                double sAll = 0.0, sSgn = 0.0, hh = 0.0, d1 = 0.0, d2 = 0.0;
+                uint32_t neg = 0, mov = 0, lm = 0;
+                uint32_t k0 = e0;
+                while (k0 < e1) {
+                    const uint32_t slot = k0 & mask;
+                    const uint32_t n = min(e1 - k0, (uint32_t)RING - slot);
+                    const uint32_t a0 = ring_base + slot * 8u, aend = a0 + n * 8u;
+                    uint32_t am = 0;
+#pragma unroll 1
+                    for (uint32_t a = a0; a < aend; a += 8u) {
+                        const double y = lds_f64(a), d = lds_f64_off<kD>(a);
+                        sAll += fabs(y);
+                        sSgn += y;
+                        hh = fma(hh, decay, fabs(y));
+                        neg += (uint32_t)__double2hiint(y) >> 31;
+                        if (((uint32_t)__double2hiint(y) << 1) != 0u) { ++mov; am = a; }
+                        d1 += d;
+                        d2 = fma(d, d, d2);
+                    }
+                    if (am != 0u) lm = k0 + ((am - a0) >> 3) + 1u;
+                    k0 += n;
+                }
+                // ticks that leave the direction window: [q0, q1)
+                const uint32_t q0 = max(baseK, sub_floor0(e0, Wd)), q1 = max(baseK, sub_floor0(e1, Wd));
+                uint32_t qneg = 0, qmov = 0;
+                for_ring<RING>(ring_base, q0, q1, [&](uint32_t a) {
+                    const uint32_t hi = lds_hi32(a);
+                    qneg += hi >> 31;
+                    if ((hi << 1) != 0u) ++qmov;
+                });
+                ps.A[0][ct] = sAll;
+                ps.A[1][ct] = sSgn;
+                ps.A[2][ct] = d1;
+                ps.A[3][ct] = d2;
+                ps.A[4][ct] = (ct < nr) ? P.ewm_alpha * hh * __ldg(P.ewm_ipow + (e1 - E0)) : 0.0;
+                ps.AI[0][ct] = (int)neg;
+                ps.AI[1][ct] = (int)(neg - qneg) + ((int)(mov - qmov) << 16);
+                ps.LM[ct] = lm;
+            }
+            {   // ticks that leave the mid window: [s0, s1) — same thread, same slots: no exchange needed
+                const uint32_t s0 = max(baseK, sub_floor0(e0, Wm)), s1 = max(baseK, sub_floor0(e1, Wm));
+                double bAll = 0.0, bSgn = 0.0, b1 = 0.0, b2 = 0.0, hE = 0.0;
+                uint32_t neg = 0;
+                for_ring<RING>(ring_base, s0, s1, [&](uint32_t a) {
+                    const double y = lds_f64(a), d = lds_f64_off<kD>(a);
+                    bAll += fabs(y);
+                    bSgn += y;
+                    hE = fma(hE, decay, fabs(y));
+                    neg += (uint32_t)__double2hiint(y) >> 31;
+                    b1 += d;
+                    b2 = fma(d, d, b2);
+                });
+                if (s1 > s0) {
+                    ps.A[0][ct] -= bAll;
+                    ps.A[1][ct] -= bSgn;
+                    ps.A[2][ct] -= b1;
+                    ps.A[3][ct] -= b2;
+                    ps.A[4][ct] -= P.ewm_alpha * hE * __ldg(P.ewm_pow + (e1 - s1)) * __ldg(P.ewm_ipow + (e1 - E0));
+                    ps.AI[0][ct] -= (int)neg;
+                }
+            }
+            bar_sync_n(2, kWinRows);
+            if (warp == 0) {
+                scan128(ps.A[0], carry_a, lane);
+                scan128(ps.A[4], carry_b, lane);
+                carry_b *= __ldg(P.ewm_pow + (Elast - E0));   // F is relative to the chunk's first tick
+                scan128(D.TD[0], carry_t, lane);
+            } else if (warp == 1) {
+                scan128(ps.A[1], carry_a, lane);
+                scan128(ps.AI[0], carry_i, lane);
+                scan128(D.TD[1], carry_t, lane);
+            } else if (warp == 2) {
+                scan128(ps.A[2], carry_a, lane);
+                scan128(ps.AI[1], carry_i, lane);
+            } else {
+                scan128(ps.A[3], carry_a, lane);
+                scan128_max(ps.LM, carry_lm, lane);
+            }
+            bar_sync_n(2, kWinRows);
+            if (ct < nr && row >= out_from) {
+                const uint32_t e = e1;
+                finish_tick_row(out, N, row, P, e, pivot, ps.A[0][ct], ps.A[1][ct], ps.A[2][ct], ps.A[3][ct],
+                                ps.A[4][ct] * __ldg(P.ewm_pow + (e - E0)), ps.AI[0][ct], ps.AI[1][ct], ps.LM[ct],
+                                lds_f64(ring_base + (sub_floor0(e, Wm) & mask) * 8u),
+                                lds_f64(ring_base + ((sub_floor0(e, Wm) + 1u) & mask) * 8u));
+                const uint32_t je = D.J[ct];
+                const uint32_t jb = sub_floor0(je, Wd);
+                const int w0 = D.TD[0][ct], w1 = D.TD[1][ct];
+                const int pos = w0 & 0xffff, neg = (w0 >> 16) & 0xffff, rev = w1 & 0xffff;
+                const int isum = (w1 - rev) >> 16;
+                write_trade_row(out, N, row, P.clog2c, (int)(je - jb), pos, neg, rev, isum);
+            }
+            bar_sync_n(2, kWinRows);      // the A arrays and this descriptor are free again
+            bar_arrive_n(5 + b, kWinThreads);
+        }
+    }
+    __syncthreads();
+    // exactly one of the two descriptors carries the terminating mode; it names the first unprocessed row
+    const int64_t resume = ps.d[0].mode != PIPE_RUN ? (int64_t)ps.d[0].c0 : (int64_t)ps.d[1].c0;
+    __syncthreads();
+    return resume;
+}
+
 template <int RING>
 __global__ void __launch_bounds__(kWinThreads, 3)
 k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
     extern __shared__ __align__(16) double ring[];  // y: ring[0, RING)   d: ring[RING, 2 RING)
-    __shared__ WinShared sh;
+    __shared__ __align__(16) unsigned char shraw[sizeof(PipeShared) > sizeof(WinShared) ? sizeof(PipeShared) : sizeof(WinShared)];
+    WinShared& sh = *reinterpret_cast<WinShared*>(shraw);
+    PipeShared& ps = *reinterpret_cast<PipeShared*>(shraw);   // the pipelined and the sequential loop never overlap in time
+    bool try_pipeline = P.win_pipeline != 0;
     constexpr uint32_t mask = RING - 1;
     constexpr int kD = RING * 8;  // byte offset of the d ring
     const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
@@ -373,6 +740,19 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             carry_lm = 0;
             need_restart = false;
             pre_valid = false;
+            if (try_pipeline) {
+                // clean data runs through the producer / consumer pipeline; it hands back the first row it left alone
+                try_pipeline = false;
+                const int64_t resume = pipelined_chunks<RING>(ps, ring_base, in, out, sg, P, c0, out_from, Eprev, Jprev, baseK, baseJ, pivot);
+                if (tid == 0) sh.excP1 = 0u;
+                __syncthreads();
+                c0 = resume;
+                if (c0 >= rb) break;
+                out_from = c0 > out_from ? c0 : out_from;
+                restart_at = out_from;
+                need_restart = true;
+                continue;
+            }
         }
 
         // ------------------------------------------------------------------ cursors of up to 128 rows
@@ -584,59 +964,10 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 if (flagged) {
                     direct_tick_row(mid, spread, e, dp, out.raw, out.counts, N, row);
                 } else {
-                    double ewm = 0.0, rv = 0.0, dv = 0.0, sv = 0.0, tent = 0.0;
-                    int cnt = 0, nUp = 0, t_up = 0, t_dn = 0, t_tot = 0;
-                    if (e > 0u) {
-                        const uint32_t s = sub_floor0(e, Wm);
-                        cnt = (int)(e - s) - 1;
-                        // the sliding sums cover the ticks [s, e); the window's returns are (s, e): take tick s out again
-                        const double ys = lds_f64(ring_base + (s & mask) * 8u);
-                        const double D1 = sh.A[2][i], D2 = sh.A[3][i];
-                        const int dirw = sh.AI[1][i];
-                        if (cnt > 0) {
-                            const double SA = sh.A[0][i] - fabs(ys), SS = sh.A[1][i] - ys;
-                            nUp = cnt - (sh.AI[0][i] - (int)((uint32_t)__double2hiint(ys) >> 31));
-                            // a window of flat ticks only is exactly zero in the reference; do not let rounding residue of
-                            // the sliding sums through the square roots
-                            const bool moved = sh.LM[i] > s + 1u;
-                            const double tot = (SA > 0.0 && moved) ? SA : 0.0;
-                            rv = tot * __ldg(P.inv_cnt + cnt);  // feature_processor.cpp:61 (tabulated 1/count)
-                            double w = 0.0;
-                            if (tot != 0.0) {
-                                // :64-79, see the header: E over (s, e) plus the restart correction of the first return
-                                const double E = sh.A[4][i] * __ldg(P.ewm_pow + (e - E0));
-                                w = E + __ldg(P.ewm_pow + cnt) * (fabs(lds_f64(ring_base + ((s + 1u) & mask) * 8u)) - P.ewm_alpha * fabs(ys));
-                                if (!(w > 0.0)) w = 0.0;
-                            }
-                            ewm = sqrt(w);
-                            double sumU = 0.5 * (SA + SS), sumD = 0.5 * (SA - SS);
-                            if (!(sumU > 0.0) || !moved) sumU = 0.0;
-                            if (!(sumD > 0.0) || !moved) sumD = 0.0;
-                            const double au = sumU * __ldg(P.inv_cnt + nUp);          // :95-98 (inv_cnt[0] = 0: empty side)
-                            const double ad = sumD * __ldg(P.inv_cnt + (cnt - nUp));
-                            const double diff = au - ad;
-                            dv = sqrt(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
-                        }
-                        {   // :101-107 with s_k = pivot + d_k: mean = (sum s)/1500, var = sum (s_k - mean)^2 / 1500
-                            const double n = (double)(e - s);
-                            const double mean = (D1 + n * pivot) * P.inv_spread_divisor;
-                            const double delta = mean - pivot;
-                            double ss = D2 - 2.0 * delta * D1 + n * delta * delta;
-                            if (!(ss > 0.0)) ss = 0.0;
-                            sv = sqrt(ss * P.inv_spread_divisor);
-                        }
-                        const uint32_t d0 = sub_floor0(e, Wd);
-                        t_tot = (int)(e - d0);
-                        const int negd = dirw & 0xffff, movd = (dirw >> 16) & 0xffff;
-                        t_up = t_tot - negd;            // sign clear <=> the midprice rose
-                        t_dn = negd + movd - t_tot;     // sign set and moved
-                        const int zero = t_tot - movd;
-                        // :222-229: -sum p log2 p = (T log2 T - sum c log2 c) / T, c*log2(c) tabulated by the host
-                        tent = ((__ldg(P.clog2c + t_tot) - __ldg(P.clog2c + t_up)) - __ldg(P.clog2c + t_dn) - __ldg(P.clog2c + zero)) *
-                               __ldg(P.inv_cnt + t_tot);
-                        if (cnt < 0) cnt = 0;
-                    }
-                    write_tick_row(out, N, row, ewm, rv, dv, sv, tent, cnt, nUp, t_up, t_dn, t_tot);
+                    finish_tick_row(out, N, row, P, e, pivot, sh.A[0][i], sh.A[1][i], sh.A[2][i], sh.A[3][i],
+                                    sh.A[4][i] * __ldg(P.ewm_pow + (e - E0)), sh.AI[0][i], sh.AI[1][i], sh.LM[i],
+                                    lds_f64(ring_base + (sub_floor0(e, Wm) & mask) * 8u),
+                                    lds_f64(ring_base + ((sub_floor0(e, Wm) + 1u) & mask) * 8u));
                 }
             } else {
                 const uint32_t je = sh.J[i + 1];

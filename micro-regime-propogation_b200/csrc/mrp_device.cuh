@@ -80,6 +80,7 @@ struct DevParams {
     const double* inv_cnt;      // [max(mid_window, dir_window)+2]  1/n, [0] = 0
     // window kernel: shared-memory ring entries (power of two) and the most new ticks one chunk may bring
     int32_t win_ring, win_span_max;
+    int32_t win_pipeline;       // 1: producer / consumer chunk pipeline for clean data (kernels_window.cu)
     int32_t ema_warm_rows;      // halo rows that warm the two row-axis EMAs
     int32_t tile_rows;          // normaliser tile (divides norm_window, or == norm_window)
     int32_t tiles_back;         // norm_window / tile_rows
