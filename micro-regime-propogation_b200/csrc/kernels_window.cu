@@ -458,8 +458,8 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
                     double Ma = 1.0, Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
                     auto fetch = [&](uint32_t kk, double& fMa, double& fMp, double& fMb, double& fSa, double& fSb) {
                         if (kk < Elast) {
+                            // (defaults must not copy fMa: that would wait for its load before the others are even issued)
                             fMa = __ldg(mid + kk);
-                            fMp = fMb = fMa;
                             fSa = fSb = pivot;
                             if (kk != baseK) fMp = __ldg(mid + kk - 1);
                             if (kk >= Eprev) fSa = __ldg(spread + kk);
@@ -788,14 +788,17 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         for (uint32_t k = (Eprev & ~1u) + 2u * tid; k < Elast; k += 2u * kWinThreads) {
             // ticks a = k (new unless k < Eprev) and b = k + 1 (new unless past the chunk); k is even
             const bool va = k >= Eprev, vb = k + 1u < Elast;
+            // all five loads are issued before any value is touched (a default such as `Mp = Ma` would wait for Ma's load first)
             const double Ma = __ldg(mid + k);
-            double Mp = Ma, Mb = Ma, Sa = pivot, Sb = pivot;  // defaults give flat, unflagged ticks
-            if (k != baseK) Mp = __ldg(mid + k - 1);           // the tick at the base (tick 0) has no return: flat
+            double Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
+            if (k != baseK) Mp = __ldg(mid + k - 1);
             if (va) Sa = __ldg(spread + k);
             if (vb) {
                 Mb = __ldg(mid + k + 1);
                 Sb = __ldg(spread + k + 1);
             }
+            if (k == baseK) Mp = Ma;   // the tick at the base (tick 0) has no return: flat
+            if (!vb) Mb = Ma;          // defaults give flat, unflagged ticks
             const double ra = rcp_pos(Ma);
             const double ta = Mp - Ma, tb = Ma - Mb;
             const double va_ = ta * ra, vb_ = -tb * ra;        // (Mp-Ma)/Ma and (Mb-Ma)/Ma
