@@ -453,7 +453,6 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
                         if (q1 > q0) dq = (int)tdir[q0];
                     }
                     // tick phase: new ticks -> ring, two per thread (see the sequential loop for the derivation)
-                    // the next pair's five values are requested before the current pair is worked on
                     uint32_t k = (Eprev & ~1u) + 2u * pt;
                     double Ma = 1.0, Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
                     auto fetch = [&](uint32_t kk, double& fMa, double& fMp, double& fMb, double& fSa, double& fSb) {
@@ -469,10 +468,13 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
                             }
                         }
                     };
+                    // two pairs ahead: the loads of pairs k+512 and k+1024 are in flight while pair k is worked on
+                    double Ma1 = 1.0, Mp1 = 1.0, Mb1 = 1.0, Sa1 = pivot, Sb1 = pivot;
                     fetch(k, Ma, Mp, Mb, Sa, Sb);
+                    fetch(k + 2u * kWinRows, Ma1, Mp1, Mb1, Sa1, Sb1);
                     while (k < Elast) {
-                        double nMa = 1.0, nMp = 1.0, nMb = 1.0, nSa = pivot, nSb = pivot;
-                        fetch(k + 2u * kWinRows, nMa, nMp, nMb, nSa, nSb);
+                        double Ma2 = 1.0, Mp2 = 1.0, Mb2 = 1.0, Sa2 = pivot, Sb2 = pivot;
+                        fetch(k + 4u * kWinRows, Ma2, Mp2, Mb2, Sa2, Sb2);
                         const bool va = k >= Eprev, vb = k + 1u < Elast;
                         if (k == baseK) Mp = Ma;
                         if (!vb) Mb = Ma;
@@ -488,7 +490,8 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
                         if (vb) { sts_f64_off<8>(a, yb); sts_f64_off<kD + 8>(a, db); }
                         if (!ok) ps.exc = 1u;
                         k += 2u * kWinRows;
-                        Ma = nMa; Mp = nMp; Mb = nMb; Sa = nSa; Sb = nSb;
+                        Ma = Ma1; Mp = Mp1; Mb = Mb1; Sa = Sa1; Sb = Sb1;
+                        Ma1 = Ma2; Mp1 = Mp2; Mb1 = Mb2; Sa1 = Sa2; Sb1 = Sb2;
                     }
                     // trade deltas of this chunk's rows, read straight from global memory
                     int w0 = 0, w1 = 0;
