@@ -468,30 +468,39 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
                             }
                         }
                     };
-                    // two pairs ahead: the loads of pairs k+512 and k+1024 are in flight while pair k is worked on
-                    double Ma1 = 1.0, Mp1 = 1.0, Mb1 = 1.0, Sa1 = pivot, Sb1 = pivot;
-                    fetch(k, Ma, Mp, Mb, Sa, Sb);
-                    fetch(k + 2u * kWinRows, Ma1, Mp1, Mb1, Sa1, Sb1);
-                    while (k < Elast) {
-                        double Ma2 = 1.0, Mp2 = 1.0, Mb2 = 1.0, Sa2 = pivot, Sb2 = pivot;
-                        fetch(k + 4u * kWinRows, Ma2, Mp2, Mb2, Sa2, Sb2);
-                        const bool va = k >= Eprev, vb = k + 1u < Elast;
-                        if (k == baseK) Mp = Ma;
-                        if (!vb) Mb = Ma;
-                        const double ra = rcp_pos(Ma);
-                        const double ta = Mp - Ma, tb = Ma - Mb;
+                    // two pairs ahead: the loads of pairs k+256 and k+512 are in flight while pair k is worked on.  The three
+                    // register sets rotate by unrolling, not by copying (a copy would wait for the load it copies).
+                    auto work = [&](const uint32_t kk, double wMa, double wMp, double wMb, const double wSa, const double wSb) {
+                        const bool va = kk >= Eprev, vb = kk + 1u < Elast;
+                        if (kk == baseK) wMp = wMa;
+                        if (!vb) wMb = wMa;
+                        const double ra = rcp_pos(wMa);
+                        const double ta = wMp - wMa, tb = wMa - wMb;
                         const double va_ = ta * ra, vb_ = -tb * ra;
                         const double ya = signed_sq_return(ta, va_), yb = signed_sq_return(tb, vb_);
-                        const double da = Sa - pivot, db = Sb - pivot;
-                        const bool ok = (uint32_t)(__double2hiint(Ma) - 0x00100000) < 0x7fe00000u && small_mag(va_, 0x3f500000u) &&
+                        const double da = wSa - pivot, db = wSb - pivot;
+                        const bool ok = (uint32_t)(__double2hiint(wMa) - 0x00100000) < 0x7fe00000u && small_mag(va_, 0x3f500000u) &&
                                         small_mag(vb_, 0x3f500000u) && small_mag(da, 0x5f138d35u) && small_mag(db, 0x5f138d35u);
-                        const uint32_t a = ring_base + (k & mask) * 8u;
+                        const uint32_t a = ring_base + (kk & mask) * 8u;
                         if (va) { sts_f64_off<0>(a, ya); sts_f64_off<kD>(a, da); }
                         if (vb) { sts_f64_off<8>(a, yb); sts_f64_off<kD + 8>(a, db); }
                         if (!ok) ps.exc = 1u;
-                        k += 2u * kWinRows;
-                        Ma = Ma1; Mp = Mp1; Mb = Mb1; Sa = Sa1; Sb = Sb1;
-                        Ma1 = Ma2; Mp1 = Mp2; Mb1 = Mb2; Sa1 = Sa2; Sb1 = Sb2;
+                    };
+                    constexpr uint32_t S = 2u * kWinRows;
+                    double Ma1 = 1.0, Mp1 = 1.0, Mb1 = 1.0, Sa1 = pivot, Sb1 = pivot;
+                    double Ma2 = 1.0, Mp2 = 1.0, Mb2 = 1.0, Sa2 = pivot, Sb2 = pivot;
+                    fetch(k, Ma, Mp, Mb, Sa, Sb);
+                    fetch(k + S, Ma1, Mp1, Mb1, Sa1, Sb1);
+                    while (k < Elast) {
+                        fetch(k + 2u * S, Ma2, Mp2, Mb2, Sa2, Sb2);
+                        work(k, Ma, Mp, Mb, Sa, Sb);
+                        if (k + S >= Elast) break;
+                        fetch(k + 3u * S, Ma, Mp, Mb, Sa, Sb);
+                        work(k + S, Ma1, Mp1, Mb1, Sa1, Sb1);
+                        if (k + 2u * S >= Elast) break;
+                        fetch(k + 4u * S, Ma1, Mp1, Mb1, Sa1, Sb1);
+                        work(k + 2u * S, Ma2, Mp2, Mb2, Sa2, Sb2);
+                        k += 3u * S;
                     }
                     // trade deltas of this chunk's rows, read straight from global memory
                     int w0 = 0, w1 = 0;
