@@ -303,7 +303,6 @@ def main():
     launches0 = eng.launch_count()
     eng.enable_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kt_acc = {}
     barrier()
     t_wall0 = time.time()
     ev0.record()
@@ -313,9 +312,15 @@ def main():
     barrier()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    kt = eng.kernel_times_ms()      # last step's per-kernel CUDA-event durations (same stream)
-    eng.enable_timing(False)
     launches = eng.launch_count() - launches0
+    # per-kernel CUDA-event durations (same stream): mean over a second pass of the same steps, read back step by step
+    kt = {}
+    for _ in range(args.steps):
+        eng.run(stream)
+        torch.cuda.synchronize()
+        for k, v in eng.kernel_times_ms().items():
+            kt[k] = kt.get(k, 0.0) + v / args.steps
+    eng.enable_timing(False)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)

@@ -42,7 +42,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
     deps = srcs + [os.path.join(CSRC, "mrp_device.cuh"), os.path.join(HERE, "..", "include", "mrp_fg.h"), __file__]
     if force or _stale(LIB, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+        extra = os.environ.get("MRP_FG_NVCC_EXTRA", "").split()   # experiment switches (-DNAME=value), empty in normal builds
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
         # nvcc's host compiler must be the PATH g++ (the image's CC/CXX wrappers are not usable by nvcc)
         env = dict(os.environ)
         env.pop("CC", None)

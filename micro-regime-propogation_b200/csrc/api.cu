@@ -195,7 +195,6 @@ int setup_params(mrp_fg_ctx* c) {
     std::vector<double> tab;
     const size_t o_w = 0;
     for (int i = 0; i < p.depth_levels; ++i) tab.push_back(std::exp(-i * p.ofi_depth_decay));  // feature_processor.cpp:121
-    for (int i = 0; i < kOfiWeights; ++i) d.ofi_w[i] = std::exp(-i * p.ofi_depth_decay);
     const size_t o_e = tab.size();
     for (int n = 0; n <= d.win_ring; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
     const size_t o_ei = tab.size();
@@ -203,10 +202,15 @@ int setup_params(mrp_fg_ctx* c) {
         tab.push_back(n <= d.win_span_max + 1 ? (double)powl((long double)d.ewm_decay, -(long double)n) : 0.0);
     const size_t o_o = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
+    for (int k = 0; k < 6; ++k) {
+        d.ofi_pw2[k] = (double)powl((long double)d.ofi_decay, (long double)(1 << k));
+        d.stress_pw2[k] = (double)powl((long double)d.stress_decay, (long double)(1 << k));
+    }
     const size_t o_s = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.stress_decay, (long double)n));
     const size_t o_i = tab.size();
     for (int n = 0; n <= p.norm_window; ++n) tab.push_back(n > 0 ? 1.0 / (double)n : 0.0);
+    for (int n = 0; n < 160; ++n) tab.push_back(0.0);  // the normaliser's idle lanes of a partial step read past 1/W
     const size_t o_h = tab.size();
     const int hmax = std::max(p.dir_window, p.mid_window) + 1;
     for (int n = 0; n <= hmax; ++n) tab.push_back(n > 0 ? (double)((long double)n * log2l((long double)n)) : 0.0);

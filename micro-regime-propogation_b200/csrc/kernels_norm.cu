@@ -188,6 +188,8 @@ __device__ __forceinline__ void tile_zscores(const double* __restrict__ x, doubl
             load4<ALIGN>(x, ib + kStep, n, vn);
             if (has_lag) load4<ALIGN>(xl, ib + kStep, n, ln);
         }
+        // a tile without lag lies inside the first window of its stream (tl0 + n <= W): 1/n needs no clamp there
+        const double* __restrict__ inv_fill = inv_n + (has_lag ? 0 : tl0 + ib + 1);
         double p1[kRPL], p2[kRPL];
         double a1 = 0.0, a2 = 0.0;
 #pragma unroll
@@ -211,10 +213,7 @@ __device__ __forceinline__ void tile_zscores(const double* __restrict__ x, doubl
         for (int k = 0; k < kRPL; ++k) {
             const double e1 = b1 + p1[k], e2 = b2 + p2[k];
             double inv = invW;
-            if (!has_lag) {  // the window is still filling: n = rows so far (feature_normalizer.cpp:71)
-                const int64_t tl = tl0 + ib + k;
-                inv = __ldg(inv_n + (tl + 1 >= W ? W : (int)(tl + 1)));
-            }
+            if (!has_lag) inv = __ldg(inv_fill + k);  // the window is still filling: n = rows so far (feature_normalizer.cpp:71)
             const double mean = e1 * inv;                       // :62
             const double variance = e2 * inv - mean * mean;     // :63
             // :67 — std = 1 unless the variance is positive.  Fast path: positive, normal, far from the range ends

@@ -46,17 +46,20 @@ __device__ __noinline__ void lob_sums_direct(const double* __restrict__ bid_px, 
     *ask_lw = al;
 }
 
-__device__ __forceinline__ double ema_scan(double b, const double* __restrict__ pw, double carry_in, double* sWarp,
+// pw2 = decay^(1,2,4,8,16,32) (kernel-parameter constants: operands, not loads); pw[n] = decay^n per lane
+__device__ __forceinline__ double ema_scan(double b, const double (&pw2)[6], const double* __restrict__ pw, double carry_in, double* sWarp,
                                            int lane, int warp, double& carry_out) {
     double v = b;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
+    for (int k = 0; k < 5; ++k) {
+        const int d = 1 << k;
         const double t = shfl_up_d(v, d);
-        if (lane >= d) v = __ldg(pw + d) * t + v;
+        if (lane >= d) v = pw2[k] * t + v;
     }
+    const double pl = __ldg(pw + lane + 1);
     if (lane == 31) sWarp[warp] = v;
     __syncthreads();
-    const double p32 = __ldg(pw + 32);
+    const double p32 = pw2[5];
     double cw = carry_in, co = carry_in;
 #pragma unroll
     for (int u = 0; u < kWarps; ++u) {
@@ -64,24 +67,76 @@ __device__ __forceinline__ double ema_scan(double b, const double* __restrict__ 
         co = p32 * co + sWarp[u];
     }
     carry_out = co;
-    return __ldg(pw + lane + 1) * cw + v;
+    return pl * cw + v;
 }
 
+#ifndef MRP_BOOK_MINB
+#define MRP_BOOK_MINB 2
+#endif
 constexpr int kStressCache = 4;  // levels 1..4 keep their last exp(-distance*decay) per thread
 
-// LG = levels per load batch; it divides the depth L, so the level loop carries no bounds predicates.
+// ---- bulk asynchronous copies (TMA, UBLKCP) with mbarrier completion.  One lane per (array, level) of a batch requests the
+// chunk's 256-row run of that level as ONE copy; nobody spends issue slots or registers on per-row loads.  Source
+// addresses are rounded down / up to the 16 bytes the copy engine wants and every thread adds the resulting element
+// shift (published in the stage header) to its slot index, so any row count and any 8 / 4-byte aligned base works.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kPxSlot = kThreads + 4;    // doubles: 256 rows + the <= 1 element alignment shift, padded to 16 bytes
+constexpr int kSzSlot = kThreads + 12;   // ints: 4 pad + previous row + 256 rows + the <= 3 element shift, padded
+constexpr int kSzPad = 4;                // the copy lands 16 bytes into the slot, so "previous row" of row 0 never indexes below it
+
+// one landing stage: LG levels of a 256-row chunk
 template <int LG>
-__global__ void __launch_bounds__(kThreads, 2)
+struct __align__(16) BookStage {
+    double bp[LG][kPxSlot], ap[LG][kPxSlot];
+    int bs[LG][kSzSlot], as[LG][kSzSlot];
+    int4 shift[LG];   // slot index of the chunk's first row: x bid_px, y ask_px, z bid_sz, w ask_sz
+};
+
+// LG = levels per staged batch (it divides the depth L, so the level loop carries no bounds predicates), NS = stages.
+template <int LG, int NS>
+__global__ void __launch_bounds__(kThreads, MRP_BOOK_MINB)
 k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
+    static_assert(4 * LG <= 32, "one lane of warp 0 per (array, level) of a batch");
+    extern __shared__ __align__(16) unsigned char book_dyn[];
+    BookStage<LG>* __restrict__ stg = reinterpret_cast<BookStage<LG>*>(book_dyn);
+    double* __restrict__ sOfiW = reinterpret_cast<double*>(book_dyn + sizeof(BookStage<LG>) * NS);  // [L] depth weights
     __shared__ double sInv[2][kThreads], sMid[2][kThreads];
     __shared__ double sWarpLiq[kWarps], sCarLiq;
     __shared__ double sWOfi[kWarps], sWSt[kWarps];
+    __shared__ __align__(8) uint64_t sFull[NS], sEmpty[NS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevSegment sg = segs[blockIdx.x];
     const int64_t ra = sg.row_begin, rb = sg.row_end, sr0 = sg.stream_row0;
     const int64_t N = in.n_rows;
     const int L = P.L;
+    const int nb = L / LG;
     int64_t wa = ra - P.ema_warm_rows;
     if (wa < sr0) wa = sr0;
     const int back = P.return_lag + 1;  // feature_normalizer.hpp:19-24
@@ -92,9 +147,60 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     double cx[kStressCache], ce[kStressCache];
 #pragma unroll
     for (int j = 0; j < kStressCache; ++j) { cx[j] = 0.0; ce[j] = 1.0; }
-    if (tid == 0) sCarLiq = 0.0;
+    if (tid == 0) {
+        sCarLiq = 0.0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&sFull[s], 4 * LG);     // one arrival (with its byte count) per requesting lane
+            mbar_init(&sEmpty[s], kWarps);    // one arrival per warp that has finished reading the stage
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    for (int i = tid; i < L; i += kThreads) sOfiW[i] = P.ofi_weight[i];
     int buf = 0;
     __syncthreads();
+
+    // ---- staging pipeline: batch b = (chunk, level group) lands in stage b % NS; warp 0 requests batch b + NS - 1 when it
+    // starts batch b, after every warp has released the stage's previous occupant
+    int64_t ic = wa;   // chunk of the next batch to request
+    int ib = 0;        // its level group
+    int nreq = 0;      // batches requested so far
+    auto request = [&]() {   // warp 0 only
+        if (ic < rb) {
+            const int s = nreq % NS;
+            if (nreq >= NS) mbar_wait(&sEmpty[s], (uint32_t)((nreq / NS - 1) & 1));
+            if (lane < 4 * LG) {
+                const int a = lane / LG, g = lane - a * LG;
+                const bool px = a < 2;
+                const bool prev_row = !px && ic > sr0;                  // sizes also bring the row before the chunk
+                const int64_t lvl = (int64_t)(ib * LG + g) * N;
+                const int64_t r_first = ic - (prev_row ? 1 : 0);
+                const int64_t r_end = ic + kThreads < rb ? ic + kThreads : rb;
+                const char* base = a == 0 ? reinterpret_cast<const char*>(in.bid_px)
+                                 : a == 1 ? reinterpret_cast<const char*>(in.ask_px)
+                                 : a == 2 ? reinterpret_cast<const char*>(in.bid_sz) : reinterpret_cast<const char*>(in.ask_sz);
+                const int esh = px ? 3 : 2;
+                const uintptr_t p0 = reinterpret_cast<uintptr_t>(base) + ((uintptr_t)(lvl + r_first) << esh);
+                const uintptr_t p1 = reinterpret_cast<uintptr_t>(base) + ((uintptr_t)(lvl + r_end) << esh);
+                const uintptr_t q0 = p0 & ~(uintptr_t)15, q1 = (p1 + 15) & ~(uintptr_t)15;
+                const uint32_t bytes = (uint32_t)(q1 - q0);
+                const int sh = (int)((p0 - q0) >> esh) + (prev_row ? 1 : 0) + (px ? 0 : kSzPad);
+                BookStage<LG>& S = stg[s];
+                void* dst = a == 0 ? (void*)&S.bp[g][0] : a == 1 ? (void*)&S.ap[g][0] : a == 2 ? (void*)&S.bs[g][kSzPad] : (void*)&S.as[g][kSzPad];
+                reinterpret_cast<int*>(&S.shift[g])[a] = sh;
+                mbar_expect_tx(&sFull[s], bytes);
+                bulk_g2s(dst, reinterpret_cast<const void*>(q0), bytes, &sFull[s]);
+            }
+            ++nreq;
+            if (++ib == nb) { ib = 0; ic += kThreads; }
+        }
+    };
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < NS - 1; ++s) request();
+    }
+    int nuse = 0;      // batches consumed so far
 
     for (int64_t c0 = wa; c0 < rb; c0 += kThreads, buf ^= 1) {
         const int64_t t = c0 + tid;
@@ -104,7 +210,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         const int64_t tc = act ? t : rb - 1;    // clamp loads of idle lanes
         const bool own_prev = lane == 0 && hasprev;  // lane 0 fetches the previous row itself; the others ask their neighbour
 
-        // row scalars first: one batch of independent loads
+        // row scalars: independent loads, consumed after the level loop
         const unsigned long long ts = in.ts[tc];
         const double buy = in.buy[tc], sell = in.sell[tc];
         const int adds = in.adds[tc];
@@ -116,67 +222,73 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         bool oor = false;  // some level outside the log1p series range
         double p0b = 0, p1b = 0, p0a = 0, p1a = 0;
         int s0b = 0, s1b = 0, s0a = 0, s1a = 0;
-        const double* __restrict__ pbp = in.bid_px + tc;
-        const double* __restrict__ pap = in.ask_px + tc;
-        const int32_t* __restrict__ pbs = in.bid_sz + tc;
-        const int32_t* __restrict__ pas = in.ask_sz + tc;
         int8_t* __restrict__ obd = out.bdir + tc;
         int8_t* __restrict__ oad = out.adir + tc;
         for (int i0 = 0; i0 < L; i0 += LG) {
-            // all loads of a batch of levels are issued before any is used
-            double bp[LG], ap[LG];
-            int bs[LG], as[LG], qbs[LG], qas[LG];
-#pragma unroll
-            for (int g = 0; g < LG; ++g) {
-                const int64_t o = (int64_t)g * N;
-                bp[g] = pbp[o];
-                ap[g] = pap[o];
-                bs[g] = pbs[o];
-                as[g] = pas[o];
-                qbs[g] = own_prev ? pbs[o - 1] : 0;
-                qas[g] = own_prev ? pas[o - 1] : 0;
-            }
+            if (warp == 0) request();   // keeps NS-1 batches in flight
+            const int sidx = nuse % NS;
+            mbar_wait(&sFull[sidx], (uint32_t)((nuse / NS) & 1));
+            ++nuse;
+            const BookStage<LG>& S = stg[sidx];
             if (i0 == 0) {
-                bb = bp[0];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
-                ba = ap[0];
+                const int4 sh = S.shift[0];
+                bb = S.bp[0][sh.x + tid];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
+                ba = S.ap[0][sh.y + tid];
                 midp = (ba + bb) / 2;  // feature_processor.cpp:34,161
                 inv_mid = 1.0 / midp;
             }
 #pragma unroll
             for (int g = 0; g < LG; ++g) {
                 const int i = i0 + g;
+                const int4 sh = S.shift[g];
+                const double bp = S.bp[g][sh.x + tid], ap = S.ap[g][sh.y + tid];
+                const int bs = S.bs[g][sh.z + tid], as = S.as[g][sh.w + tid];
                 // first snapshot compares with an empty book (order_book.cpp:115,168)
-                const int nbs = __shfl_up_sync(0xffffffffu, bs[g], 1), nas = __shfl_up_sync(0xffffffffu, as[g], 1);
-                const int qb = hasprev ? (lane == 0 ? qbs[g] : nbs) : 0;
-                const int qa = hasprev ? (lane == 0 ? qas[g] : nas) : 0;
-                const int bd = (bs[g] > qb) - (bs[g] < qb);  // order_book.cpp:208-239
-                const int ad = (as[g] > qa) - (as[g] < qa);
+                int qb = 0, qa = 0;
+                if (hasprev) {
+                    qb = S.bs[g][sh.z + tid - 1];
+                    qa = S.as[g][sh.w + tid - 1];
+                }
+                const int bd = (bs > qb) - (bs < qb);  // order_book.cpp:208-239
+                const int ad = (as > qa) - (as < qa);
                 if (want_dirs && full) {
                     obd[(int64_t)g * N] = (int8_t)bd;
                     oad[(int64_t)g * N] = (int8_t)ad;
                 }
-                const double w = i < kOfiWeights ? P.ofi_w[i < kOfiWeights ? i : 0] : __ldg(P.ofi_weight + i);  // exp(-i*0.5), :121
-                const double bid_contrib = (double)(bd * bs[g]) * w;   // (int8 * int) * double, as the reference
-                const double ask_contrib = (double)(ad * as[g]) * w;
+                const double w = sOfiW[i];  // exp(-i*0.5), :121
+                const double bid_contrib = (double)(bd * bs) * w;   // (int8 * int) * double, as the reference
+                const double ask_contrib = (double)(ad * as) * w;
                 raw_ofi += bid_contrib - ask_contrib;      // :125
-                const double fbs = (double)bs[g], fas = (double)as[g];
-                if (i < P.stress_levels && (i == 0 || i > kStressCache || i0 != 0)) {   // :282-299 (levels 1..kStressCache of
-                    const bool ub = bp[g] > 0.0 && fbs >= P.stress_min_size;              //  the first batch: cached, below)
-                    const bool ua = ap[g] > 0.0 && fas >= P.stress_min_size;
+                const double fbs = (double)bs, fas = (double)as;
+                if (i < P.stress_levels) {   // :282-299
+                    const bool ub = bp > 0.0 && fbs >= P.stress_min_size;
+                    const bool ua = ap > 0.0 && fas >= P.stress_min_size;
                     if (i == 0) {  // distance 0 exactly: weight 1
                         if (ub) liq_b += fbs;
                         if (ua) liq_a += fas;
                     } else {
-                        const double xb = -(bb - bp[g]) * P.stress_distance_decay, xa = -(ap[g] - ba) * P.stress_distance_decay;
-                        if (ub) liq_b += exp(xb) * fbs;
-                        if (ua) liq_a += exp(xa) * fas;
+                        const double xb = -(bb - bp) * P.stress_distance_decay, xa = -(ap - ba) * P.stress_distance_decay;
+                        if (g >= 1 && g <= kStressCache && i0 == 0) {
+                            // near-touch weights exp(-distance*decay): on a regular tick grid the arguments repeat row after
+                            // row, so each thread remembers its last bid-side argument per level and the ask side shares it
+                            // when the book is symmetric
+                            const int j = (g >= 1 && g <= kStressCache) ? g - 1 : 0;
+                            if (ub) {
+                                if (xb != cx[j]) { cx[j] = xb; ce[j] = exp(xb); }
+                                liq_b += ce[j] * fbs;
+                            }
+                            if (ua) liq_a += ((xa == cx[j]) ? ce[j] : exp(xa)) * fas;
+                        } else {
+                            if (ub) liq_b += exp(xb) * fbs;
+                            if (ua) liq_a += exp(xa) * fas;
+                        }
                     }
                 }
-                if (i == 0) { p0b = bp[g]; p0a = ap[g]; s0b = bs[g]; s0a = as[g]; }
-                if (i == 1) { p1b = bp[g]; p1a = ap[g]; s1b = bs[g]; s1a = as[g]; }
+                if (i == 0) { p0b = bp; p0a = ap; s0b = bs; s0a = as; }
+                if (i == 1) { p1b = bp; p1a = ap; s1b = bs; s1a = as; }
                 {   // :164-175, :189-200 — branch-free: out-of-range arguments only raise the row's flag
-                    const double ub_ = (bp[g] - midp) * inv_mid, ua_ = (ap[g] - midp) * inv_mid;
-                    const bool hb = bp[g] > 0, ha = ap[g] > 0;
+                    const double ub_ = (bp - midp) * inv_mid, ua_ = (ap - midp) * inv_mid;
+                    const bool hb = bp > 0, ha = ap > 0;
                     oor |= (hb && !(fabs(ub_) <= kSeriesMax)) || (ha && !(fabs(ua_) <= kSeriesMax));
                     const double lb = fabs(log1p_series(ub_)), la = fabs(log1p_series(ua_));
                     bid_lw += hb ? lb * fbs : 0.0;   // |log mid - log bp| * size
@@ -185,33 +297,10 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
                     ask_depth += ha ? fas : 0.0;
                 }
             }
-            if (i0 == 0) {
-                // near-touch liquidity weights exp(-distance*decay) of levels 1..kStressCache (:282-299): on a regular tick
-                // grid the arguments repeat row after row, so each thread remembers its last bid-side argument per level
-                // and the ask side shares it when the book is symmetric
-#pragma unroll
-                for (int j = 0; j < kStressCache; ++j) {
-                    constexpr int kTop = LG - 1;
-                    const int g = j + 1 < kTop ? j + 1 : kTop;   // == j + 1 whenever the level exists in this batch
-                    if (j + 1 < LG && j + 1 < P.stress_levels) {
-                        const double fbs = (double)bs[g], fas = (double)as[g];
-                        const bool ub = bp[g] > 0.0 && fbs >= P.stress_min_size;
-                        const bool ua = ap[g] > 0.0 && fas >= P.stress_min_size;
-                        const double xb = -(bb - bp[g]) * P.stress_distance_decay, xa = -(ap[g] - ba) * P.stress_distance_decay;
-                        if (ub) {
-                            if (xb != cx[j]) { cx[j] = xb; ce[j] = exp(xb); }
-                            liq_b += ce[j] * fbs;
-                        }
-                        if (ua) liq_a += ((xa == cx[j]) ? ce[j] : exp(xa)) * fas;
-                    }
-                }
-            }
-            pbp += (int64_t)LG * N;
-            pap += (int64_t)LG * N;
-            pbs += (int64_t)LG * N;
-            pas += (int64_t)LG * N;
             obd += (int64_t)LG * N;
             oad += (int64_t)LG * N;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sEmpty[sidx]);   // this warp is done with the stage
         }
         if (oor && full) lob_sums_direct(in.bid_px, in.ask_px, in.bid_sz, in.ask_sz, N, tc, L, midp, &bid_lw, &ask_lw);
         const double liq = liq_b + liq_a;  // :301
@@ -243,8 +332,8 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         if (pliq > 0.0) raw_stress = -((liq - pliq) / pliq);
 
         double coOfi, coSt;
-        const double ofi = ema_scan(act ? P.ofi_alpha * x_ofi : 0.0, P.ofi_pow, yOfi, sWOfi, lane, warp, coOfi);  // :133
-        const double stress = ema_scan(act ? P.stress_alpha * raw_stress : 0.0, P.stress_pow, ySt, sWSt, lane, warp, coSt);  // :311-313
+        const double ofi = ema_scan(act ? P.ofi_alpha * x_ofi : 0.0, P.ofi_pw2, P.ofi_pow, yOfi, sWOfi, lane, warp, coOfi);  // :133
+        const double stress = ema_scan(act ? P.stress_alpha * raw_stress : 0.0, P.stress_pw2, P.stress_pow, ySt, sWSt, lane, warp, coSt);  // :311-313
         yOfi = coOfi;
         ySt = coSt;
         if (tid == kThreads - 1) sCarLiq = liq;
@@ -292,14 +381,28 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     }
 }
 
+template <int LG, int NS>
+static cudaError_t launch_book_t(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
+                                 const DevParams& P, cudaStream_t st) {
+    constexpr int kStageBytes = (int)sizeof(BookStage<LG>) * NS;
+    const int bytes = kStageBytes + P.L * (int)sizeof(double);  // + the depth weights
+    static int ready_for = -1;  // idempotent; a race only repeats the call
+    if (ready_for < bytes) {
+        cudaError_t e = cudaFuncSetAttribute(k_book<LG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return e;
+        ready_for = bytes;
+    }
+    k_book<LG, NS><<<nseg, kThreads, bytes, st>>>(in, out, segs, P);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
                         const DevParams& P, cudaStream_t st) {
     const int L = P.L;
-    if (L % 5 == 0) k_book<5><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
-    else if (L % 4 == 0) k_book<4><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
-    else if (L % 2 == 0) k_book<2><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
-    else k_book<1><<<nseg, kThreads, 0, st>>>(in, out, segs, P);
-    return cudaGetLastError();
+    if (L % 5 == 0) return launch_book_t<5, 2>(in, out, segs, nseg, P, st);
+    if (L % 4 == 0) return launch_book_t<4, 2>(in, out, segs, nseg, P, st);
+    if (L % 2 == 0) return launch_book_t<2, 3>(in, out, segs, nseg, P, st);
+    return launch_book_t<1, 4>(in, out, segs, nseg, P, st);
 }
 
 }  // namespace mrp

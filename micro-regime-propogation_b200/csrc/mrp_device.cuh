@@ -60,7 +60,6 @@ struct DevTile {
     int32_t stream;       // stream index within the batch
 };
 
-constexpr int kOfiWeights = 16;
 
 struct DevParams {
     int32_t L, mid_window, dir_window, spread_divisor, norm_window, return_lag, stress_levels;
@@ -70,10 +69,10 @@ struct DevParams {
     double ofi_alpha, ofi_decay, ofi_min_total_vol;
     double stress_alpha, stress_decay, stress_min_size, stress_distance_decay;
     const double* ofi_weight;   // [L]  exp(-i*depth_decay), computed by the host libm
-    double ofi_w[kOfiWeights];  // the first weights again, as kernel-parameter constants
     const double* ewm_pow;      // [win_ring+1]    decay^n
     const double* ewm_ipow;     // [win_ring+1]    decay^-n (n <= win_span_max keeps it far from overflow)
     const double* ofi_pow;      // [257]           ofi_decay^n
+    double ofi_pw2[6], stress_pw2[6];  // decay^(1,2,4,8,16,32) again, as kernel-parameter constants (the scan steps)
     const double* stress_pow;   // [257]           stress_decay^n
     const double* inv_cnt_norm; // [norm_window+1] 1/n, [0] = 0
     const double* clog2c;       // [max(dir_window, mid_window)+2]  c*log2(c), [0] = 0
