@@ -46,9 +46,10 @@ __device__ __noinline__ void lob_sums_direct(const double* __restrict__ bid_px, 
     *ask_lw = al;
 }
 
-// pw2 = decay^(1,2,4,8,16,32) (kernel-parameter constants: operands, not loads); pw[n] = decay^n per lane
-__device__ __forceinline__ double ema_scan(double b, const double (&pw2)[6], const double* __restrict__ pw, double carry_in, double* sWarp,
-                                           int lane, int warp, double& carry_out) {
+// The EMA y_t = decay * y_{t-1} + b_t over a 256-row chunk, as a scan of affine maps.  pw2 = decay^(1,2,4,8,16,32)
+// (kernel-parameter constants: operands, not loads); pw[n] = decay^n per lane.  Two halves around ONE block barrier so
+// that several EMAs share it: ema_warp (in-warp scan, publishes the warp's total), then ema_block (carries across warps).
+__device__ __forceinline__ double ema_warp(double b, const double (&pw2)[6], double* sWarp, int lane, int warp) {
     double v = b;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -56,9 +57,11 @@ __device__ __forceinline__ double ema_scan(double b, const double (&pw2)[6], con
         const double t = shfl_up_d(v, d);
         if (lane >= d) v = pw2[k] * t + v;
     }
-    const double pl = __ldg(pw + lane + 1);
     if (lane == 31) sWarp[warp] = v;
-    __syncthreads();
+    return v;
+}
+__device__ __forceinline__ double ema_block(double v, const double (&pw2)[6], double pl, double carry_in, const double* sWarp, int warp,
+                                            double& carry_out) {
     const double p32 = pw2[5];
     double cw = carry_in, co = carry_in;
 #pragma unroll
@@ -70,6 +73,9 @@ __device__ __forceinline__ double ema_scan(double b, const double (&pw2)[6], con
     return pl * cw + v;
 }
 
+#ifndef MRP_BOOK_NS
+#define MRP_BOOK_NS 2
+#endif
 #ifndef MRP_BOOK_MINB
 #define MRP_BOOK_MINB 2
 #endif
@@ -166,17 +172,18 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     int64_t ic = wa;   // chunk of the next batch to request
     int ib = 0;        // its level group
     int nreq = 0;      // batches requested so far
-    auto request = [&]() {   // warp 0 only
+    auto request = [&]() {   // every warp requests its share of the batch's 4*LG runs: (array, level) pairs warp, warp+8, ...
         if (ic < rb) {
             const int s = nreq % NS;
             if (nreq >= NS) mbar_wait(&sEmpty[s], (uint32_t)((nreq / NS - 1) & 1));
-            if (lane < 4 * LG) {
-                const int a = lane / LG, g = lane - a * LG;
+            BookStage<LG>& S = stg[s];
+            const int64_t r_end = ic + kThreads < rb ? ic + kThreads : rb;
+            for (int pr = warp; pr < 4 * LG; pr += kWarps) {   // warp-uniform: one lane issues
+                const int a = pr / LG, g = pr - a * LG;
                 const bool px = a < 2;
                 const bool prev_row = !px && ic > sr0;                  // sizes also bring the row before the chunk
                 const int64_t lvl = (int64_t)(ib * LG + g) * N;
                 const int64_t r_first = ic - (prev_row ? 1 : 0);
-                const int64_t r_end = ic + kThreads < rb ? ic + kThreads : rb;
                 const char* base = a == 0 ? reinterpret_cast<const char*>(in.bid_px)
                                  : a == 1 ? reinterpret_cast<const char*>(in.ask_px)
                                  : a == 2 ? reinterpret_cast<const char*>(in.bid_sz) : reinterpret_cast<const char*>(in.ask_sz);
@@ -186,21 +193,21 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
                 const uintptr_t q0 = p0 & ~(uintptr_t)15, q1 = (p1 + 15) & ~(uintptr_t)15;
                 const uint32_t bytes = (uint32_t)(q1 - q0);
                 const int sh = (int)((p0 - q0) >> esh) + (prev_row ? 1 : 0) + (px ? 0 : kSzPad);
-                BookStage<LG>& S = stg[s];
                 void* dst = a == 0 ? (void*)&S.bp[g][0] : a == 1 ? (void*)&S.ap[g][0] : a == 2 ? (void*)&S.bs[g][kSzPad] : (void*)&S.as[g][kSzPad];
-                reinterpret_cast<int*>(&S.shift[g])[a] = sh;
-                mbar_expect_tx(&sFull[s], bytes);
-                bulk_g2s(dst, reinterpret_cast<const void*>(q0), bytes, &sFull[s]);
+                if (lane == 0) {
+                    reinterpret_cast<int*>(&S.shift[g])[a] = sh;
+                    mbar_expect_tx(&sFull[s], bytes);
+                    bulk_g2s(dst, reinterpret_cast<const void*>(q0), bytes, &sFull[s]);
+                }
             }
             ++nreq;
             if (++ib == nb) { ib = 0; ic += kThreads; }
         }
     };
-    if (warp == 0) {
 #pragma unroll
-        for (int s = 0; s < NS - 1; ++s) request();
-    }
+    for (int s = 0; s < NS - 1; ++s) request();
     int nuse = 0;      // batches consumed so far
+    const double plOfi = __ldg(P.ofi_pow + lane + 1), plSt = __ldg(P.stress_pow + lane + 1);   // decay^(lane+1)
 
     for (int64_t c0 = wa; c0 < rb; c0 += kThreads, buf ^= 1) {
         const int64_t t = c0 + tid;
@@ -225,7 +232,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         int8_t* __restrict__ obd = out.bdir + tc;
         int8_t* __restrict__ oad = out.adir + tc;
         for (int i0 = 0; i0 < L; i0 += LG) {
-            if (warp == 0) request();   // keeps NS-1 batches in flight
+            request();   // keeps NS-1 batches in flight
             const int sidx = nuse % NS;
             mbar_wait(&sFull[sidx], (uint32_t)((nuse / NS) & 1));
             ++nuse;
@@ -332,8 +339,11 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         if (pliq > 0.0) raw_stress = -((liq - pliq) / pliq);
 
         double coOfi, coSt;
-        const double ofi = ema_scan(act ? P.ofi_alpha * x_ofi : 0.0, P.ofi_pw2, P.ofi_pow, yOfi, sWOfi, lane, warp, coOfi);  // :133
-        const double stress = ema_scan(act ? P.stress_alpha * raw_stress : 0.0, P.stress_pw2, P.stress_pow, ySt, sWSt, lane, warp, coSt);  // :311-313
+        const double vOfi = ema_warp(act ? P.ofi_alpha * x_ofi : 0.0, P.ofi_pw2, sWOfi, lane, warp);            // :133
+        const double vSt = ema_warp(act ? P.stress_alpha * raw_stress : 0.0, P.stress_pw2, sWSt, lane, warp);  // :311-313
+        __syncthreads();
+        const double ofi = ema_block(vOfi, P.ofi_pw2, plOfi, yOfi, sWOfi, warp, coOfi);
+        const double stress = ema_block(vSt, P.stress_pw2, plSt, ySt, sWSt, warp, coSt);
         yOfi = coOfi;
         ySt = coSt;
         if (tid == kThreads - 1) sCarLiq = liq;
@@ -399,7 +409,7 @@ static cudaError_t launch_book_t(const DevInputs& in, const DevOutputs& out, con
 cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
                         const DevParams& P, cudaStream_t st) {
     const int L = P.L;
-    if (L % 5 == 0) return launch_book_t<5, 2>(in, out, segs, nseg, P, st);
+    if (L % 5 == 0) return launch_book_t<5, MRP_BOOK_NS>(in, out, segs, nseg, P, st);
     if (L % 4 == 0) return launch_book_t<4, 2>(in, out, segs, nseg, P, st);
     if (L % 2 == 0) return launch_book_t<2, 3>(in, out, segs, nseg, P, st);
     return launch_book_t<1, 4>(in, out, segs, nseg, P, st);
