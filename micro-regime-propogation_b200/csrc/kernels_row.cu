@@ -167,41 +167,49 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     int buf = 0;
     __syncthreads();
 
-    // ---- staging pipeline: batch b = (chunk, level group) lands in stage b % NS; warp 0 requests batch b + NS - 1 when it
-    // starts batch b, after every warp has released the stage's previous occupant
+    // ---- staging pipeline: batch b = (chunk, level group) lands in stage b % NS; batch b + NS - 1 is requested when batch b
+    // starts, after every warp has released the stage's previous occupant.  The batch's 4*LG runs are spread over the
+    // warps: lane j of warp w owns run w + 8 j (array a, level g of the group) and keeps its invariants in registers.
     int64_t ic = wa;   // chunk of the next batch to request
     int ib = 0;        // its level group
     int nreq = 0;      // batches requested so far
-    auto request = [&]() {   // every warp requests its share of the batch's 4*LG runs: (array, level) pairs warp, warp+8, ...
+    const int my_run = warp + kWarps * lane;
+    const bool has_run = my_run < 4 * LG;
+    const int run_a = has_run ? my_run / LG : 0, run_g = has_run ? my_run - run_a * LG : 0;
+    const bool run_px = run_a < 2;
+    const int run_esh = run_px ? 3 : 2;
+    const uintptr_t run_base = reinterpret_cast<uintptr_t>(run_a == 0 ? (const void*)in.bid_px : run_a == 1 ? (const void*)in.ask_px
+                                                          : run_a == 2 ? (const void*)in.bid_sz : (const void*)in.ask_sz);
+    // byte offset of the run's landing slot and of its shift word inside a stage
+    const uint32_t run_dst = run_a == 0 ? (uint32_t)(offsetof(BookStage<LG>, bp) + run_g * kPxSlot * 8)
+                           : run_a == 1 ? (uint32_t)(offsetof(BookStage<LG>, ap) + run_g * kPxSlot * 8)
+                           : run_a == 2 ? (uint32_t)(offsetof(BookStage<LG>, bs) + (run_g * kSzSlot + kSzPad) * 4)
+                                        : (uint32_t)(offsetof(BookStage<LG>, as) + (run_g * kSzSlot + kSzPad) * 4);
+    const uint32_t run_shw = (uint32_t)(offsetof(BookStage<LG>, shift) + run_g * 16 + run_a * 4);
+    int64_t run_e = (int64_t)run_g * N + wa;                      // element index of (level, chunk's first row) of the next request
+    const int64_t step_in = (int64_t)LG * N;                      // next level group, same chunk
+    const int64_t step_out = kThreads - (int64_t)(nb - 1) * LG * N;   // first level group of the next chunk
+    auto request = [&]() {
         if (ic < rb) {
             const int s = nreq % NS;
             if (nreq >= NS) mbar_wait(&sEmpty[s], (uint32_t)((nreq / NS - 1) & 1));
-            BookStage<LG>& S = stg[s];
-            const int64_t r_end = ic + kThreads < rb ? ic + kThreads : rb;
-            for (int pr = warp; pr < 4 * LG; pr += kWarps) {   // warp-uniform: one lane issues
-                const int a = pr / LG, g = pr - a * LG;
-                const bool px = a < 2;
-                const bool prev_row = !px && ic > sr0;                  // sizes also bring the row before the chunk
-                const int64_t lvl = (int64_t)(ib * LG + g) * N;
-                const int64_t r_first = ic - (prev_row ? 1 : 0);
-                const char* base = a == 0 ? reinterpret_cast<const char*>(in.bid_px)
-                                 : a == 1 ? reinterpret_cast<const char*>(in.ask_px)
-                                 : a == 2 ? reinterpret_cast<const char*>(in.bid_sz) : reinterpret_cast<const char*>(in.ask_sz);
-                const int esh = px ? 3 : 2;
-                const uintptr_t p0 = reinterpret_cast<uintptr_t>(base) + ((uintptr_t)(lvl + r_first) << esh);
-                const uintptr_t p1 = reinterpret_cast<uintptr_t>(base) + ((uintptr_t)(lvl + r_end) << esh);
+            if (has_run) {
+                const int prev = (!run_px && ic > sr0) ? 1 : 0;   // sizes also bring the row before the chunk
+                const int64_t left = rb - ic;
+                const int nrows = left < kThreads ? (int)left : kThreads;
+                const uintptr_t p0 = run_base + ((uintptr_t)(run_e - prev) << run_esh);
+                const uintptr_t p1 = p0 + ((uintptr_t)(nrows + prev) << run_esh);
                 const uintptr_t q0 = p0 & ~(uintptr_t)15, q1 = (p1 + 15) & ~(uintptr_t)15;
                 const uint32_t bytes = (uint32_t)(q1 - q0);
-                const int sh = (int)((p0 - q0) >> esh) + (prev_row ? 1 : 0) + (px ? 0 : kSzPad);
-                void* dst = a == 0 ? (void*)&S.bp[g][0] : a == 1 ? (void*)&S.ap[g][0] : a == 2 ? (void*)&S.bs[g][kSzPad] : (void*)&S.as[g][kSzPad];
-                if (lane == 0) {
-                    reinterpret_cast<int*>(&S.shift[g])[a] = sh;
-                    mbar_expect_tx(&sFull[s], bytes);
-                    bulk_g2s(dst, reinterpret_cast<const void*>(q0), bytes, &sFull[s]);
-                }
+                const int sh = (int)((p0 - q0) >> run_esh) + prev + (run_px ? 0 : kSzPad);
+                unsigned char* sbase = reinterpret_cast<unsigned char*>(&stg[s]);
+                *reinterpret_cast<int*>(sbase + run_shw) = sh;
+                mbar_expect_tx(&sFull[s], bytes);
+                bulk_g2s(sbase + run_dst, reinterpret_cast<const void*>(q0), bytes, &sFull[s]);
             }
             ++nreq;
-            if (++ib == nb) { ib = 0; ic += kThreads; }
+            if (++ib == nb) { ib = 0; ic += kThreads; run_e += step_out; }
+            else run_e += step_in;
         }
     };
 #pragma unroll
@@ -227,6 +235,8 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         double raw_ofi = 0.0, liq_b = 0.0, liq_a = 0.0;
         double bid_depth = 0.0, ask_depth = 0.0, bid_lw = 0.0, ask_lw = 0.0;
         bool oor = false;  // some level outside the log1p series range
+        double spread0 = 0.0;        // log ask0 - log bid0 from the level-0 series
+        bool spread0_ok = false;
         double p0b = 0, p1b = 0, p0a = 0, p1a = 0;
         int s0b = 0, s1b = 0, s0a = 0, s1a = 0;
         int8_t* __restrict__ obd = out.bdir + tc;
@@ -266,42 +276,59 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
                 const double bid_contrib = (double)(bd * bs) * w;   // (int8 * int) * double, as the reference
                 const double ask_contrib = (double)(ad * as) * w;
                 raw_ofi += bid_contrib - ask_contrib;      // :125
-                const double fbs = (double)bs, fas = (double)as;
-                if (i < P.stress_levels) {   // :282-299
+                if (i == 0) { p0b = bp; p0a = ap; s0b = bs; s0a = as; }
+                if (i == 1) { p1b = bp; p1a = ap; s1b = bs; s1a = as; }
+                {   // :164-175, :189-200 — branch-free.  A side without a price (0, negative, NaN) takes part with the
+                    // midprice as its price and size 0: distance 0, weight 0.  Out-of-range arguments only raise the row's flag.
+                    const bool hb = bp > 0, ha = ap > 0;
+                    const double ub_ = ((hb ? bp : midp) - midp) * inv_mid, ua_ = ((ha ? ap : midp) - midp) * inv_mid;
+                    oor |= !(fabs(ub_) <= kSeriesMax) || !(fabs(ua_) <= kSeriesMax);
+                    const double sb_ = log1p_series(ub_), sa_ = log1p_series(ua_);
+                    const double fbe = (double)(hb ? bs : 0), fae = (double)(ha ? as : 0);
+                    bid_lw = fma(fabs(sb_), fbe, bid_lw);   // |log mid - log bp| * size
+                    ask_lw = fma(fabs(sa_), fae, ask_lw);   // |log ap - log mid| * size
+                    bid_depth += fbe;
+                    ask_depth += fae;
+                    if (i == 0) {   // log ask0 - log bid0 (:33) = log(ask0 / mid) - log(bid0 / mid)
+                        spread0 = sa_ - sb_;
+                        spread0_ok = hb && ha;
+                    }
+                }
+            }
+            if (i0 < P.stress_levels) {   // :282-299 — the levels nearest the touch (re-read from the stage: a handful of LDS)
+#pragma unroll
+                for (int g = 0; g < LG; ++g) {
+                    const int i = i0 + g;
+                    if (i >= P.stress_levels) break;
+                    const int4 sh = S.shift[g];
+                    const double bp = S.bp[g][sh.x + tid], ap = S.ap[g][sh.y + tid];
+                    const double fbs = (double)S.bs[g][sh.z + tid], fas = (double)S.as[g][sh.w + tid];
                     const bool ub = bp > 0.0 && fbs >= P.stress_min_size;
                     const bool ua = ap > 0.0 && fas >= P.stress_min_size;
                     if (i == 0) {  // distance 0 exactly: weight 1
-                        if (ub) liq_b += fbs;
-                        if (ua) liq_a += fas;
-                    } else {
-                        const double xb = -(bb - bp) * P.stress_distance_decay, xa = -(ap - ba) * P.stress_distance_decay;
-                        if (g >= 1 && g <= kStressCache && i0 == 0) {
-                            // near-touch weights exp(-distance*decay): on a regular tick grid the arguments repeat row after
-                            // row, so each thread remembers its last bid-side argument per level and the ask side shares it
-                            // when the book is symmetric
-                            const int j = (g >= 1 && g <= kStressCache) ? g - 1 : 0;
+                        liq_b += ub ? fbs : 0.0;
+                        liq_a += ua ? fas : 0.0;
+                        continue;
+                    }
+                    const double xb = -(bb - bp) * P.stress_distance_decay, xa = -(ap - ba) * P.stress_distance_decay;
+                    if (g >= 1 && g <= kStressCache && i0 == 0) {
+                        // weights exp(-distance*decay): on a regular tick grid the arguments repeat row after row, so each
+                        // thread remembers its last bid-side argument per level; the ask side shares it when the book is symmetric
+                        const int j = (g >= 1 && g <= kStressCache) ? g - 1 : 0;
+                        if ((ub && xb != cx[j]) || (ua && xa != cx[j])) {   // rare: something moved
                             if (ub) {
                                 if (xb != cx[j]) { cx[j] = xb; ce[j] = exp(xb); }
                                 liq_b += ce[j] * fbs;
                             }
                             if (ua) liq_a += ((xa == cx[j]) ? ce[j] : exp(xa)) * fas;
                         } else {
-                            if (ub) liq_b += exp(xb) * fbs;
-                            if (ua) liq_a += exp(xa) * fas;
+                            liq_b += ub ? ce[j] * fbs : 0.0;
+                            liq_a += ua ? ce[j] * fas : 0.0;
                         }
+                    } else {
+                        if (ub) liq_b += exp(xb) * fbs;
+                        if (ua) liq_a += exp(xa) * fas;
                     }
-                }
-                if (i == 0) { p0b = bp; p0a = ap; s0b = bs; s0a = as; }
-                if (i == 1) { p1b = bp; p1a = ap; s1b = bs; s1a = as; }
-                {   // :164-175, :189-200 — branch-free: out-of-range arguments only raise the row's flag
-                    const double ub_ = (bp - midp) * inv_mid, ua_ = (ap - midp) * inv_mid;
-                    const bool hb = bp > 0, ha = ap > 0;
-                    oor |= (hb && !(fabs(ub_) <= kSeriesMax)) || (ha && !(fabs(ua_) <= kSeriesMax));
-                    const double lb = fabs(log1p_series(ub_)), la = fabs(log1p_series(ua_));
-                    bid_lw += hb ? lb * fbs : 0.0;   // |log mid - log bp| * size
-                    ask_lw += ha ? la * fas : 0.0;   // |log ap - log mid| * size
-                    bid_depth += hb ? fbs : 0.0;
-                    ask_depth += ha ? fas : 0.0;
                 }
             }
             obd += (int64_t)LG * N;
@@ -350,12 +377,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
 
         if (full) {
             // log_spread = log(ask0) - log(bid0), :33
-            double log_spread;
-            {
-                const double u = (ba - bb) / bb;
-                if (bb > 0.0 && fabs(u) <= kSeriesMax) log_spread = log1p_series(u);
-                else log_spread = log(ba) - log(bb);
-            }
+            const double log_spread = (spread0_ok && !oor) ? spread0 : log(ba) - log(bb);
             // log_return, :37-42: the normaliser deque holds min(t, W) earlier rows when row t asks for index `lag`
             const int64_t tl = t - sr0;
             const int64_t have = tl < P.norm_window ? tl : P.norm_window;
