@@ -28,3 +28,10 @@ def _built():
     if not os.path.exists(hostlib.HOST_LIB_PATH):
         b.build_host()
     yield
+
+
+@pytest.fixture
+def small_segments(monkeypatch):
+    """Row segments of 257 rows: every halo / restart / partial-chunk path of the segment kernels runs many times."""
+    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "257")
+    yield

@@ -73,7 +73,13 @@ def run_gpu(batch, params=None, mode="upload"):
                 dev[k] = v
             else:
                 t = torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else (v.view(np.int32) if v.dtype == np.uint32 else v))
-                dev[k] = t.cuda()
+                if mode == "device_offset":
+                    # every array starts one element past an allocation boundary: bases are only 8 / 4 / 1-byte aligned
+                    flat = torch.empty(t.numel() + 1, dtype=t.dtype, device="cuda")
+                    flat[1:].copy_(t.reshape(-1))
+                    dev[k] = flat[1:].view(t.shape)
+                else:
+                    dev[k] = t.cuda()
         eng.bind_device(dev)
     eng.run()
     out = eng.download()

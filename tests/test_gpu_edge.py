@@ -21,12 +21,6 @@ def _check(batch, **kw):
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def small_segments(monkeypatch):
-    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "257")
-    yield
-
-
 def test_small_segments_halo_and_restart(small_segments):
     _check(make_host_batch([synth.SynthSpec(n_rows=5000, seed=31, variable_cursors=True)]))
 
