@@ -210,7 +210,7 @@ int setup_params(mrp_fg_ctx* c) {
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.stress_decay, (long double)n));
     const size_t o_i = tab.size();
     for (int n = 0; n <= p.norm_window; ++n) tab.push_back(n > 0 ? 1.0 / (double)n : 0.0);
-    for (int n = 0; n < 160; ++n) tab.push_back(0.0);  // the normaliser's idle lanes of a partial step read past 1/W
+    for (int n = 0; n < 256; ++n) tab.push_back(0.0);  // idle lanes of the normaliser's last partial block read past 1/W
     const size_t o_h = tab.size();
     const int hmax = std::max(p.dir_window, p.mid_window) + 1;
     for (int n = 0; n <= hmax; ++n) tab.push_back(n > 0 ? (double)((long double)n * log2l((long double)n)) : 0.0);

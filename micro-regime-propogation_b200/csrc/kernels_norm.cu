@@ -23,6 +23,8 @@
 //
 // k_normalize_faithful re-enacts the reference's add-then-evict chain in its exact rounding order
 // (one thread per stream x feature; serial, for validation only).
+#include <cstdlib>
+
 #include "mrp_device.cuh"
 
 namespace mrp {
@@ -276,6 +278,297 @@ k_normalize(const DevOutputs out, const int64_t N, const DevTile* __restrict__ t
     }
 }
 
+// ================================================================================================
+// k_normalize_runs — the same two passes with the tile streamed through shared memory by the copy engine.
+//
+// Blocks of 224 rows are fetched by ONE bulk asynchronous copy per array (cp.async.bulk + mbarrier, issued by lane 0 two
+// blocks ahead), a lane owns 7 CONSECUTIVE rows of the block (odd run length: 64-bit shared accesses at lane stride 7 are
+// conflict-free), so the in-block prefix is seven serial adds in registers and the warp scan is paid once per 224 rows
+// instead of once per 128; z-scores leave through shared memory and one bulk store per block.  No lane ever issues a
+// global load for the data: ~45 instructions per z-score instead of ~110.
+// Source / destination addresses are rounded to the 16 bytes the copy engine wants; the element shift that results
+// (0 or 1) is added to the slot index, and the at most two edge rows of a block that a 16-byte store cannot cover are
+// written by lane 0.
+// ================================================================================================
+constexpr int kRun = 7;                  // rows per lane per block
+constexpr int kBlk = 32 * kRun;          // 224
+constexpr int kBlkSlot = kBlk + 2;       // + the alignment shift, padded to 16 bytes
+constexpr int kSlots = 6;                // pass 1 uses all six as a ring; pass 2: x = 0,1  lag = 2,3  z = 4,5
+struct __align__(16) NormWarpStage {
+    double slot[kSlots][kBlkSlot];
+    uint64_t full[kSlots];               // pass 1: one per slot; pass 2: full[0..1] (a block's x and lag complete together)
+};
+
+// lane 0: request rows [0, rows) starting at src into slot (16-byte rounding on both ends); returns the bytes requested
+__device__ __forceinline__ uint32_t block_bytes(const double* src, int rows) {
+    const uintptr_t p0 = reinterpret_cast<uintptr_t>(src), p1 = p0 + (uintptr_t)rows * 8u;
+    return (uint32_t)(((p1 + 15) & ~(uintptr_t)15) - (p0 & ~(uintptr_t)15));
+}
+__device__ __forceinline__ void block_load(double* slot, const double* src, int rows, uint64_t* bar) {
+    const uintptr_t q0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
+    bulk_g2s(slot, reinterpret_cast<const void*>(q0), block_bytes(src, rows), bar);
+}
+__device__ __forceinline__ int block_shift(const double* src) { return (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1u); }
+
+// per-warp staging state: bit i = the phase parity the next wait on full[i] expects
+struct RunPipe {
+    uint32_t phase;
+    __device__ __forceinline__ void wait(NormWarpStage& S, int i) {
+        mbar_wait(&S.full[i], (phase >> i) & 1u);
+        phase ^= 1u << i;
+    }
+};
+
+// pass 1: tile total of one column; the six slots form a ring, so six blocks (10 KB per warp) are in flight from HBM
+__device__ __forceinline__ void run_total(NormWarpStage& S, RunPipe& rp, const double* __restrict__ x, const int n, const int64_t tl0,
+                                          double* __restrict__ tot, NormPoison* __restrict__ q, int* __restrict__ any_poison, const int lane) {
+    const int nblk = (n + kBlk - 1) / kBlk;
+    auto issue = [&](int j, int sl) {
+        if (lane == 0) {
+            const int rows = min(kBlk, n - j * kBlk);
+            const double* src = x + (int64_t)j * kBlk;
+            mbar_expect_tx(&S.full[sl], block_bytes(src, rows));
+            block_load(S.slot[sl], src, rows, &S.full[sl]);
+        }
+    };
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j)
+        if (j < nblk) issue(j, j);
+    double s = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
+    unsigned int fn = 0xffffffffu, fp = 0xffffffffu, fm = 0xffffffffu;
+    int sl = 0;
+    for (int j = 0; j < nblk; ++j) {
+        rp.wait(S, sl);
+        const int rows = min(kBlk, n - j * kBlk);
+        const double* __restrict__ xs = S.slot[sl] + block_shift(x + (int64_t)j * kBlk) + lane * kRun;
+        double v[kRun];
+        if (rows == kBlk) {
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) v[k] = xs[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) v[k] = lane * kRun + k < rows ? xs[k] : 0.0;
+        }
+        uint32_t m = 0u;  // largest |high word|: >= 0x7ff00000 means an infinity or a NaN
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+            if (k & 1) { t1 += v[k]; t2 = fma(v[k], v[k], t2); }
+            else { s += v[k]; s2 = fma(v[k], v[k], s2); }
+            m = max(m, (uint32_t)__double2hiint(v[k]) & 0x7fffffffu);
+        }
+        if (m >= 0x7ff00000u) {  // rare: record where the column first goes non-finite (stream-local rows)
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) {
+                const unsigned int r = (unsigned int)(tl0 + j * kBlk + lane * kRun + k);
+                const double y = v[k];
+                if (y != y) fn = min(fn, r);
+                else if (y == __longlong_as_double(0x7ff0000000000000ll)) fp = min(fp, r);
+                else if (y == __longlong_as_double(0xfff0000000000000ll)) fm = min(fm, r);
+            }
+        }
+        __syncwarp();   // every lane has read the slot
+        if (j + kSlots < nblk) issue(j + kSlots, sl);
+        if (++sl == kSlots) sl = 0;
+    }
+    if ((fn & fp & fm) != 0xffffffffu) {
+        if (fn != 0xffffffffu) atomicMin(&q->first_nan, fn);
+        if (fp != 0xffffffffu) atomicMin(&q->first_pinf, fp);
+        if (fm != 0xffffffffu) atomicMin(&q->first_ninf, fm);
+        *any_poison = 1;
+    }
+    s += t1;
+    s2 += t2;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) {
+        __stcg(tot, publishable(s));
+        __stcg(tot + kNF, publishable(s2));
+    }
+}
+
+// pass 2: z-scores of one column of the tile
+template <bool LAG>
+__device__ __forceinline__ void run_zscores(NormWarpStage& S, RunPipe& rp, const double* __restrict__ x, double* __restrict__ z, const int n,
+                                            const int W, const int64_t tl0, const double* __restrict__ pred_tot, const int nb,
+                                            const double* __restrict__ inv_n, int32_t* __restrict__ cnt_out, const int lane) {
+    const double* __restrict__ xl = x - W;
+    const int nblk = (n + kBlk - 1) / kBlk;
+    auto issue = [&](int j) {
+        if (lane == 0) {
+            const int rows = min(kBlk, n - j * kBlk);
+            const double* src = x + (int64_t)j * kBlk;
+            const int s = j & 1;
+            uint32_t bytes = block_bytes(src, rows);
+            if (LAG) bytes += block_bytes(src - W, rows);
+            mbar_expect_tx(&S.full[s], bytes);
+            block_load(S.slot[s], src, rows, &S.full[s]);
+            if (LAG) block_load(S.slot[2 + s], src - W, rows, &S.full[s]);
+        }
+    };
+    // the first blocks are in flight while the predecessors' totals are collected
+    if (nblk > 0) issue(0);
+    if (nblk > 1) issue(1);
+    double run1 = 0.0, run2 = 0.0;
+    {
+        double h1 = 0.0, h2 = 0.0;
+        for (int j0 = 0; j0 < nb; j0 += 32) {
+            if (j0 + lane < nb) {
+                const double* __restrict__ tp = pred_tot + (int64_t)(j0 + lane) * 2 * kNF;
+                const unsigned long long ua = peek_total(tp), ub = peek_total(tp + kNF);  // both in flight together
+                h1 += poll_total(tp, ua);
+                h2 += poll_total(tp + kNF, ub);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            h1 += __shfl_xor_sync(0xffffffffu, h1, d);
+            h2 += __shfl_xor_sync(0xffffffffu, h2, d);
+        }
+        run1 = h1;
+        run2 = h2;
+    }
+    const double invW = __ldg(inv_n + W);
+    const int r0 = lane * kRun;    // this lane's first row of a block
+    for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        rp.wait(S, st);
+        const int rows = min(kBlk, n - j * kBlk);
+        const double* __restrict__ xs = S.slot[st] + block_shift(x + (int64_t)j * kBlk) + r0;
+        const double* __restrict__ ls = S.slot[2 + st] + block_shift(xl + (int64_t)j * kBlk) + r0;
+        double v[kRun], l[kRun], p1[kRun], p2[kRun];
+        if (rows == kBlk) {
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) {
+                v[k] = xs[k];
+                if (LAG) l[k] = ls[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) {
+                const bool ok = r0 + k < rows;
+                v[k] = ok ? xs[k] : 0.0;
+                if (LAG) l[k] = ok ? ls[k] : 0.0;
+            }
+        }
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+            if (LAG) {
+                a1 += v[k] - l[k];
+                a2 += fma(v[k], v[k], -(l[k] * l[k]));
+            } else {
+                a1 += v[k];
+                a2 = fma(v[k], v[k], a2);
+            }
+            p1[k] = a1;
+            p2[k] = a2;
+        }
+        __syncwarp();   // every lane has read the stage
+        if (j + 2 < nblk) issue(j + 2);
+        double s1 = a1, s2 = a2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double u1 = shfl_up_d(s1, d), u2 = shfl_up_d(s2, d);
+            if (lane >= d) { s1 += u1; s2 += u2; }
+        }
+        // exclusive offsets by shuffle, not by subtraction: a NaN in this lane's rows must not reach the rows before it
+        const double x1 = shfl_up_d(s1, 1), x2 = shfl_up_d(s2, 1);
+        const double b1 = run1 + (lane ? x1 : 0.0), b2 = run2 + (lane ? x2 : 0.0);
+        // the z slot of two blocks ago must have left shared memory
+        if (j >= 2) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+        }
+        double* __restrict__ zg = z + (int64_t)j * kBlk;
+        const int zsh = block_shift(zg);
+        double* __restrict__ zs = S.slot[4 + st] + zsh;
+        // a tile without lag lies inside the first window of its stream (tl0 + n <= W): 1/n needs no clamp there
+        const double* __restrict__ inv_fill = inv_n + (LAG ? 0 : tl0 + (int64_t)j * kBlk + r0 + 1);
+        double var[kRun], mean[kRun];
+        uint32_t okmin = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < kRun; ++k) {
+            const double e1 = b1 + p1[k], e2 = b2 + p2[k];
+            double inv = invW;
+            if (!LAG) inv = __ldg(inv_fill + k);  // the window is still filling: n = rows so far (feature_normalizer.cpp:71)
+            mean[k] = e1 * inv;                             // :62
+            var[k] = e2 * inv - mean[k] * mean[k];          // :63
+            // fast path of :67 — positive, normal, far from the range ends
+            okmin = min(okmin, (uint32_t)((uint32_t)(__double2hiint(var[k]) - 0x03000000) < 0x79000000u));
+        }
+        if (okmin != 0u) {
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) zs[r0 + k] = (v[k] - mean[k]) * rsqrt_pos(var[k]);   // :68
+        } else {   // some variance is zero, negative, NaN or extreme: std = 1 unless the variance is positive (:67)
+#pragma unroll
+            for (int k = 0; k < kRun; ++k) {
+                const double rstd = var[k] > 0.0 ? rsqrt(var[k]) : 1.0;
+                zs[r0 + k] = (v[k] - mean[k]) * rstd;
+            }
+        }
+        fence_proxy_async_smem();   // the copy engine reads what the lanes just wrote
+        __syncwarp();
+        if (lane == 0) {
+            // rows [ra, ra + cnt) are covered by 16-byte units; at most one row on either side is stored directly
+            const int ra = zsh, cnt = (rows - ra) & ~1;
+            if (ra && rows > 0) zg[0] = zs[0];
+            if (cnt > 0) bulk_s2g(zg + ra, zs + ra, (uint32_t)cnt * 8u);
+            bulk_commit();
+            if (ra + cnt < rows) zg[rows - 1] = zs[rows - 1];
+        }
+        if (cnt_out) {
+#pragma unroll
+            for (int k = 0; k < kRun; ++k)
+                if (r0 + k < rows) {
+                    const int64_t tl = tl0 + (int64_t)j * kBlk + r0 + k;
+                    cnt_out[(int64_t)j * kBlk + r0 + k] = tl + 1 >= W ? W : (int)(tl + 1);
+                }
+        }
+        run1 += __shfl_sync(0xffffffffu, s1, 31);
+        run2 += __shfl_sync(0xffffffffu, s2, 31);
+    }
+    if (lane == 0) bulk_wait_read<0>();   // shared memory may be reused (and the CTA may exit) only after the stores have read it
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kNormThreads, 2)
+k_normalize_runs(const DevOutputs out, const int64_t N, const DevTile* __restrict__ tiles, double* __restrict__ tile_tot,
+                 unsigned int* __restrict__ ticket, NormPoison* __restrict__ poison, int* __restrict__ any_poison, const DevParams P) {
+    extern __shared__ __align__(16) unsigned char norm_dyn[];
+    __shared__ int sId;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    NormWarpStage& S = reinterpret_cast<NormWarpStage*>(norm_dyn)[warp];
+    if (tid == 0) sId = (int)atomicAdd(ticket, 1u);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i) mbar_init(&S.full[i], 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    RunPipe rp{0u};
+    const int id = sId;
+    const DevTile T = tiles[id];
+    const int n = T.n, W = P.norm_window;
+    const int64_t tl0 = (int64_t)T.index * P.tile_rows;  // stream-local index of the tile's first row
+    for (int c = warp; c < kNF; c += kNormWarps) {
+        const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
+        run_total(S, rp, x, n, tl0, tile_tot + (int64_t)id * 2 * kNF + c, poison + (int64_t)T.stream * kNF + c, any_poison, lane);
+    }
+    const int nb = T.index < P.tiles_back ? T.index : P.tiles_back;  // preceding tiles inside the window
+    const bool has_lag = T.index >= P.tiles_back;
+    for (int c = warp; c < kNF; c += kNormWarps) {
+        const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
+        double* __restrict__ z = out.norm + (int64_t)c * N + T.row;
+        const double* pred = tile_tot + (int64_t)(id - nb) * 2 * kNF + c;
+        int32_t* cnt_out = (c == 0 && out.counts) ? out.counts + (int64_t)MRP_C_NORM_N * N + T.row : nullptr;
+        if (has_lag) run_zscores<true>(S, rp, x, z, n, W, tl0, pred, nb, P.inv_cnt_norm, cnt_out, lane);
+        else run_zscores<false>(S, rp, x, z, n, W, tl0, pred, nb, P.inv_cnt_norm, cnt_out, lane);
+    }
+}
+
 // Rewrites the z-scores of columns that went non-finite, following the reference's running-sum arithmetic
 // (feature_normalizer.cpp:37-51,61-69):  a NaN makes sum / sum2 NaN for ever; an infinity makes sum = +-inf and
 // sum2 = +inf (variance NaN -> std 1 -> z = x - (+-inf)) until a NaN, an infinity of the other sign or its own
@@ -352,8 +645,24 @@ cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* ti
     int* any = reinterpret_cast<int*>(static_cast<unsigned char*>(poison) + pb);
     e = cudaMemsetAsync(any, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
-    k_normalize<<<ntiles, kNormThreads, 0, st>>>(out, N, tiles, tile_tot, flags, reinterpret_cast<unsigned int*>(flags + ntiles),
-                                                    static_cast<NormPoison*>(poison), any, P);
+    static const bool use_runs = [] {   // MRP_FG_NORM_KERNEL=scan selects the register-scan kernel (kept for comparison)
+        const char* v = std::getenv("MRP_FG_NORM_KERNEL");
+        return !(v && v[0] == 's');
+    }();
+    if (use_runs) {
+        constexpr int kBytes = (int)sizeof(NormWarpStage) * kNormWarps;
+        static bool ready = false;  // idempotent; a race only repeats the call
+        if (!ready) {
+            e = cudaFuncSetAttribute(k_normalize_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
+            if (e != cudaSuccess) return e;
+            ready = true;
+        }
+        k_normalize_runs<<<ntiles, kNormThreads, kBytes, st>>>(out, N, tiles, tile_tot, reinterpret_cast<unsigned int*>(flags + ntiles),
+                                                               static_cast<NormPoison*>(poison), any, P);
+    } else {
+        k_normalize<<<ntiles, kNormThreads, 0, st>>>(out, N, tiles, tile_tot, flags, reinterpret_cast<unsigned int*>(flags + ntiles),
+                                                        static_cast<NormPoison*>(poison), any, P);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_norm_poison<<<n_streams * kNF, 256, 0, st>>>(out, N, row_off, static_cast<const NormPoison*>(poison), any, P);

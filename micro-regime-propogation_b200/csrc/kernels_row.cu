@@ -85,33 +85,6 @@ constexpr int kStressCache = 4;  // levels 1..4 keep their last exp(-distance*de
 // chunk's 256-row run of that level as ONE copy; nobody spends issue slots or registers on per-row loads.  Source
 // addresses are rounded down / up to the 16 bytes the copy engine wants and every thread adds the resulting element
 // shift (published in the stage header) to its slot index, so any row count and any 8 / 4-byte aligned base works.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 constexpr int kPxSlot = kThreads + 4;    // doubles: 256 rows + the <= 1 element alignment shift, padded to 16 bytes
 constexpr int kSzSlot = kThreads + 12;   // ints: 4 pad + previous row + 256 rows + the <= 3 element shift, padded
 constexpr int kSzPad = 4;                // the copy lands 16 bytes into the slot, so "previous row" of row 0 never indexes below it
