@@ -319,73 +319,86 @@ struct RunPipe {
     }
 };
 
-// pass 1: tile total of one column; the six slots form a ring, so six blocks (10 KB per warp) are in flight from HBM
-__device__ __forceinline__ void run_total(NormWarpStage& S, RunPipe& rp, const double* __restrict__ x, const int n, const int64_t tl0,
-                                          double* __restrict__ tot, NormPoison* __restrict__ q, int* __restrict__ any_poison, const int lane) {
+// pass 1: tile totals of this warp's columns (c0, c0 + 10, ...), one after the other through ONE ring of six slots, so six
+// blocks (10 KB per warp) are in flight from HBM and only the very first block's latency is exposed
+__device__ __forceinline__ void run_totals(NormWarpStage& S, RunPipe& rp, const double* __restrict__ raw, const int64_t N, const int64_t row,
+                                           const int c0, const int n, const int64_t tl0, double* __restrict__ tot0,
+                                           NormPoison* __restrict__ q0, int* __restrict__ any_poison, const int lane) {
     const int nblk = (n + kBlk - 1) / kBlk;
-    auto issue = [&](int j, int sl) {
+    const int ncol = (kNF - c0 + kNormWarps - 1) / kNormWarps;
+    const int total = nblk * ncol;
+    const double* __restrict__ x0 = raw + (int64_t)c0 * N + row;
+    const int64_t col_stride = (int64_t)kNormWarps * N;
+    int ij = 0;              // block and column of the next request
+    int64_t icol = 0;
+    auto issue = [&](int sl) {
         if (lane == 0) {
-            const int rows = min(kBlk, n - j * kBlk);
-            const double* src = x + (int64_t)j * kBlk;
+            const int rows = min(kBlk, n - ij * kBlk);
+            const double* src = x0 + icol + (int64_t)ij * kBlk;
             mbar_expect_tx(&S.full[sl], block_bytes(src, rows));
             block_load(S.slot[sl], src, rows, &S.full[sl]);
         }
+        if (++ij == nblk) { ij = 0; icol += col_stride; }
     };
 #pragma unroll
-    for (int j = 0; j < kSlots; ++j)
-        if (j < nblk) issue(j, j);
-    double s = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
-    unsigned int fn = 0xffffffffu, fp = 0xffffffffu, fm = 0xffffffffu;
-    int sl = 0;
-    for (int j = 0; j < nblk; ++j) {
-        rp.wait(S, sl);
-        const int rows = min(kBlk, n - j * kBlk);
-        const double* __restrict__ xs = S.slot[sl] + block_shift(x + (int64_t)j * kBlk) + lane * kRun;
-        double v[kRun];
-        if (rows == kBlk) {
+    for (int t = 0; t < kSlots; ++t)
+        if (t < total) issue(t);
+    int sl = 0, t = 0;
+    for (int ci = 0; ci < ncol; ++ci) {
+        const double* __restrict__ x = x0 + (int64_t)ci * col_stride;
+        double s = 0.0, s2 = 0.0, t1 = 0.0, t2 = 0.0;
+        unsigned int fn = 0xffffffffu, fp = 0xffffffffu, fm = 0xffffffffu;
+        for (int j = 0; j < nblk; ++j, ++t) {
+            rp.wait(S, sl);
+            const int rows = min(kBlk, n - j * kBlk);
+            const double* __restrict__ xs = S.slot[sl] + block_shift(x + (int64_t)j * kBlk) + lane * kRun;
+            double v[kRun];
+            if (rows == kBlk) {
 #pragma unroll
-            for (int k = 0; k < kRun; ++k) v[k] = xs[k];
-        } else {
+                for (int k = 0; k < kRun; ++k) v[k] = xs[k];
+            } else {
 #pragma unroll
-            for (int k = 0; k < kRun; ++k) v[k] = lane * kRun + k < rows ? xs[k] : 0.0;
-        }
-        uint32_t m = 0u;  // largest |high word|: >= 0x7ff00000 means an infinity or a NaN
-#pragma unroll
-        for (int k = 0; k < kRun; ++k) {
-            if (k & 1) { t1 += v[k]; t2 = fma(v[k], v[k], t2); }
-            else { s += v[k]; s2 = fma(v[k], v[k], s2); }
-            m = max(m, (uint32_t)__double2hiint(v[k]) & 0x7fffffffu);
-        }
-        if (m >= 0x7ff00000u) {  // rare: record where the column first goes non-finite (stream-local rows)
+                for (int k = 0; k < kRun; ++k) v[k] = lane * kRun + k < rows ? xs[k] : 0.0;
+            }
 #pragma unroll
             for (int k = 0; k < kRun; ++k) {
-                const unsigned int r = (unsigned int)(tl0 + j * kBlk + lane * kRun + k);
-                const double y = v[k];
-                if (y != y) fn = min(fn, r);
-                else if (y == __longlong_as_double(0x7ff0000000000000ll)) fp = min(fp, r);
-                else if (y == __longlong_as_double(0xfff0000000000000ll)) fm = min(fm, r);
+                if (k & 1) { t1 += v[k]; t2 = fma(v[k], v[k], t2); }
+                else { s += v[k]; s2 = fma(v[k], v[k], s2); }
             }
-        }
-        __syncwarp();   // every lane has read the slot
-        if (j + kSlots < nblk) issue(j + kSlots, sl);
-        if (++sl == kSlots) sl = 0;
-    }
-    if ((fn & fp & fm) != 0xffffffffu) {
-        if (fn != 0xffffffffu) atomicMin(&q->first_nan, fn);
-        if (fp != 0xffffffffu) atomicMin(&q->first_pinf, fp);
-        if (fm != 0xffffffffu) atomicMin(&q->first_ninf, fm);
-        *any_poison = 1;
-    }
-    s += t1;
-    s2 += t2;
+            // an infinity or a NaN among the values makes the sum of squares non-finite (and it stays so)
+            if (!(fabs(s2 + t2) <= 1.7976931348623157e308)) {  // rare: record where the column first goes non-finite
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, d);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-    }
-    if (lane == 0) {
-        __stcg(tot, publishable(s));
-        __stcg(tot + kNF, publishable(s2));
+                for (int k = 0; k < kRun; ++k) {
+                    const unsigned int r = (unsigned int)(tl0 + j * kBlk + lane * kRun + k);   // stream-local row
+                    const double y = v[k];
+                    if (y != y) fn = min(fn, r);
+                    else if (y == __longlong_as_double(0x7ff0000000000000ll)) fp = min(fp, r);
+                    else if (y == __longlong_as_double(0xfff0000000000000ll)) fm = min(fm, r);
+                }
+            }
+            __syncwarp();   // every lane has read the slot
+            if (t + kSlots < total) issue(sl);
+            if (++sl == kSlots) sl = 0;
+        }
+        if ((fn & fp & fm) != 0xffffffffu) {
+            NormPoison* q = q0 + ci * kNormWarps;
+            if (fn != 0xffffffffu) atomicMin(&q->first_nan, fn);
+            if (fp != 0xffffffffu) atomicMin(&q->first_pinf, fp);
+            if (fm != 0xffffffffu) atomicMin(&q->first_ninf, fm);
+            *any_poison = 1;
+        }
+        s += t1;
+        s2 += t2;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+        }
+        if (lane == 0) {
+            double* tot = tot0 + ci * kNormWarps;
+            __stcg(tot, publishable(s));
+            __stcg(tot + kNF, publishable(s2));
+        }
     }
 }
 
@@ -553,10 +566,8 @@ k_normalize_runs(const DevOutputs out, const int64_t N, const DevTile* __restric
     const DevTile T = tiles[id];
     const int n = T.n, W = P.norm_window;
     const int64_t tl0 = (int64_t)T.index * P.tile_rows;  // stream-local index of the tile's first row
-    for (int c = warp; c < kNF; c += kNormWarps) {
-        const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
-        run_total(S, rp, x, n, tl0, tile_tot + (int64_t)id * 2 * kNF + c, poison + (int64_t)T.stream * kNF + c, any_poison, lane);
-    }
+    run_totals(S, rp, out.raw, N, T.row, warp, n, tl0, tile_tot + (int64_t)id * 2 * kNF + warp, poison + (int64_t)T.stream * kNF + warp,
+               any_poison, lane);
     const int nb = T.index < P.tiles_back ? T.index : P.tiles_back;  // preceding tiles inside the window
     const bool has_lag = T.index >= P.tiles_back;
     for (int c = warp; c < kNF; c += kNormWarps) {
