@@ -290,6 +290,13 @@ k_normalize(const DevOutputs out, const int64_t N, const DevTile* __restrict__ t
 // (0 or 1) is added to the slot index, and the at most two edge rows of a block that a 16-byte store cannot cover are
 // written by lane 0.
 // ================================================================================================
+#ifndef MRP_NORM_RUN_WARPS
+#define MRP_NORM_RUN_WARPS 10
+#endif
+#ifndef MRP_NORM_RUN_CTAS
+#define MRP_NORM_RUN_CTAS 2
+#endif
+constexpr int kRunWarps = MRP_NORM_RUN_WARPS;   // warps per CTA (= tile); each owns the columns w, w + kRunWarps, ...
 constexpr int kRun = 7;                  // rows per lane per block
 constexpr int kBlk = 32 * kRun;          // 224
 constexpr int kBlkSlot = kBlk + 2;       // + the alignment shift, padded to 16 bytes
@@ -308,6 +315,13 @@ __device__ __forceinline__ void block_load(double* slot, const double* src, int 
     const uintptr_t q0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
     bulk_g2s(slot, reinterpret_cast<const void*>(q0), block_bytes(src, rows), bar);
 }
+__device__ __forceinline__ void block_load_hint(double* slot, const double* src, int rows, uint64_t* bar, uint64_t pol) {
+    const uintptr_t q0 = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)15;
+    bulk_g2s_hint(slot, reinterpret_cast<const void*>(q0), block_bytes(src, rows), bar, pol);
+}
+#ifndef MRP_NORM_HINTS
+#define MRP_NORM_HINTS 3
+#endif
 __device__ __forceinline__ int block_shift(const double* src) { return (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1u); }
 
 // per-warp staging state: bit i = the phase parity the next wait on full[i] expects
@@ -325,10 +339,10 @@ __device__ __forceinline__ void run_totals(NormWarpStage& S, RunPipe& rp, const 
                                            const int c0, const int n, const int64_t tl0, double* __restrict__ tot0,
                                            NormPoison* __restrict__ q0, int* __restrict__ any_poison, const int lane) {
     const int nblk = (n + kBlk - 1) / kBlk;
-    const int ncol = (kNF - c0 + kNormWarps - 1) / kNormWarps;
+    const int ncol = (kNF - c0 + kRunWarps - 1) / kRunWarps;
     const int total = nblk * ncol;
     const double* __restrict__ x0 = raw + (int64_t)c0 * N + row;
-    const int64_t col_stride = (int64_t)kNormWarps * N;
+    const int64_t col_stride = (int64_t)kRunWarps * N;
     int ij = 0;              // block and column of the next request
     int64_t icol = 0;
     auto issue = [&](int sl) {
@@ -381,7 +395,7 @@ __device__ __forceinline__ void run_totals(NormWarpStage& S, RunPipe& rp, const 
             if (++sl == kSlots) sl = 0;
         }
         if ((fn & fp & fm) != 0xffffffffu) {
-            NormPoison* q = q0 + ci * kNormWarps;
+            NormPoison* q = q0 + ci * kRunWarps;
             if (fn != 0xffffffffu) atomicMin(&q->first_nan, fn);
             if (fp != 0xffffffffu) atomicMin(&q->first_pinf, fp);
             if (fm != 0xffffffffu) atomicMin(&q->first_ninf, fm);
@@ -395,7 +409,7 @@ __device__ __forceinline__ void run_totals(NormWarpStage& S, RunPipe& rp, const 
             s2 += __shfl_xor_sync(0xffffffffu, s2, d);
         }
         if (lane == 0) {
-            double* tot = tot0 + ci * kNormWarps;
+            double* tot = tot0 + ci * kRunWarps;
             __stcg(tot, publishable(s));
             __stcg(tot + kNF, publishable(s2));
         }
@@ -417,8 +431,16 @@ __device__ __forceinline__ void run_zscores(NormWarpStage& S, RunPipe& rp, const
             uint32_t bytes = block_bytes(src, rows);
             if (LAG) bytes += block_bytes(src - W, rows);
             mbar_expect_tx(&S.full[s], bytes);
+#if MRP_NORM_HINTS & 4
+            block_load_hint(S.slot[s], src, rows, &S.full[s], l2_policy_evict_last());   // read again as the lag, 15 tiles on
+#else
             block_load(S.slot[s], src, rows, &S.full[s]);
+#endif
+#if MRP_NORM_HINTS & 1
+            if (LAG) block_load_hint(S.slot[2 + s], src - W, rows, &S.full[s], l2_policy_evict_first());   // last use of these rows
+#else
             if (LAG) block_load(S.slot[2 + s], src - W, rows, &S.full[s]);
+#endif
         }
     };
     // the first blocks are in flight while the predecessors' totals are collected
@@ -528,7 +550,11 @@ __device__ __forceinline__ void run_zscores(NormWarpStage& S, RunPipe& rp, const
             // rows [ra, ra + cnt) are covered by 16-byte units; at most one row on either side is stored directly
             const int ra = zsh, cnt = (rows - ra) & ~1;
             if (ra && rows > 0) zg[0] = zs[0];
+#if MRP_NORM_HINTS & 2
+            if (cnt > 0) bulk_s2g_hint(zg + ra, zs + ra, (uint32_t)cnt * 8u, l2_policy_evict_first());   // nobody reads z here
+#else
             if (cnt > 0) bulk_s2g(zg + ra, zs + ra, (uint32_t)cnt * 8u);
+#endif
             bulk_commit();
             if (ra + cnt < rows) zg[rows - 1] = zs[rows - 1];
         }
@@ -547,7 +573,7 @@ __device__ __forceinline__ void run_zscores(NormWarpStage& S, RunPipe& rp, const
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kNormThreads, 2)
+__global__ void __launch_bounds__(kRunWarps * 32, MRP_NORM_RUN_CTAS)
 k_normalize_runs(const DevOutputs out, const int64_t N, const DevTile* __restrict__ tiles, double* __restrict__ tile_tot,
                  unsigned int* __restrict__ ticket, NormPoison* __restrict__ poison, int* __restrict__ any_poison, const DevParams P) {
     extern __shared__ __align__(16) unsigned char norm_dyn[];
@@ -570,7 +596,7 @@ k_normalize_runs(const DevOutputs out, const int64_t N, const DevTile* __restric
                any_poison, lane);
     const int nb = T.index < P.tiles_back ? T.index : P.tiles_back;  // preceding tiles inside the window
     const bool has_lag = T.index >= P.tiles_back;
-    for (int c = warp; c < kNF; c += kNormWarps) {
+    for (int c = warp; c < kNF; c += kRunWarps) {
         const double* __restrict__ x = out.raw + (int64_t)c * N + T.row;
         double* __restrict__ z = out.norm + (int64_t)c * N + T.row;
         const double* pred = tile_tot + (int64_t)(id - nb) * 2 * kNF + c;
@@ -661,14 +687,14 @@ cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* ti
         return !(v && v[0] == 's');
     }();
     if (use_runs) {
-        constexpr int kBytes = (int)sizeof(NormWarpStage) * kNormWarps;
+        constexpr int kBytes = (int)sizeof(NormWarpStage) * kRunWarps;
         static bool ready = false;  // idempotent; a race only repeats the call
         if (!ready) {
             e = cudaFuncSetAttribute(k_normalize_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
             if (e != cudaSuccess) return e;
             ready = true;
         }
-        k_normalize_runs<<<ntiles, kNormThreads, kBytes, st>>>(out, N, tiles, tile_tot, reinterpret_cast<unsigned int*>(flags + ntiles),
+        k_normalize_runs<<<ntiles, kRunWarps * 32, kBytes, st>>>(out, N, tiles, tile_tot, reinterpret_cast<unsigned int*>(flags + ntiles),
                                                                static_cast<NormPoison*>(poison), any, P);
     } else {
         k_normalize<<<ntiles, kNormThreads, 0, st>>>(out, N, tiles, tile_tot, flags, reinterpret_cast<unsigned int*>(flags + ntiles),
