@@ -154,7 +154,7 @@ def run_reference_arm(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def cpu_baseline(levels: int, budget_rows: int):
@@ -448,7 +448,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "global_moments_midprice": [float(x) for x in mom[0]],
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -459,5 +459,22 @@ def dataclass_replace(spec, **kw):
     return dataclasses.replace(spec, **kw)
 
 
+def _emit(line: dict):
+    """The one JSON line, on the process's REAL stdout (see _quiet_stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout():
+    """Libraries print to fd 1 on their own (NCCL's version banner, torchrun notices): everything but the JSON line goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
