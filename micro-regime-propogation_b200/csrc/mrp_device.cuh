@@ -85,7 +85,10 @@ struct DevParams {
     int32_t tiles_back;         // norm_window / tile_rows
 };
 
-constexpr int kThreads = 256;          // CTA size of the book pass
+#ifndef MRP_BOOK_THREADS
+#define MRP_BOOK_THREADS 256
+#endif
+constexpr int kThreads = MRP_BOOK_THREADS;   // CTA size of the book pass (= rows per chunk)
 constexpr int kWarps = kThreads / 32;
 
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
