@@ -41,14 +41,20 @@ def _stale(target: str, deps: List[str]) -> bool:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES]
     deps = srcs + [os.path.join(CSRC, "mrp_device.cuh"), os.path.join(HERE, "..", "include", "mrp_fg.h"), __file__]
-    if force or _stale(LIB, deps):
-        extra = os.environ.get("MRP_FG_NVCC_EXTRA", "").split()   # experiment switches (-DNAME=value), empty in normal builds
+    extra = os.environ.get("MRP_FG_NVCC_EXTRA", "").split()   # experiment switches (-DNAME=value), empty in normal builds
+    # the flags a library was built with sit next to it: a library left behind by an experiment build is rebuilt
+    stamp = LIB + ".flags"
+    want = " ".join(NVCC_FLAGS + extra)
+    have = open(stamp).read() if os.path.exists(stamp) else None
+    if force or have != want or _stale(LIB, deps):
         cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
         # nvcc's host compiler must be the PATH g++ (the image's CC/CXX wrappers are not usable by nvcc)
         env = dict(os.environ)
         env.pop("CC", None)
         env.pop("CXX", None)
         subprocess.run(cmd, check=True, cwd=CSRC, env=env)
+        with open(stamp, "w") as f:
+            f.write(want)
     return LIB
 
 
