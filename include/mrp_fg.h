@@ -169,7 +169,10 @@ int mrp_fg_destroy(mrp_fg_ctx* ctx);
 
 /* Bind caller-owned DEVICE arrays (view->memory must be MRP_MEM_DEVICE); nothing is copied except
  * the three small offset arrays.  Replaces: handing FeatureInputSnapshot rows to
- * FeatureProcessor::GetRawFeatureSet (feature_processor.cpp:11), for all rows at once. */
+ * FeatureProcessor::GetRawFeatureSet (feature_processor.cpp:11), for all rows at once.
+ * Alignment: natural alignment of the element type is enough (8 bytes for prices, 4 for sizes); the book arrays are
+ * fetched in 16-byte units, so the copy engine may read the rest of the aligned 16-byte block that holds an array's
+ * first or last element (never a byte outside the memory page those elements live in). */
 int mrp_fg_bind_inputs(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view);
 
 /* Copy a HOST view (view->memory == MRP_MEM_HOST; pinned memory recommended) into context-owned
