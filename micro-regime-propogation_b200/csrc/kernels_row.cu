@@ -73,6 +73,9 @@ __device__ __forceinline__ double ema_block(double v, const double (&pw2)[6], do
     return pl * cw + v;
 }
 
+#ifndef MRP_BOOK_LG10
+#define MRP_BOOK_LG10 0
+#endif
 #ifndef MRP_BOOK_NS
 #define MRP_BOOK_NS 2
 #endif
@@ -101,7 +104,7 @@ struct __align__(16) BookStage {
 template <int LG, int NS>
 __global__ void __launch_bounds__(kThreads, MRP_BOOK_MINB)
 k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
-    static_assert(4 * LG <= 32, "one lane of warp 0 per (array, level) of a batch");
+    static_assert(4 * LG <= 32 * kWarps, "one lane per (array, level) run of a batch");
     extern __shared__ __align__(16) unsigned char book_dyn[];
     BookStage<LG>* __restrict__ stg = reinterpret_cast<BookStage<LG>*>(book_dyn);
     double* __restrict__ sOfiW = reinterpret_cast<double*>(book_dyn + sizeof(BookStage<LG>) * NS);  // [L] depth weights
@@ -404,6 +407,9 @@ static cudaError_t launch_book_t(const DevInputs& in, const DevOutputs& out, con
 cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
                         const DevParams& P, cudaStream_t st) {
     const int L = P.L;
+#if MRP_BOOK_LG10
+    if (L % 10 == 0) return launch_book_t<10, 2>(in, out, segs, nseg, P, st);
+#endif
     if (L % 5 == 0) return launch_book_t<5, MRP_BOOK_NS>(in, out, segs, nseg, P, st);
     if (L % 4 == 0) return launch_book_t<4, 2>(in, out, segs, nseg, P, st);
     if (L % 2 == 0) return launch_book_t<2, 3>(in, out, segs, nseg, P, st);
