@@ -432,6 +432,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if _ALL_CPUS:   # the CPU baseline gets every host core the launcher gave this process, not just the GPU's neighbours
+            os.sched_setaffinity(0, _ALL_CPUS)
         cpu = cpu_baseline(args.levels, args.ref_rows)
 
     if rank == 0:
@@ -460,12 +462,17 @@ def dataclass_replace(spec, **kw):
     return dataclasses.replace(spec, **kw)
 
 
+_ALL_CPUS = None
+
+
 def _bind_to_gpu_numa_node(gpu_index: int):
     """One process per GPU: run on the CPUs next to that GPU, so that the pinned staging buffers of the end-to-end leg are
     first-touched in the memory its PCIe root complex hangs off (host plumbing; returns what was done, for the record)."""
     try:
         import pynvml
 
+        global _ALL_CPUS
+        _ALL_CPUS = os.sched_getaffinity(0)
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
         pynvml.nvmlDeviceSetCpuAffinity(h)
