@@ -31,6 +31,9 @@
 
 namespace mrp {
 
+#ifndef MRP_WIN_MINB
+#define MRP_WIN_MINB 3
+#endif
 constexpr int kWinThreads = 256;
 constexpr int kWinRows = 128;            // snapshots per chunk: threads 0..127 add side, 128..255 evict side + trades
 // the log1p series covers relative moves below 2^-10 per tick (high word 0x3f500000)
@@ -665,7 +668,7 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
 }
 
 template <int RING>
-__global__ void __launch_bounds__(kWinThreads, 3)
+__global__ void __launch_bounds__(kWinThreads, MRP_WIN_MINB)
 k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
     extern __shared__ __align__(16) double ring[];  // y: ring[0, RING)   d: ring[RING, 2 RING)
     __shared__ __align__(16) unsigned char shraw[sizeof(PipeShared) > sizeof(WinShared) ? sizeof(PipeShared) : sizeof(WinShared)];
