@@ -187,13 +187,29 @@ __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, con
 }
 
 // trade-axis features of one snapshot from its window counts (feature_processor.cpp:231-247, :254-269)
-__device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N, int64_t r, const double* __restrict__ clog2c, int nd,
-                                                int pos, int neg, int rev, int isum) {
-    const double rr = nd > 1 ? (double)rev / (double)nd : 0.0;  // :239 — divides by size, not size-1
-    const double ab = (double)isum / (double)nd;                // :246 — 0/0 = NaN with no trades
+// a / n for a count n inside the host's 1/n table: reciprocal, product, ONE correction step (the quotient's remainder is
+// exact in an fma) — the correctly rounded quotient for the small integers that meet here, for 4 instructions and a load
+__device__ __forceinline__ double div_by_count(double a, int n, const double* __restrict__ inv_cnt) {
+    const double b = (double)n, r = __ldg(inv_cnt + n);
+    const double q = a * r;
+    return fma(fma(-q, b, a), r, q);
+}
+
+// inv_cnt == nullptr: plain divisions (the direct path)
+__device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N, int64_t r, const double* __restrict__ clog2c,
+                                                const double* __restrict__ inv_cnt, int nd, int pos, int neg, int rev, int isum) {
     const int tot = pos + neg;                                  // :261-269
-    // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T with c*log2(c) tabulated by the host
-    const double ent = tot > 0 ? ((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg)) / (double)tot : 0.0;
+    double rr, ab, ent;
+    if (inv_cnt) {
+        rr = nd > 1 ? div_by_count((double)rev, nd, inv_cnt) : 0.0;                                   // :239 — divides by size, not size-1
+        ab = nd > 0 ? div_by_count((double)isum, nd, inv_cnt) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
+        // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T with c*log2(c) tabulated by the host
+        ent = tot > 0 ? div_by_count((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg), tot, inv_cnt) : 0.0;
+    } else {
+        rr = nd > 1 ? (double)rev / (double)nd : 0.0;
+        ab = (double)isum / (double)nd;
+        ent = tot > 0 ? ((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg)) / (double)tot : 0.0;
+    }
     out.raw[(int64_t)MRP_F_REVERSAL_RATE * N + r] = rr;
     out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * N + r] = ab;
     out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + r] = ent;
@@ -221,7 +237,7 @@ __device__ __noinline__ void direct_trade_row(const int8_t* __restrict__ tdir, u
     DevOutputs o{};
     o.raw = raw;
     o.counts = counts;
-    write_trade_row(o, N, r, clog2c, (int)(je - jb), pos, neg, rev, isum);
+    write_trade_row(o, N, r, clog2c, nullptr, (int)(je - jb), pos, neg, rev, isum);
 }
 
 // explicit 32-bit shared-window accessors for the ring (keeps address formation out of the inner loops)
@@ -654,7 +670,7 @@ __device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32
                 const int w0 = D.TD[0][ct], w1 = D.TD[1][ct];
                 const int pos = w0 & 0xffff, neg = (w0 >> 16) & 0xffff, rev = w1 & 0xffff;
                 const int isum = (w1 - rev) >> 16;
-                write_trade_row(out, N, row, P.clog2c, (int)(je - jb), pos, neg, rev, isum);
+                write_trade_row(out, N, row, P.clog2c, P.inv_cnt, (int)(je - jb), pos, neg, rev, isum);
             }
             bar_sync_n(2, kWinRows);      // the A arrays and this descriptor are free again
             bar_arrive_n(5 + b, kWinThreads);
@@ -993,7 +1009,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 const int w0 = sh.TD[0][i], w1 = sh.TD[1][i];
                 const int pos = w0 & 0xffff, neg = (w0 >> 16) & 0xffff, rev = w1 & 0xffff;
                 const int isum = (w1 - rev) >> 16;
-                write_trade_row(out, N, row, P.clog2c, (int)(je - jb), pos, neg, rev, isum);
+                write_trade_row(out, N, row, P.clog2c, P.inv_cnt, (int)(je - jb), pos, neg, rev, isum);
             }
         }
         Eprev = Elast;
