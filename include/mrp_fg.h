@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 2
+#define MRP_FG_ABI_VERSION 3   /* 3: + mrp_fg_download_rows */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -205,6 +205,10 @@ int mrp_fg_outputs(mrp_fg_ctx* ctx, const double** raw, const double** norm,
 /* Copy outputs to HOST buffers (same layouts), asynchronously on `stream`; NULL = skip. */
 int mrp_fg_download(mrp_fg_ctx* ctx, double* raw, double* norm, int8_t* bid_dir, int8_t* ask_dir,
                     int32_t* counts, void* stream);
+
+/* Copy the rows [row_begin, row_end) of the RAW and z-scored features to HOST buffers laid out [19][row_end - row_begin]
+ * (what a time shard keeps after dropping its halo, or the newest row of a trailing window); NULL = skip. */
+int mrp_fg_download_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, double* raw, double* norm, void* stream);
 
 /* Per-column moments of the RAW features over all bound rows: out[c*3 + {0,1,2}] = {n, sum x, sum x^2}
  * (double [19*3], host).  These are what a caller allreduces across GPUs to get global

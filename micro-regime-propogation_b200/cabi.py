@@ -137,6 +137,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_process_host.argtypes = [vp, PV, vp, vp, i64]
     lib.mrp_fg_outputs.argtypes = [vp] + [C.POINTER(vp)] * 5
     lib.mrp_fg_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.mrp_fg_download_rows.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, vp]
     lib.mrp_fg_moments.argtypes = [vp, vp, vp]
     lib.mrp_fg_sync.argtypes = [vp, vp]
     lib.mrp_fg_num_kernels.argtypes = []
@@ -235,6 +236,16 @@ class Engine:
                                              p(out["ask_dir"]), p(out["counts"]), C.c_void_p(stream)))
         self.sync(stream)
         return out
+
+    def download_rows(self, row_begin: int, row_end: int, stream: int = 0):
+        """raw / norm of the rows [row_begin, row_end) only: ([19, m], [19, m])."""
+        m = row_end - row_begin
+        raw = np.empty((NUM_FEATURES, m), np.float64)
+        norm = np.empty((NUM_FEATURES, m), np.float64)
+        self._check(self.lib.mrp_fg_download_rows(self.ctx, C.c_int64(row_begin), C.c_int64(row_end), C.c_void_p(raw.ctypes.data),
+                                                  C.c_void_p(norm.ctypes.data), C.c_void_p(stream)))
+        self.sync(stream)
+        return raw, norm
 
     def moments(self, stream: int = 0) -> np.ndarray:
         m = np.empty((NUM_FEATURES, 3), np.float64)

@@ -685,6 +685,20 @@ int mrp_fg_download(mrp_fg_ctx* c, double* raw, double* norm, int8_t* bid_dir, i
     return MRP_FG_OK;
 }
 
+int mrp_fg_download_rows(mrp_fg_ctx* c, int64_t row_begin, int64_t row_end, double* raw, double* norm, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    if (row_begin < 0 || row_end < row_begin || row_end > c->n_rows) return fail(MRP_FG_ERR_INVALID, "row range outside the bound rows");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t N = (size_t)c->n_rows, n = (size_t)(row_end - row_begin);
+    if (n == 0) return MRP_FG_OK;
+    // one strided copy per feature matrix: 19 column slices of n rows each
+    if (raw) CU(cudaMemcpy2DAsync(raw, n * 8, c->out.raw + row_begin, N * 8, n * 8, MRP_FG_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+    if (norm) CU(cudaMemcpy2DAsync(norm, n * 8, c->out.norm + row_begin, N * 8, n * 8, MRP_FG_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+    return MRP_FG_OK;
+}
+
 int mrp_fg_moments(mrp_fg_ctx* c, double* out, void* stream) {
     if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
     if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");

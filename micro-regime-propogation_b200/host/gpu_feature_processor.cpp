@@ -1,5 +1,7 @@
 #include "gpu_feature_processor.hpp"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace microregime {
@@ -18,6 +20,7 @@ GpuFeatureProcessor::GpuFeatureProcessor(std::string symbol, int device, const m
     if (p.depth_levels != (int)mrp_host::kDepthLevels)
         throw std::runtime_error("GpuFeatureProcessor: params.depth_levels must equal the snapshot type's DEPTH_LEVELS");
     levels_ = p.depth_levels;
+    params_ = p;
     if (mrp_fg_create(&p, device, &ctx_) != MRP_FG_OK) fail("mrp_fg_create");
 }
 
@@ -48,6 +51,82 @@ void GpuFeatureProcessor::stage(const FeatureInputSnapshot& s, std::uint64_t gri
     adds_.push_back(s.adds_since_last_snapshot);
     kcur_.push_back((std::uint32_t)mid_.size());
     jcur_.push_back((std::uint32_t)tdir_.size());
+}
+
+// ---- one row per call, through the reference's own signatures
+FeatureSet GpuFeatureProcessor::GetRawFeatureSet(const FeatureInputSnapshot& snapshot) {
+    stage(snapshot, snapshot.timestamp_ns);
+    const std::int64_t t = (std::int64_t)ts_.size() - 1;
+    // rows that can still influence row t: its z-score window, the EMA warm-up of the window's first row (both EMAs have
+    // forgotten their start to < 1e-17 after `warm` rows), the lag-21 midprice and the previous row of the book deltas
+    const double slow = std::max(1.0 - params_.ofi_alpha, 1.0 - params_.stress_alpha);
+    std::int64_t warm = slow > 0.0 && slow < 1.0 ? (std::int64_t)std::ceil(std::log(1e-17) / std::log(slow)) : 0;
+    warm = std::max<std::int64_t>(warm, params_.return_lag + 1);
+    warm = ((warm + 255) / 256) * 256;
+    const std::int64_t H = (std::int64_t)params_.norm_window + warm + 32;
+    const std::int64_t a = std::max<std::int64_t>(0, t - H);
+    const std::int64_t n = t - a + 1;
+    // ticks / trades those rows can see
+    const std::int64_t wmax = std::max<std::int64_t>(params_.mid_window, (std::int64_t)params_.dir_window + 1);
+    const std::int64_t k_first = a > 0 ? (std::int64_t)kcur_[a - 1] : 0, j_first = a > 0 ? (std::int64_t)jcur_[a - 1] : 0;
+    const std::int64_t tick0 = a > 0 ? std::max<std::int64_t>(0, k_first - wmax - 2) : 0;
+    const std::int64_t trade0 = a > 0 ? std::max<std::int64_t>(0, j_first - params_.dir_window - 2) : 0;
+    const int L = levels_;
+    std::vector<double> bp((std::size_t)n * L), ap((std::size_t)n * L);
+    std::vector<std::int32_t> bs((std::size_t)n * L), as((std::size_t)n * L);
+    std::vector<std::uint32_t> kc((std::size_t)n), jc((std::size_t)n);
+    for (std::int64_t r = 0; r < n; ++r) {
+        const std::size_t g = (std::size_t)(a + r);
+        for (int i = 0; i < L; ++i) {
+            bp[(std::size_t)i * n + r] = bid_px_[g * L + i];
+            ap[(std::size_t)i * n + r] = ask_px_[g * L + i];
+            bs[(std::size_t)i * n + r] = bid_sz_[g * L + i];
+            as[(std::size_t)i * n + r] = ask_sz_[g * L + i];
+        }
+        kc[(std::size_t)r] = (std::uint32_t)((std::int64_t)kcur_[g] - tick0);
+        jc[(std::size_t)r] = (std::uint32_t)((std::int64_t)jcur_[g] - trade0);
+    }
+    const std::int64_t row_off[2] = {0, n}, tick_off[2] = {0, (std::int64_t)mid_.size() - tick0},
+                       trade_off[2] = {0, (std::int64_t)tdir_.size() - trade0};
+    mrp_fg_soa_view v{};
+    v.n_streams = 1;
+    v.memory = MRP_MEM_HOST;
+    v.row_offsets = row_off;
+    v.tick_offsets = tick_off;
+    v.trade_offsets = trade_off;
+    v.ts_ns = ts_.data() + a;
+    v.bid_px = bp.data();
+    v.ask_px = ap.data();
+    v.bid_sz = bs.data();
+    v.ask_sz = as.data();
+    v.buy_vol = buy_.data() + a;
+    v.sell_vol = sell_.data() + a;
+    v.adds = adds_.data() + a;
+    v.tick_cursor = kc.data();
+    v.trade_cursor = jc.data();
+    v.mid = mid_.data() + tick0;
+    v.spread = spread_.data() + tick0;
+    v.trade_dir = tdir_.data() + trade0;
+    double raw[MRP_FG_NUM_FEATURES];
+    if (mrp_fg_upload(ctx_, &v, nullptr) != MRP_FG_OK) fail("mrp_fg_upload");
+    if (mrp_fg_run(ctx_, nullptr) != MRP_FG_OK) fail("mrp_fg_run");
+    if (mrp_fg_download_rows(ctx_, n - 1, n, raw, last_norm_, nullptr) != MRP_FG_OK) fail("mrp_fg_download_rows");
+    if (mrp_fg_sync(ctx_, nullptr) != MRP_FG_OK) fail("mrp_fg_sync");
+    last_valid_ = true;
+    FeatureSet f;
+    f.timestamp_ns = snapshot.timestamp_ns;   // feature_processor.cpp:13
+    f.instrument = snapshot.instrument;       // :14
+    for (int c = 0; c < MRP_FG_NUM_FEATURES; ++c) f.*(mrp_host::kFeatureMembers[c]) = raw[c];
+    return f;
+}
+
+FeatureSet GpuFeatureProcessor::GetProcessedFeatureSet(const FeatureSet& raw_feature_set) {
+    if (!last_valid_) throw std::runtime_error("GpuFeatureProcessor::GetProcessedFeatureSet: no row has been computed (call GetRawFeatureSet first)");
+    FeatureSet f;
+    f.timestamp_ns = raw_feature_set.timestamp_ns;   // feature_normalizer.cpp:57-58
+    f.instrument = raw_feature_set.instrument;
+    for (int c = 0; c < MRP_FG_NUM_FEATURES; ++c) f.*(mrp_host::kFeatureMembers[c]) = last_norm_[c];
+    return f;
 }
 
 void GpuFeatureProcessor::clear() {

@@ -44,6 +44,16 @@ public:
 
     std::size_t staged_rows() const { return ts_.size(); }
 
+    // ---- the reference's own two signatures (feature_processor.hpp:14-15): ONE row per call.
+    // GetRawFeatureSet stages the snapshot (the on_tick / on_trade hooks must have been fed, as for stage()) and computes
+    // this row NOW, by a GPU pass over the trailing rows that can still influence it (norm_window + EMA warm-up + 32
+    // rows, with their ticks and trades).  GetProcessedFeatureSet returns the z-scores of the row the last
+    // GetRawFeatureSet computed, as the reference's call order has it (dual_feature_pipeline.cpp:107-108).
+    // A launch, an upload of the window and a read-back per row: milliseconds.  For code and tests written against the
+    // reference interface; throughput comes from stage() + flush().  Rows stay staged, so flush() still delivers the day.
+    FeatureSet GetRawFeatureSet(const FeatureInputSnapshot& snapshot);
+    FeatureSet GetProcessedFeatureSet(const FeatureSet& raw_feature_set);
+
     // Run the GPU pass over everything staged and deliver the rows, in order, to the sink; clears the stage.
     void flush(DataReciever& sink);
 
@@ -64,6 +74,9 @@ private:
     std::string symbol_;
     mrp_fg_ctx* ctx_ = nullptr;
     int levels_ = 0;
+    mrp_fg_params params_{};
+    double last_norm_[MRP_FG_NUM_FEATURES] = {};   // z-scores of the row computed by the last GetRawFeatureSet
+    bool last_valid_ = false;
     // snapshot axis (level-major book arrays are transposed at flush)
     std::vector<std::uint64_t> ts_, grid_;
     std::vector<double> bid_px_, ask_px_;   // row-major staging: [n][L]

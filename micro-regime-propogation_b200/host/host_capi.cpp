@@ -87,6 +87,56 @@ int mrp_host_features_to_csv(const mrp_fg_soa_view* v, const char* project_root,
     }
 }
 
+// The reference's per-row call sequence (dual_feature_pipeline.cpp:106-108) over a staged host batch of ONE stream:
+// rows before `first_row` are only staged, every later row goes through GetRawFeatureSet + GetProcessedFeatureSet.
+// raw_out / norm_out: [19][n - first_row].  With params == NULL the reference constants are used.
+int mrp_host_rows_by_reference_calls(const mrp_fg_soa_view* v, const mrp_fg_params* params, int64_t first_row, double* raw_out,
+                                     double* norm_out, int device) {
+    try {
+        if (!v || v->n_streams != 1 || v->memory != MRP_MEM_HOST) throw std::runtime_error("expects a single-stream HOST view");
+        const int64_t n = v->row_offsets[1];
+        if (first_row < 0 || first_row > n) throw std::runtime_error("first_row outside the stream");
+        const int64_t m = n - first_row;
+        constexpr int L = (int)mrp_host::kDepthLevels;
+        microregime::GpuFeatureProcessor proc("SYN", device, params);
+        int64_t k = 0, j = 0;
+        FeatureInputSnapshot s;
+        s.instrument = "SYN";
+        for (int64_t r = 0; r < n; ++r) {
+            for (; k < (int64_t)v->tick_cursor[r]; ++k) proc.on_tick(v->mid[k], v->spread[k]);
+            for (; j < (int64_t)v->trade_cursor[r]; ++j) proc.on_trade(v->trade_dir[j]);
+            s.timestamp_ns = v->ts_ns[r];
+            for (int i = 0; i < L; ++i) {
+                s.bid_prices[i] = v->bid_px[(size_t)i * n + r];
+                s.ask_prices[i] = v->ask_px[(size_t)i * n + r];
+                s.bid_sizes[i] = v->bid_sz[(size_t)i * n + r];
+                s.ask_sizes[i] = v->ask_sz[(size_t)i * n + r];
+            }
+            s.best_bid_price = s.bid_prices[0];
+            s.best_ask_price = s.ask_prices[0];
+            s.rolling_buy_volume = v->buy_vol[r];
+            s.rolling_sell_volume = v->sell_vol[r];
+            s.adds_since_last_snapshot = v->adds[r];
+            if (r < first_row) {
+                proc.stage(s, s.timestamp_ns);
+                continue;
+            }
+            const microregime::FeatureSet raw = proc.GetRawFeatureSet(s);
+            const microregime::FeatureSet norm = proc.GetProcessedFeatureSet(raw);
+            if (raw.timestamp_ns != s.timestamp_ns || norm.timestamp_ns != s.timestamp_ns || norm.instrument != s.instrument)
+                throw std::runtime_error("timestamp / instrument not carried through");
+            for (int c = 0; c < MRP_FG_NUM_FEATURES; ++c) {
+                raw_out[(size_t)c * m + (r - first_row)] = raw.*(mrp_host::kFeatureMembers[c]);
+                norm_out[(size_t)c * m + (r - first_row)] = norm.*(mrp_host::kFeatureMembers[c]);
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 int mrp_host_depth_levels(void) { return (int)mrp_host::kDepthLevels; }
 
 }  // extern "C"

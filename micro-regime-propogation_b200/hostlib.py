@@ -26,6 +26,7 @@ def load_host() -> C.CDLL:
         lib.mrp_host_write_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int]
         lib.mrp_host_features_to_csv.argtypes = [C.POINTER(SoaView), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64,
                                                  C.c_uint64, C.c_int, C.c_int]
+        lib.mrp_host_rows_by_reference_calls.argtypes = [C.POINTER(SoaView), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         _lib = lib
     return _lib
 
@@ -59,3 +60,18 @@ def features_to_csv(hv: HostView, project_root: str, base_filename: str, date: s
     if rc != 0:
         raise RuntimeError(lib.mrp_host_last_error().decode())
     return csv_directory(project_root, interval_ns, date)
+
+
+def rows_by_reference_calls(hv: HostView, first_row: int = 0, params=None, device: int = 0):
+    """Replay one stream through the adaptor's reference-signature calls — GetRawFeatureSet(snapshot) then
+    GetProcessedFeatureSet(raw), one row per call (feature_processor.hpp:14-15) — for the rows >= first_row (earlier rows
+    are only staged).  Returns (raw, norm), each [19][n - first_row]."""
+    lib = load_host()
+    m = hv.n_rows - first_row
+    raw = np.empty((19, m), dtype=np.float64)
+    norm = np.empty((19, m), dtype=np.float64)
+    rc = lib.mrp_host_rows_by_reference_calls(C.byref(hv.view), C.byref(params) if params is not None else None, first_row,
+                                              raw.ctypes.data, norm.ctypes.data, device)
+    if rc != 0:
+        raise RuntimeError(lib.mrp_host_last_error().decode())
+    return raw, norm

@@ -16,3 +16,61 @@ def test_validation_harness_passes(tmp_path, extra):
                        capture_output=True, text=True)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0
+
+
+def test_reference_signatures_row_by_row():
+    """GetRawFeatureSet(snapshot) / GetProcessedFeatureSet(raw), one row per call like dual_feature_pipeline.cpp:106-108,
+    against the oracle (the reference's arithmetic) and against the adaptor's own batch pass."""
+    import numpy as np
+
+    import mrp_b200
+    from mrp_b200 import hostlib, synth
+    from oracle import binding as ob
+
+    from helpers import make_host_batch, nan_pattern_equal, norm_check, raw_errors
+
+    hv = mrp_b200.HostView(make_host_batch([synth.SynthSpec(n_rows=700, seed=91, variable_cursors=True)]))
+    first = 380                                       # rows before this are only staged; 320 rows go through the per-row calls
+    raw, norm = hostlib.rows_by_reference_calls(hv, first_row=first)
+    ref = ob.run_oracle(hv)
+    assert nan_pattern_equal(raw, ref["raw"][:, first:])
+    re = raw_errors(raw, ref["raw"][:, first:])
+    assert (re <= 1.0).all(), re
+    assert nan_pattern_equal(norm, ref["norm"][:, first:])
+    # the rows before `first` are needed by the conditioning-aware check: splice the per-row results into the batch results
+    eng = mrp_b200.Engine(mrp_b200.default_params(), device=0)
+    eng.upload(hv)
+    eng.run()
+    got = eng.download()
+    eng.close()
+    assert np.allclose(raw, got["raw"][:, first:], rtol=1e-12, atol=0, equal_nan=True)   # same kernels, same window: same numbers
+    spliced = got["norm"].copy()
+    spliced[:, first:] = norm
+    wa, wb, _, frac = norm_check(spliced, ref["raw"], ref["norm"], hv.arrays["row_offsets"], 30000, 1e-9)
+    assert frac > 0.9 and (wa <= 1.0).all() and (wb <= 1.0).all(), (wa.max(), wb.max())
+
+
+def test_reference_signatures_truncated_history():
+    """The per-row path only re-reads the trailing rows that can influence a row.  With a short normaliser window (300 rows)
+    the history IS truncated (300 + 512 + 32 rows back), and the rows must still agree with the full-history batch pass."""
+    import numpy as np
+
+    import mrp_b200
+    from mrp_b200 import hostlib, synth
+
+    from helpers import make_host_batch
+
+    p = mrp_b200.default_params(norm_window=300)
+    hv = mrp_b200.HostView(make_host_batch([synth.SynthSpec(n_rows=1400, seed=92)]))
+    first = 1340                                      # 1340 > 844: every per-row call runs on a truncated history
+    raw, norm = hostlib.rows_by_reference_calls(hv, first_row=first, params=p)
+    eng = mrp_b200.Engine(p, device=0)
+    eng.upload(hv)
+    eng.run()
+    got = eng.download()
+    eng.close()
+    scale = np.maximum(np.abs(got["raw"]).max(axis=1, keepdims=True), 1e-300)
+    err = np.abs(raw - got["raw"][:, first:]) / np.maximum(np.abs(got["raw"][:, first:]), 1e-6 * scale)
+    assert np.nanmax(err) < 1e-9, np.nanmax(err)
+    zerr = np.abs(norm - got["norm"][:, first:]) / np.maximum(1.0, np.abs(got["norm"][:, first:]))
+    assert np.nanmax(zerr) < 1e-6, np.nanmax(zerr)

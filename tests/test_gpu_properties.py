@@ -75,3 +75,23 @@ def test_batching_invariance():
         e.close()
         for k in ("raw", "norm"):
             assert np.array_equal(W[k][:, ro[i]:ro[i + 1]], O[k], equal_nan=True), (i, k)
+
+
+def test_download_rows_is_a_slice_of_download():
+    """mrp_fg_download_rows (what a time shard keeps after its halo / the newest row of a trailing window)."""
+    import mrp_b200
+    from mrp_b200 import synth
+
+    from helpers import make_host_batch
+
+    hv = mrp_b200.HostView(make_host_batch([synth.SynthSpec(n_rows=3001, seed=55)]))
+    eng = mrp_b200.Engine(mrp_b200.default_params(), device=0)
+    eng.upload(hv)
+    eng.run()
+    full = eng.download()
+    for a, b in ((0, 3001), (3000, 3001), (17, 1234), (500, 500)):
+        raw, norm = eng.download_rows(a, b)
+        assert np.array_equal(raw, full["raw"][:, a:b], equal_nan=True) and np.array_equal(norm, full["norm"][:, a:b], equal_nan=True)
+    with pytest.raises(mrp_b200.MrpError):
+        eng.download_rows(10, 3002)
+    eng.close()
