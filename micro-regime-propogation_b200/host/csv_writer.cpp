@@ -1,5 +1,7 @@
 #include "csv_writer.hpp"
 
+#include <memory>
+
 #include <algorithm>
 #include <charconv>
 #include <cmath>
@@ -87,34 +89,44 @@ void CsvWriter::ingest_feature_set(const std::string&, std::uint64_t timestamp_n
 void CsvWriter::write_columns(const std::string& instrument, const std::uint64_t* grid_ts, const double* raw, const double* norm,
                               std::int64_t n, int threads) {
     if (n <= 0) return;
+    constexpr std::int64_t block = 1 << 13;   // rows a thread formats per round: 4.5 MB of text, stays near its cache
     int nt = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
-    nt = (int)std::min<std::int64_t>(nt, (n + 4095) / 4096);
+    nt = (int)std::min<std::int64_t>(nt, (n + block - 1) / block);
     const std::size_t row_cap = 24 + instrument.size() + 19 * 26 + 2;
-    const std::int64_t block = 1 << 16;  // rows formatted per round (bounded memory)
-    std::vector<std::vector<char>> bufs((std::size_t)nt);
-    std::vector<std::size_t> lens((std::size_t)nt);
+    // two sets of per-thread buffers: one is being written to the file while the other is being formatted
+    std::unique_ptr<char[]> bufs[2];
+    std::vector<std::size_t> lens[2];
+    for (int k = 0; k < 2; ++k) {
+        bufs[k].reset(new char[(std::size_t)nt * block * row_cap]);   // uninitialised on purpose
+        lens[k].assign((std::size_t)nt, 0);
+    }
+    std::thread writer;
+    int k = 0;
     for (int pass = 0; pass < 2; ++pass) {
         const double* cols = pass == 0 ? raw : norm;
         std::ofstream& out = pass == 0 ? raw_csv_ : norm_csv_;
-        for (std::int64_t b0 = 0; b0 < n; b0 += block * nt) {
+        for (std::int64_t b0 = 0; b0 < n; b0 += block * nt, k ^= 1) {
             std::vector<std::thread> pool;
             for (int t = 0; t < nt; ++t) {
                 const std::int64_t lo = std::min(n, b0 + (std::int64_t)t * block), hi = std::min(n, lo + block);
-                lens[(std::size_t)t] = 0;
+                lens[k][(std::size_t)t] = 0;
                 if (lo >= hi) continue;
-                pool.emplace_back([&, t, lo, hi] {
-                    auto& buf = bufs[(std::size_t)t];
-                    buf.resize((std::size_t)(hi - lo) * row_cap);
+                pool.emplace_back([&, t, lo, hi, k] {
+                    char* buf = bufs[k].get() + (std::size_t)t * block * row_cap;
                     std::size_t len = 0;
-                    for (std::int64_t r = lo; r < hi; ++r) len += format_row(buf.data() + len, grid_ts[r], instrument, cols, n, r);
-                    lens[(std::size_t)t] = len;
+                    for (std::int64_t r = lo; r < hi; ++r) len += format_row(buf + len, grid_ts[r], instrument, cols, n, r);
+                    lens[k][(std::size_t)t] = len;
                 });
             }
             for (auto& th : pool) th.join();
-            for (int t = 0; t < nt; ++t)
-                if (lens[(std::size_t)t]) out.write(bufs[(std::size_t)t].data(), (std::streamsize)lens[(std::size_t)t]);
+            if (writer.joinable()) writer.join();   // the previous round's text is on its way: file order is round order
+            writer = std::thread([&, k, nt, block, row_cap, o = &out] {
+                for (int t = 0; t < nt; ++t)
+                    if (lens[k][(std::size_t)t]) o->write(bufs[k].get() + (std::size_t)t * block * row_cap, (std::streamsize)lens[k][(std::size_t)t]);
+            });
         }
     }
+    if (writer.joinable()) writer.join();
 }
 
 }  // namespace microregime
