@@ -688,11 +688,14 @@ cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* ti
     }();
     if (use_runs) {
         constexpr int kBytes = (int)sizeof(NormWarpStage) * kRunWarps;
-        static bool ready = false;  // idempotent; a race only repeats the call
-        if (!ready) {
+        static bool ready[64];  // the opt-in is per device (idempotent; a race only repeats the call)
+        int dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (!ready[dev & 63]) {
             e = cudaFuncSetAttribute(k_normalize_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, kBytes);
             if (e != cudaSuccess) return e;
-            ready = true;
+            ready[dev & 63] = true;
         }
         k_normalize_runs<<<ntiles, kRunWarps * 32, kBytes, st>>>(out, N, tiles, tile_tot, reinterpret_cast<unsigned int*>(flags + ntiles),
                                                                static_cast<NormPoison*>(poison), any, P);

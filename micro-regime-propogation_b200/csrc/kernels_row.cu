@@ -394,11 +394,16 @@ static cudaError_t launch_book_t(const DevInputs& in, const DevOutputs& out, con
                                  const DevParams& P, cudaStream_t st) {
     constexpr int kStageBytes = (int)sizeof(BookStage<LG>) * NS;
     const int bytes = kStageBytes + P.L * (int)sizeof(double);  // + the depth weights
-    static int ready_for = -1;  // idempotent; a race only repeats the call
-    if (ready_for < bytes) {
-        cudaError_t e = cudaFuncSetAttribute(k_book<LG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    // the opt-in is per device: remembered per device ordinal (idempotent; a race only repeats the call)
+    static int ready_for[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int& ready = ready_for[dev & 63];
+    if (ready < bytes) {
+        e = cudaFuncSetAttribute(k_book<LG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
-        ready_for = bytes;
+        ready = bytes;
     }
     k_book<LG, NS><<<nseg, kThreads, bytes, st>>>(in, out, segs, P);
     return cudaGetLastError();
