@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=0, help="rows per pipelined chunk of the end-to-end leg (0 = library default)")
     ap.add_argument("--levels", type=int, default=LEVELS, help="book depth (50 = the deep-book config, BASELINE.json configs[3])")
     ap.add_argument("--days", type=int, default=1, help="instrument-days per GPU in one batch (BASELINE.json configs[2]: 32 days over the ranks, round-robin)")
+    ap.add_argument("--vol-of-vol", action="store_true",
+                    help="also run the vol-of-vol extension over 3 horizons (600 / 3000 / 30000 rows) inside every step (BASELINE.json configs[3]; no reference counterpart)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -281,10 +283,14 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     _run = eng.run
 
+    VOV_HORIZONS = (600, 3000, 30000)
+
     def run_step(st):
         if step_pre is not None:
             step_pre()
         _run(st)
+        if args.vol_of_vol:
+            eng.vol_of_vol(VOV_HORIZONS, stream=st, download=False)
 
     eng.run = run_step
 
@@ -338,7 +344,7 @@ def main():
 
     # ---- roofline of the dominant kernel (live CUDA events on the launching stream, last timed step)
     peak, peak_src = measured_peaks()
-    bytes_row = algorithmic_bytes_per_row(args.levels, m_eff, q)
+    bytes_row = algorithmic_bytes_per_row(args.levels, m_eff, q) + (48 if args.vol_of_vol else 0)   # + 3 x (raw + z) doubles
     # algorithmic bytes per kernel: what each kernel must read + write once
     kb = {
         # mids + spreads + trade dirs + both cursors, 8 feature columns
@@ -442,7 +448,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"{args.days} instrument-day(s) per GPU, {rows // args.days} snapshots x {args.levels} levels each, {m_eff:.2f} ticks and {q:.2f} trades per snapshot"
-                                   + (" (BASELINE.json configs[1])" if (rows == FULL_ROWS and args.days == 1 and args.levels == LEVELS) else " (not the headline config)"),
+                                   + (" (BASELINE.json configs[1])" if (rows == FULL_ROWS and args.days == 1 and args.levels == LEVELS) else " (not the headline config)")
+                                   + (" + vol-of-vol over %s rows (extension, no reference counterpart)" % (VOV_HORIZONS,) if args.vol_of_vol else ""),
                        "rows_per_gpu": rows, "levels": args.levels, "days_per_gpu": args.days,
                        "sharding": ("ONE stream split by time; per step each rank sends its last %d rows (+ window of ticks / trades) to its right "
                                     "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % tsh.halo_rows())

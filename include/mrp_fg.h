@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 3   /* 3: + mrp_fg_download_rows */
+#define MRP_FG_ABI_VERSION 4   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -209,6 +209,19 @@ int mrp_fg_download(mrp_fg_ctx* ctx, double* raw, double* norm, int8_t* bid_dir,
 /* Copy the rows [row_begin, row_end) of the RAW and z-scored features to HOST buffers laid out [19][row_end - row_begin]
  * (what a time shard keeps after dropping its halo, or the newest row of a trailing window); NULL = skip. */
 int mrp_fg_download_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, double* raw, double* norm, void* stream);
+
+/* EXTENSION WITHOUT A REFERENCE COUNTERPART (BASELINE.json configs[3]: "vol-of-vol over 3 horizons"; the reference has no
+ * such feature, SURVEY.md 0.1 D2 — PARITY UNPINNED: its only checker is the restatement of this definition in oracle/).
+ * After mrp_fg_run, for each of n_horizons (1..8) row horizons h:
+ *     vov_h(t) = population standard deviation of the ewm_volatility column over the rows t-n+1 .. t of the same stream,
+ *                n = min(t + 1, h); 0 when the variance is not positive
+ *     z_h(t)   = rolling z-score of vov_h over norm_window rows, arithmetic of feature_normalizer.cpp:61-69
+ * A non-finite value makes exactly the rows whose window contains it non-finite.  The horizons and norm_window must share
+ * a divisor >= 64.  raw / norm receive DEVICE pointers to double [n_horizons][n_rows] owned by the context (either may be
+ * NULL); the 19 reference columns and the CSV layout are untouched. */
+int mrp_fg_vol_of_vol(mrp_fg_ctx* ctx, const int32_t* horizons, int32_t n_horizons, const double** raw, const double** norm, void* stream);
+/* Copy what the last mrp_fg_vol_of_vol produced to HOST buffers, double [n_horizons][n_rows] each; NULL = skip. */
+int mrp_fg_download_vol_of_vol(mrp_fg_ctx* ctx, double* raw, double* norm, void* stream);
 
 /* Per-column moments of the RAW features over all bound rows: out[c*3 + {0,1,2}] = {n, sum x, sum x^2}
  * (double [19*3], host).  These are what a caller allreduces across GPUs to get global

@@ -138,6 +138,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_outputs.argtypes = [vp] + [C.POINTER(vp)] * 5
     lib.mrp_fg_download.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.mrp_fg_download_rows.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, vp]
+    lib.mrp_fg_vol_of_vol.argtypes = [vp, vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), vp]
+    lib.mrp_fg_download_vol_of_vol.argtypes = [vp, vp, vp, vp]
     lib.mrp_fg_moments.argtypes = [vp, vp, vp]
     lib.mrp_fg_sync.argtypes = [vp, vp]
     lib.mrp_fg_num_kernels.argtypes = []
@@ -244,6 +246,20 @@ class Engine:
         norm = np.empty((NUM_FEATURES, m), np.float64)
         self._check(self.lib.mrp_fg_download_rows(self.ctx, C.c_int64(row_begin), C.c_int64(row_end), C.c_void_p(raw.ctypes.data),
                                                   C.c_void_p(norm.ctypes.data), C.c_void_p(stream)))
+        self.sync(stream)
+        return raw, norm
+
+    def vol_of_vol(self, horizons, stream: int = 0, download: bool = True):
+        """The vol-of-vol extension (no reference counterpart; see include/mrp_fg.h).  Returns (raw, norm) [n_horizons, n] on
+        the host, or the two device pointers when download is False."""
+        h = np.ascontiguousarray(horizons, dtype=np.int32)
+        praw, pnorm = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.mrp_fg_vol_of_vol(self.ctx, C.c_void_p(h.ctypes.data), len(h), C.byref(praw), C.byref(pnorm), C.c_void_p(stream)))
+        if not download:
+            return praw.value, pnorm.value
+        raw = np.empty((len(h), self.n_rows), np.float64)
+        norm = np.empty((len(h), self.n_rows), np.float64)
+        self._check(self.lib.mrp_fg_download_vol_of_vol(self.ctx, C.c_void_p(raw.ctypes.data), C.c_void_p(norm.ctypes.data), C.c_void_p(stream)))
         self.sync(stream)
         return raw, norm
 

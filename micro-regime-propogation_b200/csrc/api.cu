@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <numeric>
 #include <vector>
 
 #include "mrp_device.cuh"
@@ -18,6 +19,8 @@ cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, 
 cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, void*, const int64_t*, int, const DevParams&, cudaStream_t);
 size_t norm_poison_bytes(int);
 cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_rolling(const double* x, int64_t x_stride, double* out, int64_t out_stride, const void* tiles, int ntiles, double* tot,
+                           const int32_t* windows_dev, int njobs, int tile_rows, int mode, cudaStream_t st);
 size_t win_smem_bytes(int);
 }  // namespace mrp
 
@@ -87,6 +90,14 @@ struct mrp_fg_ctx {
     // tables
     DevBuf b_segs, b_tiles, b_tile_tot, b_flags, b_tables, b_row_off, b_poison;
     int nseg = 0, ntiles = 0;
+    // vol-of-vol extension (mrp_fg_vol_of_vol)
+    DevBuf b_vov_raw, b_vov_norm, b_vov_tiles, b_vov_tot, b_vov_win;
+    int vov_n = 0;
+    uint64_t shape_gen = 0;            // bumped whenever the bound shape changes
+    uint64_t vov_gen = ~0ull;          // shape_gen the cached vol-of-vol tile list was built for
+    std::vector<int32_t> vov_h;        // ... and its horizons
+    int vov_nt = 0;
+    int64_t vov_tile = 0;
     // timing
     bool timing = false, have_times = false;
     cudaEvent_t ev[kNumKernels + 1] = {};
@@ -327,6 +338,7 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
             tiles.push_back(t);
         }
     }
+    ++c->shape_gen;
     c->nseg = (int)segs.size();
     c->ntiles = (int)tiles.size();
     if ((rc = c->b_segs.ensure(segs.size() * sizeof(DevSegment)))) return rc;
@@ -410,7 +422,8 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
     }
     DevBuf* bufs[] = {&c->b_ts, &c->b_bpx, &c->b_apx, &c->b_bsz, &c->b_asz, &c->b_buy, &c->b_sell, &c->b_adds, &c->b_kcur,
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
-                      &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison};
+                      &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison,
+                      &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win};
     for (DevBuf* b : bufs) b->release();
     if (c->ev_made)
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -682,6 +695,84 @@ int mrp_fg_download(mrp_fg_ctx* c, double* raw, double* norm, int8_t* bid_dir, i
     if (ask_dir) CU(cudaMemcpyAsync(ask_dir, c->out.adir, N * L, cudaMemcpyDeviceToHost, st));
     if (counts && !c->out.counts) return fail(MRP_FG_ERR_STATE, "counts were not requested (params.emit_counts)");
     if (counts) CU(cudaMemcpyAsync(counts, c->out.counts, N * MRP_FG_NUM_COUNTS * 4, cudaMemcpyDeviceToHost, st));
+    return MRP_FG_OK;
+}
+
+// ---- vol-of-vol: an extension without a reference counterpart (see include/mrp_fg.h and kernels_volvol.cu)
+int mrp_fg_vol_of_vol(mrp_fg_ctx* c, const int32_t* horizons, int32_t n_horizons, const double** raw, const double** norm, void* stream) {
+    if (!c || !horizons) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    if (n_horizons < 1 || n_horizons > 8) return fail(MRP_FG_ERR_INVALID, "n_horizons must be in [1,8]");
+    // one tile length for every window: the greatest common divisor of the horizons and the z-score window
+    int64_t g = c->p.norm_window;
+    for (int k = 0; k < n_horizons; ++k) {
+        if (horizons[k] < 1) return fail(MRP_FG_ERR_INVALID, "horizons must be positive");
+        g = std::gcd<int64_t, int64_t>(g, horizons[k]);
+    }
+    if (g < 64) return fail(MRP_FG_ERR_INVALID, "the horizons and norm_window must share a divisor >= 64 (the tile length of the rolling sums)");
+    int64_t tile = g;
+    while (tile > 2048 && tile % 2 == 0) tile /= 2;   // any divisor of g divides every window; keep tiles short enough to spread over the SMs
+    if (tile > 8192) tile = g;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t N = c->n_rows;
+    c->vov_n = n_horizons;
+    if (raw) *raw = nullptr;
+    if (norm) *norm = nullptr;
+    if (N == 0) return MRP_FG_OK;
+    int rc;
+    if ((rc = c->b_vov_raw.ensure((size_t)N * n_horizons * sizeof(double)))) return rc;
+    if ((rc = c->b_vov_norm.ensure((size_t)N * n_horizons * sizeof(double)))) return rc;
+    const std::vector<int32_t> hv(horizons, horizons + n_horizons);
+    if (c->vov_gen != c->shape_gen || c->vov_h != hv || c->vov_tile != tile) {   // the tile list depends on the shape and the windows only
+        struct HostTile { int64_t row; int32_t n; int32_t index; };
+        std::vector<HostTile> tiles;
+        for (int s = 0; s < c->n_streams; ++s) {
+            int idx = 0;
+            for (int64_t a = c->row_off[s]; a < c->row_off[s + 1]; a += tile, ++idx)
+                tiles.push_back({a, (int32_t)std::min<int64_t>(tile, c->row_off[s + 1] - a), idx});
+        }
+        const int nt_new = (int)tiles.size();
+        if ((rc = c->b_vov_tiles.ensure(tiles.size() * sizeof(HostTile)))) return rc;
+        if ((rc = c->b_vov_tot.ensure((size_t)nt_new * n_horizons * 2 * sizeof(double)))) return rc;
+        if ((rc = c->b_vov_win.ensure(16 * sizeof(int32_t)))) return rc;
+        int32_t win[16];
+        for (int k = 0; k < 8; ++k) {
+            win[k] = k < n_horizons ? horizons[k] : 1;
+            win[8 + k] = c->p.norm_window;
+        }
+        // (pageable sources: the copies are staged by the runtime before the calls return)
+        CU(cudaMemcpyAsync(c->b_vov_tiles.p, tiles.data(), tiles.size() * sizeof(HostTile), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->b_vov_win.p, win, sizeof(win), cudaMemcpyHostToDevice, st));
+        c->vov_gen = c->shape_gen;
+        c->vov_h = hv;
+        c->vov_tile = tile;
+        c->vov_nt = nt_new;
+    }
+    const int nt = c->vov_nt;
+    double* vraw = static_cast<double*>(c->b_vov_raw.p);
+    double* vnorm = static_cast<double*>(c->b_vov_norm.p);
+    const int32_t* wdev = static_cast<const int32_t*>(c->b_vov_win.p);
+    // horizon k: rolling standard deviation of the ewm_volatility column ...
+    CU(launch_rolling(c->out.raw + (int64_t)MRP_F_EWM_VOLATILITY * N, 0, vraw, N, c->b_vov_tiles.p, nt, static_cast<double*>(c->b_vov_tot.p),
+                      wdev, n_horizons, (int)tile, /*std*/ 0, st));
+    // ... and its rolling z-score over norm_window rows
+    CU(launch_rolling(vraw, N, vnorm, N, c->b_vov_tiles.p, nt, static_cast<double*>(c->b_vov_tot.p), wdev + 8, n_horizons, (int)tile, /*z*/ 1, st));
+    c->launches += 4;
+    if (raw) *raw = vraw;
+    if (norm) *norm = vnorm;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_download_vol_of_vol(mrp_fg_ctx* c, double* raw, double* norm, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    if (!c->bound || c->vov_n == 0) return fail(MRP_FG_ERR_STATE, "mrp_fg_vol_of_vol has not run");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t bytes = (size_t)c->n_rows * c->vov_n * sizeof(double);
+    if (bytes == 0) return MRP_FG_OK;
+    if (raw) CU(cudaMemcpyAsync(raw, c->b_vov_raw.p, bytes, cudaMemcpyDeviceToHost, st));
+    if (norm) CU(cudaMemcpyAsync(norm, c->b_vov_norm.p, bytes, cudaMemcpyDeviceToHost, st));
     return MRP_FG_OK;
 }
 

@@ -54,15 +54,6 @@ __device__ __forceinline__ double publishable(double s) {  // keep computed NaNs
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// 1/sqrt(v) for a positive normal v: the seed plus one third-order step (the library's own fast path)
-__device__ __forceinline__ double rsqrt_pos(double v) {
-    double r;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
-    const double e = fma(-v * r, r, 1.0);           // 1 - v r^2
-    const double p = fma(e, 0.375, 0.5);
-    return fma(p, e * r, r);                         // r (1 + e/2 + 3 e^2/8)
-}
-
 // Four consecutive doubles of a lane.  ALIGN = 32: one 256-bit access (sm_100 LDG.256 / STG.256: the warp's 32 lanes
 // touch 8 full lines); ALIGN = 16: two 128-bit accesses; otherwise scalar.
 template <int ALIGN>

@@ -104,6 +104,17 @@ __device__ __forceinline__ double entropy_term(double acc, double p) {
 }
 
 
+// 1/sqrt(v) for a positive normal v: the seed plus one third-order step (the library's own fast path)
+__device__ __forceinline__ double rsqrt_pos(double v) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
+    const double e = fma(-v * r, r, 1.0);           // 1 - v r^2
+    const double p = fma(e, 0.375, 0.5);
+    return fma(p, e * r, r);                         // r (1 + e/2 + 3 e^2/8)
+}
+// positive, normal and far from the range ends: the inputs rsqrt_pos is exact enough for
+__device__ __forceinline__ bool rsqrt_pos_ok(double v) { return (uint32_t)(__double2hiint(v) - 0x03000000) < 0x79000000u; }
+
 // ---- bulk asynchronous copies (TMA unit, SASS UBLKCP) and the mbarriers that track them
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {

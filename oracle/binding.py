@@ -82,6 +82,23 @@ def run_oracle(hv: HostView, params: Optional[Params] = None, nthreads: int = 0,
     return out
 
 
+def vol_of_vol(ewm: np.ndarray, row_offsets, horizons, norm_window: int = 30000):
+    """vol-of-vol extension, PARITY UNPINNED: the restated definition (direct window loops in extended precision).
+    Returns (raw, norm), each [n_horizons][n_rows]."""
+    ewm = np.ascontiguousarray(ewm, dtype=np.float64)
+    ro = np.ascontiguousarray(row_offsets, dtype=np.int64)
+    h = np.ascontiguousarray(horizons, dtype=np.int32)
+    n = ewm.shape[0]
+    raw = np.empty((len(h), n), np.float64)
+    norm = np.empty((len(h), n), np.float64)
+    lib = oracle_lib()
+    lib.mrp_oracle_vol_of_vol.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rc = lib.mrp_oracle_vol_of_vol(_ptr(ewm), _ptr(ro), len(ro) - 1, _ptr(h), len(h), norm_window, _ptr(raw), _ptr(norm))
+    if rc != 0:
+        raise RuntimeError(f"mrp_oracle_vol_of_vol failed ({rc})")
+    return raw, norm
+
+
 def run_reference(hv: HostView, trade_size: Optional[np.ndarray] = None, use_book: bool = False,
                   nthreads: int = 1) -> Dict[str, np.ndarray]:
     """The compiled, unmodified reference (L = 10 or 50 as hv.levels says)."""

@@ -392,3 +392,37 @@ int mrp_oracle_default_params(mrp_fg_params* p) {
     p->stress_alpha = 0.1;
     return 0;
 }
+
+/* ---- vol-of-vol extension: PARITY UNPINNED (no reference implementation exists; restates include/mrp_fg.h's definition).
+ * Every window is summed afresh in long double, oldest row first: no sliding state, nothing shared with the CUDA algorithm. */
+static void rolling_stat(const double* x, int64_t n, int window, int zscore, double* out) {
+    for (int64_t t = 0; t < n; ++t) {
+        const int64_t cnt = t + 1 < window ? t + 1 : window;
+        long double s = 0.0L, s2 = 0.0L;
+        for (int64_t i = t - cnt + 1; i <= t; ++i) {
+            s += (long double)x[i];
+            s2 += (long double)x[i] * (long double)x[i];
+        }
+        const double mean = (double)(s / (long double)cnt);
+        /* variance from the exactly summed moments, rounded once: the quantity the device approximates */
+        const long double m = s / (long double)cnt;
+        const double var = (double)(s2 / (long double)cnt - m * m);
+        if (zscore) out[t] = (x[t] - mean) / (var > 0.0 ? sqrt(var) : 1.0);
+        else out[t] = var > 0.0 ? sqrt(var) : (var == var ? 0.0 : var);
+    }
+}
+
+int mrp_oracle_vol_of_vol(const double* ewm, const int64_t* row_offsets, int n_streams, const int32_t* horizons, int n_horizons,
+                          int norm_window, double* raw, double* norm) {
+    if (!ewm || !row_offsets || !horizons || !raw || !norm || n_streams < 1 || n_horizons < 1 || norm_window < 1) return 1;
+    const int64_t N = row_offsets[n_streams];
+    for (int k = 0; k < n_horizons; ++k) {
+        if (horizons[k] < 1) return 1;
+        for (int s = 0; s < n_streams; ++s) {
+            const int64_t a = row_offsets[s], n = row_offsets[s + 1] - a;
+            rolling_stat(ewm + a, n, horizons[k], 0, raw + (int64_t)k * N + a);
+            rolling_stat(raw + (int64_t)k * N + a, n, norm_window, 1, norm + (int64_t)k * N + a);
+        }
+    }
+    return 0;
+}

@@ -32,6 +32,16 @@ extern "C" {
 int mrp_oracle_run(const mrp_fg_params* p, const mrp_fg_soa_view* host_view, double* raw,
                    double* norm, int8_t* bid_dir, int8_t* ask_dir, int32_t* counts, int nthreads);
 
+/* vol-of-vol EXTENSION — PARITY UNPINNED.  The reference has no such feature, so there is nothing to
+ * pin this function against: it restates the DEFINITION in include/mrp_fg.h (mrp_fg_vol_of_vol) with direct O(window) loops
+ * in extended precision, and is the only checker the CUDA extension has.
+ *   ewm        double [n_rows]   the ewm_volatility column (raw feature MRP_F_EWM_VOLATILITY)
+ *   row_offsets int64 [n_streams + 1]
+ *   raw, norm  double [n_horizons][n_rows]
+ * Returns 0, or 1 on bad arguments. */
+int mrp_oracle_vol_of_vol(const double* ewm, const int64_t* row_offsets, int n_streams, const int32_t* horizons, int n_horizons,
+                          int norm_window, double* raw, double* norm);
+
 #ifdef __cplusplus
 }
 #endif
