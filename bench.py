@@ -342,6 +342,21 @@ def main():
         dist.all_reduce(mom, op=dist.ReduceOp.SUM)
     mom = mom.cpu().numpy()
 
+    # ---- what the Python stage does next (StandardScaler over the z-scored columns of all dates): moments of the z-scores,
+    # ONE all-reduce of 19 x 3 doubles, then every rank scales its own rows.  Outside the timed region; reported on its own.
+    nm = torch.from_numpy(eng.norm_moments(stream)).to(dev)
+    if world > 1:
+        dist.all_reduce(nm, op=dist.ReduceOp.SUM)
+    nm = nm.cpu().numpy()
+    sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.standardize(nm, stream, download=False)
+    sv0.record()
+    eng.standardize(nm, stream, download=False)
+    sv1.record()
+    torch.cuda.synchronize()
+    scaler = {"standardize_ms": sv0.elapsed_time(sv1), "moments_combined_over_ranks": world,
+              "mean_scale_log_return": [float(x) for x in mrp_b200.mean_scale(nm)[mrp_b200.FEATURES.index("log_return")]]}
+
     # ---- roofline of the dominant kernel (live CUDA events on the launching stream, last timed step)
     peak, peak_src = measured_peaks()
     bytes_row = algorithmic_bytes_per_row(args.levels, m_eff, q) + (48 if args.vol_of_vol else 0)   # + 3 x (raw + z) doubles
@@ -455,7 +470,7 @@ def main():
                                     "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % tsh.halo_rows())
                        if (args.timeshard and world > 1) else "instrument-day per GPU, no data-path collective",
                        "l2": "inputs (>= 20 GB at 50 M rows) far exceed the 126 MB L2; no explicit flush"},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "host_affinity": numa,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "host_affinity": numa, "global_standardisation": scaler,
             "global_moments_midprice": [float(x) for x in mom[0]],
         }
         _emit(line)

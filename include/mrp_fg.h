@@ -49,7 +49,8 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 4   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol */
+#define MRP_FG_ABI_VERSION 5   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
+                                  5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -228,6 +229,19 @@ int mrp_fg_download_vol_of_vol(mrp_fg_ctx* ctx, double* raw, double* norm, void*
  * (StandardScaler-style) statistics (ref: regime_classifier/python/data_checks.py:79-80).
  * Synchronises `stream`. */
 int mrp_fg_moments(mrp_fg_ctx* ctx, double* out, void* stream);
+
+/* The step the reference's Python stage takes next (sklearn StandardScaler over the z-scored columns of ALL rows of ALL dates:
+ * regime_classifier/python/classifier.py:35-37, data_checks.py:78-80), as three calls so that several GPUs / processes can combine:
+ *   mrp_fg_norm_moments   out[c*3 + {0,1,2}] = {number of non-NaN cells, sum z, sum z^2} of column c of the z-scored features
+ *                         (double [19*3], host; NaN cells are missing values as for the scaler; deterministic; synchronises `stream`)
+ *   (callers ADD the moment arrays of all contexts / ranks: one all-reduce of 57 doubles)
+ *   mrp_fg_mean_scale     mean_scale[c*2 + {0,1}] = {mean, population standard deviation} from combined moments; a constant
+ *                         column keeps scale 1 (sklearn's rule).  Pure host arithmetic, no context needed.
+ *   mrp_fg_standardize    (z - mean) / scale for every bound row into a context-owned device array double [19][n_rows]
+ *                         (*out_device, may be NULL) and / or a HOST buffer of the same layout (out_host, may be NULL). */
+int mrp_fg_norm_moments(mrp_fg_ctx* ctx, double* out, void* stream);
+int mrp_fg_mean_scale(const double* moments, double* mean_scale);
+int mrp_fg_standardize(mrp_fg_ctx* ctx, const double* moments, double* out_host, const double** out_device, void* stream);
 
 /* Block until everything enqueued on `stream` by this context has finished; surfaces kernel faults. */
 int mrp_fg_sync(mrp_fg_ctx* ctx, void* stream);

@@ -141,6 +141,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_vol_of_vol.argtypes = [vp, vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), vp]
     lib.mrp_fg_download_vol_of_vol.argtypes = [vp, vp, vp, vp]
     lib.mrp_fg_moments.argtypes = [vp, vp, vp]
+    lib.mrp_fg_norm_moments.argtypes = [vp, vp, vp]
+    lib.mrp_fg_mean_scale.argtypes = [vp, vp]
+    lib.mrp_fg_standardize.argtypes = [vp, vp, vp, C.POINTER(vp), vp]
     lib.mrp_fg_sync.argtypes = [vp, vp]
     lib.mrp_fg_num_kernels.argtypes = []
     lib.mrp_fg_kernel_name.argtypes = [i32]
@@ -268,6 +271,23 @@ class Engine:
         self._check(self.lib.mrp_fg_moments(self.ctx, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
         return m
 
+    # -- the Python stage's StandardScaler over the z-scored columns (classifier.py:35-37), combinable across GPUs
+    def norm_moments(self, stream: int = 0) -> np.ndarray:
+        """[19, 3] = {non-NaN count, sum z, sum z^2} per z-scored column; ADD these across contexts / ranks."""
+        m = np.empty((NUM_FEATURES, 3), np.float64)
+        self._check(self.lib.mrp_fg_norm_moments(self.ctx, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
+        return m
+
+    def standardize(self, moments: np.ndarray, stream: int = 0, download: bool = True):
+        """(z - mean) / scale with mean / scale from (combined) moments: [19, n] on the host, or the device pointer."""
+        m = np.ascontiguousarray(moments, dtype=np.float64)
+        out = np.empty((NUM_FEATURES, self.n_rows), np.float64) if download else None
+        dev = C.c_void_p()
+        self._check(self.lib.mrp_fg_standardize(self.ctx, C.c_void_p(m.ctypes.data), C.c_void_p(out.ctypes.data) if download else C.c_void_p(),
+                                                C.byref(dev), C.c_void_p(stream)))
+        self.sync(stream)
+        return out if download else dev.value
+
     # -- introspection
     def enable_timing(self, on: bool = True):
         self._check(self.lib.mrp_fg_enable_timing(self.ctx, int(on)))
@@ -280,3 +300,13 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mrp_fg_launch_count(self.ctx))
+
+
+def mean_scale(moments: np.ndarray) -> np.ndarray:
+    """[19, 2] = {mean, scale} from [19, 3] combined moments (mrp_fg_mean_scale: host arithmetic, no GPU needed)."""
+    m = np.ascontiguousarray(moments, dtype=np.float64)
+    out = np.empty((NUM_FEATURES, 2), np.float64)
+    rc = load().mrp_fg_mean_scale(C.c_void_p(m.ctypes.data), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise MrpError(f"mrp_fg_mean_scale failed ({rc})")
+    return out

@@ -19,6 +19,9 @@ cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, 
 cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, void*, const int64_t*, int, const DevParams&, cudaStream_t);
 size_t norm_poison_bytes(int);
 cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
+int col_moment_blocks(int64_t N);
+cudaError_t launch_col_moments(const double* x, int64_t N, double* part, cudaStream_t st);
+cudaError_t launch_standardize(const double* x, double* out, int64_t N, const double* mean_scale_dev, cudaStream_t st);
 cudaError_t launch_rolling(const double* x, int64_t x_stride, double* out, int64_t out_stride, const void* tiles, int ntiles, double* tot,
                            const int32_t* windows_dev, int njobs, int tile_rows, int mode, cudaStream_t st);
 size_t win_smem_bytes(int);
@@ -92,6 +95,8 @@ struct mrp_fg_ctx {
     int nseg = 0, ntiles = 0;
     // vol-of-vol extension (mrp_fg_vol_of_vol)
     DevBuf b_vov_raw, b_vov_norm, b_vov_tiles, b_vov_tot, b_vov_win;
+    // global standardisation (mrp_fg_norm_moments / mrp_fg_standardize)
+    DevBuf b_mom_part, b_scaled, b_mean_scale;
     int vov_n = 0;
     uint64_t shape_gen = 0;            // bumped whenever the bound shape changes
     uint64_t vov_gen = ~0ull;          // shape_gen the cached vol-of-vol tile list was built for
@@ -423,7 +428,8 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
     DevBuf* bufs[] = {&c->b_ts, &c->b_bpx, &c->b_apx, &c->b_bsz, &c->b_asz, &c->b_buy, &c->b_sell, &c->b_adds, &c->b_kcur,
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
                       &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison,
-                      &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win};
+                      &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win, &c->b_mom_part, &c->b_scaled,
+                      &c->b_mean_scale};
     for (DevBuf* b : bufs) b->release();
     if (c->ev_made)
         for (auto& ev : c->ev) cudaEventDestroy(ev);
@@ -809,6 +815,79 @@ int mrp_fg_moments(mrp_fg_ctx* c, double* out, void* stream) {
         out[f * 3 + 1] = (double)s;
         out[f * 3 + 2] = (double)s2;
     }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_norm_moments(mrp_fg_ctx* c, double* out, void* stream) {
+    if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t N = c->n_rows;
+    const int nb = col_moment_blocks(N);
+    std::vector<double> part((size_t)nb * MRP_FG_NUM_FEATURES * 3);
+    if (nb > 0) {
+        int rc = c->b_mom_part.ensure(part.size() * sizeof(double));
+        if (rc) return rc;
+        CU(launch_col_moments(c->out.norm, N, static_cast<double*>(c->b_mom_part.p), st));
+        c->launches += 1;
+        CU(cudaMemcpyAsync(part.data(), c->b_mom_part.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    for (int f = 0; f < MRP_FG_NUM_FEATURES; ++f) {   // block partials, in block order, in extended precision
+        long double n = 0, s = 0, s2 = 0;
+        for (int b = 0; b < nb; ++b) {
+            const double* p = &part[((size_t)b * MRP_FG_NUM_FEATURES + f) * 3];
+            n += p[0];
+            s += p[1];
+            s2 += p[2];
+        }
+        out[f * 3 + 0] = (double)n;
+        out[f * 3 + 1] = (double)s;
+        out[f * 3 + 2] = (double)s2;
+    }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_mean_scale(const double* moments, double* mean_scale) {
+    if (!moments || !mean_scale) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    for (int f = 0; f < MRP_FG_NUM_FEATURES; ++f) {
+        const long double n = moments[f * 3], s = moments[f * 3 + 1], s2 = moments[f * 3 + 2];
+        double mean = 0.0, scale = 1.0;
+        if (n > 0) {
+            const long double m = s / n;
+            long double var = s2 / n - m * m;
+            if (var < 0) var = 0;
+            mean = (double)m;
+            // sklearn's constant-feature rule (utils/extmath.py: _is_constant_feature) and zero handling: such columns are left unscaled
+            const long double eps = 2.220446049250313e-16L;
+            const long double bound = n * eps * var + (n * m * eps) * (n * m * eps);
+            scale = (var <= bound || !(var > 0)) ? 1.0 : (double)sqrtl(var);
+        }
+        mean_scale[f * 2] = mean;
+        mean_scale[f * 2 + 1] = scale;
+    }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_standardize(mrp_fg_ctx* c, const double* moments, double* out_host, const double** out_device, void* stream) {
+    if (!c || !moments) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t N = c->n_rows;
+    if (out_device) *out_device = nullptr;
+    if (N == 0) return MRP_FG_OK;
+    double ms[MRP_FG_NUM_FEATURES * 2];
+    int rc = mrp_fg_mean_scale(moments, ms);
+    if (rc) return rc;
+    if ((rc = c->b_scaled.ensure((size_t)N * MRP_FG_NUM_FEATURES * sizeof(double)))) return rc;
+    if ((rc = c->b_mean_scale.ensure(sizeof(ms)))) return rc;
+    CU(cudaMemcpyAsync(c->b_mean_scale.p, ms, sizeof(ms), cudaMemcpyHostToDevice, st));   // pageable source: staged before the call returns
+    CU(launch_standardize(c->out.norm, static_cast<double*>(c->b_scaled.p), N, static_cast<const double*>(c->b_mean_scale.p), st));
+    c->launches += 1;
+    if (out_host) CU(cudaMemcpyAsync(out_host, c->b_scaled.p, (size_t)N * MRP_FG_NUM_FEATURES * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_device) *out_device = static_cast<const double*>(c->b_scaled.p);
     return MRP_FG_OK;
 }
 

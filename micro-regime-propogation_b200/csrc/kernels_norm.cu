@@ -23,6 +23,7 @@
 //
 // k_normalize_faithful re-enacts the reference's add-then-evict chain in its exact rounding order
 // (one thread per stream x feature; serial, for validation only).
+#include <algorithm>
 #include <cstdlib>
 
 #include "mrp_device.cuh"
@@ -697,6 +698,71 @@ cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* ti
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_norm_poison<<<n_streams * kNF, 256, 0, st>>>(out, N, row_off, static_cast<const NormPoison*>(poison), any, P);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// Global standardisation of the z-scored columns — what the reference's Python stage does next with sklearn's StandardScaler
+// (regime_classifier/python/classifier.py:35-37, data_checks.py:78-80: mean and population standard deviation of every column over ALL
+// rows of ALL dates, NaN cells skipped).  Moments are additive, so ranks all-reduce 19 x {n, sum, sum of squares} once and every
+// rank scales its own rows.  Deterministic: block b of column c always sums the same rows in the same order.
+// ================================================================================================
+constexpr int kMomRows = 8192, kMomThreads = 256;
+
+__global__ void __launch_bounds__(kMomThreads)
+k_col_moments(const double* __restrict__ x, const int64_t N, double* __restrict__ part) {
+    __shared__ double sh[3][kMomThreads / 32];
+    const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * kMomRows;
+    const int64_t r1 = r0 + kMomRows < N ? r0 + kMomRows : N;
+    const double* __restrict__ col = x + (int64_t)c * N;
+    double cnt = 0.0, s = 0.0, s2 = 0.0;
+    for (int64_t r = r0 + tid; r < r1; r += kMomThreads) {
+        const double v = col[r];
+        if (v == v) {   // NaN cells are missing values for the scaler
+            cnt += 1.0;
+            s += v;
+            s2 = fma(v, v, s2);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        s += __shfl_xor_sync(0xffffffffu, s, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) { sh[0][warp] = cnt; sh[1][warp] = s; sh[2][warp] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, b = 0.0, q = 0.0;
+        for (int w = 0; w < kMomThreads / 32; ++w) { a += sh[0][w]; b += sh[1][w]; q += sh[2][w]; }
+        double* o = part + ((int64_t)blockIdx.x * kNF + c) * 3;
+        o[0] = a; o[1] = b; o[2] = q;
+    }
+}
+
+// out = (x - mean) / scale per column; ms = [19][2] {mean, scale} on the device
+__global__ void __launch_bounds__(256)
+k_standardize(const double* __restrict__ x, double* __restrict__ out, const int64_t N, const double* __restrict__ ms) {
+    const int c = blockIdx.y;
+    const double mean = ms[c * 2], scale = ms[c * 2 + 1];
+    const double* __restrict__ xi = x + (int64_t)c * N;
+    double* __restrict__ xo = out + (int64_t)c * N;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (int64_t)gridDim.x * blockDim.x) xo[r] = (xi[r] - mean) / scale;
+}
+
+int col_moment_blocks(int64_t N) { return (int)((N + kMomRows - 1) / kMomRows); }
+
+cudaError_t launch_col_moments(const double* x, int64_t N, double* part, cudaStream_t st) {
+    if (N == 0) return cudaSuccess;
+    k_col_moments<<<dim3((unsigned)col_moment_blocks(N), kNF), kMomThreads, 0, st>>>(x, N, part);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_standardize(const double* x, double* out, int64_t N, const double* mean_scale_dev, cudaStream_t st) {
+    if (N == 0) return cudaSuccess;
+    const unsigned gx = (unsigned)std::min<int64_t>((N + 255) / 256, 148 * 16);
+    k_standardize<<<dim3(gx, kNF), 256, 0, st>>>(x, out, N, mean_scale_dev);
     return cudaGetLastError();
 }
 
