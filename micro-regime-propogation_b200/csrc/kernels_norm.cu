@@ -341,6 +341,7 @@ __device__ __forceinline__ void run_totals(NormWarpStage& S, RunPipe& rp, const 
         if (lane == 0) {
             const int rows = min(kBlk, n - ij * kBlk);
             const double* src = x0 + icol + (int64_t)ij * kBlk;
+            fence_proxy_async_smem();   // the lanes' reads of this slot (ordered before this point by __syncwarp) precede the engine's write
             mbar_expect_tx(&S.full[sl], block_bytes(src, rows));
             block_load(S.slot[sl], src, rows, &S.full[sl]);
         }
@@ -422,6 +423,7 @@ __device__ __forceinline__ void run_zscores(NormWarpStage& S, RunPipe& rp, const
             const int s = j & 1;
             uint32_t bytes = block_bytes(src, rows);
             if (LAG) bytes += block_bytes(src - W, rows);
+            fence_proxy_async_smem();   // as in pass 1: generic-proxy reads of the slots before the engine's writes
             mbar_expect_tx(&S.full[s], bytes);
 #if MRP_NORM_HINTS & 4
             block_load_hint(S.slot[s], src, rows, &S.full[s], l2_policy_evict_last());   // read again as the lag, 15 tiles on
