@@ -123,7 +123,7 @@ int check_params(const mrp_fg_params& p) {
     if (p.stress_levels < 0 || p.stress_levels > p.depth_levels) return fail(MRP_FG_ERR_INVALID, "stress_levels must be in [0,depth_levels]");
     if (p.mid_window < 1 || p.dir_window < 1 || p.spread_divisor < 1 || p.ewm_span < 0 || p.norm_window < 1)
         return fail(MRP_FG_ERR_INVALID, "windows must be positive");
-    if (p.return_lag < 0 || p.return_lag + 1 > kThreads) return fail(MRP_FG_ERR_INVALID, "return_lag must be in [0,255]");
+    if (p.return_lag < 0 || p.return_lag + 1 > kThreads) return fail(MRP_FG_ERR_INVALID, "return_lag must be below the book kernel's chunk length (384 rows)");
     if (p.norm_mode != MRP_NORM_COMPENSATED && p.norm_mode != MRP_NORM_FAITHFUL) return fail(MRP_FG_ERR_INVALID, "unknown norm_mode");
     return MRP_FG_OK;
 }

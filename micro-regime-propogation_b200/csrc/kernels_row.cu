@@ -8,7 +8,7 @@
 namespace mrp {
 
 // ------------------------------------------------------------------------------------------------
-// book pass: one thread per snapshot row, 256 rows per chunk, chunks walked in time order so that the
+// book pass: one thread per snapshot row, kThreads (384) rows per chunk, chunks walked in time order so that the
 // two EMAs (ofi: 0.2/0.8, liquidity stress: 0.1/0.9) are carried as block scans of y -> a*y + b.
 // A segment that starts mid-stream first walks `ema_warm_rows` halo rows (only what feeds the EMAs
 // and the lag-21 midprice); 0.9^halo is below 1e-17, far under the fp64 noise of the features.
@@ -46,7 +46,7 @@ __device__ __noinline__ void lob_sums_direct(const double* __restrict__ bid_px, 
     *ask_lw = al;
 }
 
-// The EMA y_t = decay * y_{t-1} + b_t over a 256-row chunk, as a scan of affine maps.  pw2 = decay^(1,2,4,8,16,32)
+// The EMA y_t = decay * y_{t-1} + b_t over a chunk, as a scan of affine maps.  pw2 = decay^(1,2,4,8,16,32)
 // (kernel-parameter constants: operands, not loads); pw[n] = decay^n per lane.  Two halves around ONE block barrier so
 // that several EMAs share it: ema_warp (in-warp scan, publishes the warp's total), then ema_block (carries across warps).
 __device__ __forceinline__ double ema_warp(double b, const double (&pw2)[6], double* sWarp, int lane, int warp) {
@@ -80,19 +80,19 @@ __device__ __forceinline__ double ema_block(double v, const double (&pw2)[6], do
 #define MRP_BOOK_NS 2
 #endif
 #ifndef MRP_BOOK_MINB
-#define MRP_BOOK_MINB 2
+#define MRP_BOOK_MINB 1
 #endif
 constexpr int kStressCache = 4;  // levels 1..4 keep their last exp(-distance*decay) per thread
 
 // ---- bulk asynchronous copies (TMA, UBLKCP) with mbarrier completion.  One lane per (array, level) of a batch requests the
-// chunk's 256-row run of that level as ONE copy; nobody spends issue slots or registers on per-row loads.  Source
+// chunk's run of that level (kThreads rows) as ONE copy; nobody spends issue slots or registers on per-row loads.  Source
 // addresses are rounded down / up to the 16 bytes the copy engine wants and every thread adds the resulting element
 // shift (published in the stage header) to its slot index, so any row count and any 8 / 4-byte aligned base works.
-constexpr int kPxSlot = kThreads + 4;    // doubles: 256 rows + the <= 1 element alignment shift, padded to 16 bytes
-constexpr int kSzSlot = kThreads + 12;   // ints: 4 pad + previous row + 256 rows + the <= 3 element shift, padded
+constexpr int kPxSlot = kThreads + 4;    // doubles: a chunk's rows + the <= 1 element alignment shift, padded to 16 bytes
+constexpr int kSzSlot = kThreads + 12;   // ints: 4 pad + previous row + a chunk's rows + the <= 3 element shift, padded
 constexpr int kSzPad = 4;                // the copy lands 16 bytes into the slot, so "previous row" of row 0 never indexes below it
 
-// one landing stage: LG levels of a 256-row chunk
+// one landing stage: LG levels of a chunk
 template <int LG>
 struct __align__(16) BookStage {
     double bp[LG][kPxSlot], ap[LG][kPxSlot];
@@ -145,7 +145,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
 
     // ---- staging pipeline: batch b = (chunk, level group) lands in stage b % NS; batch b + NS - 1 is requested when batch b
     // starts, after every warp has released the stage's previous occupant.  The batch's 4*LG runs are spread over the
-    // warps: lane j of warp w owns run w + 8 j (array a, level g of the group) and keeps its invariants in registers.
+    // warps: lane j of warp w owns run w + kWarps j (array a, level g of the group) and keeps its invariants in registers.
     int64_t ic = wa;   // chunk of the next batch to request
     int ib = 0;        // its level group
     int nreq = 0;      // batches requested so far

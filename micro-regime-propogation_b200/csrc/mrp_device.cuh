@@ -86,7 +86,7 @@ struct DevParams {
 };
 
 #ifndef MRP_BOOK_THREADS
-#define MRP_BOOK_THREADS 256
+#define MRP_BOOK_THREADS 384   // measured: 384 x 1 CTA/SM (up to 168 registers) 4.88 ms, 256 x 2 (128 registers) 4.99 ms at 50 M rows
 #endif
 constexpr int kThreads = MRP_BOOK_THREADS;   // CTA size of the book pass (= rows per chunk)
 constexpr int kWarps = kThreads / 32;
