@@ -93,3 +93,14 @@ def test_product_package_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or fn == "Makefile":
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.lower().replace("# oracle-free", ""), os.path.join(dirpath, fn)
+
+
+def test_graft_entry_build_passes():
+    """The driver's "does it build" check: __graft_entry__.build() (nvcc cross-compile, host adaptor, checkers, ABI version
+    of the built library == the header's)."""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build(); print('ok')"], cwd=ROOT, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
