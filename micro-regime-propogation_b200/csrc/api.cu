@@ -114,6 +114,10 @@ struct mrp_fg_ctx {
     cudaEvent_t lane_done[2] = {nullptr, nullptr};
     uint32_t* lane_cursors[2] = {nullptr, nullptr};   // pinned: rebased tick / trade cursors of the chunk in flight
     size_t lane_cursor_cap[2] = {0, 0};
+    // the window and the book kernels write disjoint columns: the book pass may run on a second stream beside the window pass
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux[2] = {nullptr, nullptr};
+    int two_streams = 0;
 };
 
 namespace {
@@ -407,6 +411,7 @@ int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out) {
     mrp_fg_ctx* c = new mrp_fg_ctx();
     c->p = pp;
     c->device = device;
+    if (const char* e = std::getenv("MRP_FG_TWO_STREAMS")) c->two_streams = std::atoi(e) != 0;
     rc = setup_params(c);
     if (rc) {
         delete c;
@@ -433,6 +438,9 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
     for (DevBuf* b : bufs) b->release();
     if (c->ev_made)
         for (auto& ev : c->ev) cudaEventDestroy(ev);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    for (cudaEvent_t ev : {c->ev_fork, c->ev_join, c->ev_aux[0], c->ev_aux[1]})
+        if (ev) cudaEventDestroy(ev);
     delete c;
     return MRP_FG_OK;
 }
@@ -655,10 +663,30 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
         for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
         c->ev_made = true;
     }
+    if (c->two_streams && !c->aux_stream) {
+        CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CU(cudaEventCreate(&c->ev_aux[0]));
+        CU(cudaEventCreate(&c->ev_aux[1]));
+    }
     if (tm) CU(cudaEventRecord(c->ev[0], st));
-    CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, st));
-    if (tm) CU(cudaEventRecord(c->ev[1], st));
-    CU(launch_book(c->in, c->out, segs, c->nseg, c->dp, st));
+    if (c->two_streams) {
+        // fork: the book pass on the auxiliary stream, the window pass on the caller's; join before the normaliser
+        CU(cudaEventRecord(c->ev_fork, st));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        if (tm) CU(cudaEventRecord(c->ev_aux[0], c->aux_stream));
+        CU(launch_book(c->in, c->out, segs, c->nseg, c->dp, c->aux_stream));
+        if (tm) CU(cudaEventRecord(c->ev_aux[1], c->aux_stream));
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, st));
+        if (tm) CU(cudaEventRecord(c->ev[1], st));
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+    } else {
+        CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, st));
+        if (tm) CU(cudaEventRecord(c->ev[1], st));
+        CU(launch_book(c->in, c->out, segs, c->nseg, c->dp, st));
+    }
     if (tm) CU(cudaEventRecord(c->ev[2], st));
     CU(launch_normalize(c->out, c->n_rows, static_cast<const DevTile*>(c->b_tiles.p), c->ntiles,
                         static_cast<double*>(c->b_tile_tot.p), static_cast<int*>(c->b_flags.p), c->b_poison.p,
@@ -914,6 +942,7 @@ int mrp_fg_kernel_times_ms(mrp_fg_ctx* c, float* ms) {
     if (!c->have_times) return fail(MRP_FG_ERR_STATE, "no timed run yet (mrp_fg_enable_timing, then mrp_fg_run)");
     CU(cudaEventSynchronize(c->ev[kNumKernels]));
     for (int i = 0; i < kNumKernels; ++i) CU(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    if (c->two_streams && c->ev_aux[0]) CU(cudaEventElapsedTime(&ms[1], c->ev_aux[0], c->ev_aux[1]));   // the book pass ran beside the window pass
     return MRP_FG_OK;
 }
 

@@ -50,7 +50,9 @@ def test_large_run_is_idempotent_and_sane():
         mean = (p1[t + 1] - p1[t + 1 - W]) / W
         var = (p2[t + 1] - p2[t + 1 - W]) / W - mean * mean
         z = ((x[t] - mean) / np.sqrt(var)).astype(np.float64)
-        assert np.allclose(norm[c][t], z, rtol=0, atol=1e-7), mrp_b200.FEATURES[c]
+        kappa = ((p2[t + 1] - p2[t + 1 - W]) / W / var).astype(np.float64)     # conditioning of the window
+        tol = np.maximum(1.0, np.abs(z)) * (1e-9 + 16 * np.finfo(np.float64).eps * kappa)
+        assert (np.abs(norm[c][t] - z) <= tol).all(), (mrp_b200.FEATURES[c], float((np.abs(norm[c][t] - z) / tol).max()))
     # global moments == column sums (what an all-reduce across GPUs would add up)
     mom = eng.moments()
     assert np.allclose(mom[:, 0], n)
