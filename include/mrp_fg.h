@@ -49,8 +49,9 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 5   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
-                                  5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize */
+#define MRP_FG_ABI_VERSION 6   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
+                                  5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize;
+                                  6: + mrp_fg_halo_rows(_for), mrp_fg_moments_rows, mrp_fg_norm_moments_rows */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -217,18 +218,26 @@ int mrp_fg_download_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, do
  *     vov_h(t) = population standard deviation of the ewm_volatility column over the rows t-n+1 .. t of the same stream,
  *                n = min(t + 1, h); 0 when the variance is not positive
  *     z_h(t)   = rolling z-score of vov_h over norm_window rows, arithmetic of feature_normalizer.cpp:61-69
- * A non-finite value makes exactly the rows whose window contains it non-finite.  The horizons and norm_window must share
+ * A non-finite value makes the rows whose window contains it non-finite, and up to one tile (the shared divisor below) of rows
+ * after them (the sliding sums of that tile carry it).  The horizons and norm_window must share
  * a divisor >= 64.  raw / norm receive DEVICE pointers to double [n_horizons][n_rows] owned by the context (either may be
  * NULL); the 19 reference columns and the CSV layout are untouched. */
 int mrp_fg_vol_of_vol(mrp_fg_ctx* ctx, const int32_t* horizons, int32_t n_horizons, const double** raw, const double** norm, void* stream);
 /* Copy what the last mrp_fg_vol_of_vol produced to HOST buffers, double [n_horizons][n_rows] each; NULL = skip. */
 int mrp_fg_download_vol_of_vol(mrp_fg_ctx* ctx, double* raw, double* norm, void* stream);
 
-/* Per-column moments of the RAW features over all bound rows: out[c*3 + {0,1,2}] = {n, sum x, sum x^2}
- * (double [19*3], host).  These are what a caller allreduces across GPUs to get global
- * (StandardScaler-style) statistics (ref: regime_classifier/python/data_checks.py:79-80).
- * Synchronises `stream`. */
+/* Per-column moments of the RAW features: out[c*3 + {0,1,2}] = {non-NaN cells, sum x, sum x^2} (double [19*3], host) over all
+ * bound rows, or over the rows [row_begin, row_end) only — a time shard passes its OWN rows, so that the halo rows it
+ * recomputed (which its left neighbour also counts) stay out.  These are what a caller allreduces across GPUs to get
+ * global (StandardScaler-style) statistics (ref: regime_classifier/python/data_checks.py:79-80).  Synchronises `stream`. */
 int mrp_fg_moments(mrp_fg_ctx* ctx, double* out, void* stream);
+int mrp_fg_moments_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, double* out, void* stream);
+
+/* Rows of history that can still influence a row's features: norm_window + the EMA warm-up + a margin.  A time shard (or a
+ * chunk of a host-resident stream) that is preceded by this many rows of its stream — plus one window of ticks / trades in
+ * front of them — reproduces the whole-stream result on its own rows.  The one definition every caller uses. */
+int mrp_fg_halo_rows(const mrp_fg_ctx* ctx);
+int mrp_fg_halo_rows_for(const mrp_fg_params* p);   /* the same from parameters alone (NULL = defaults); needs no GPU */
 
 /* The step the reference's Python stage takes next (sklearn StandardScaler over the z-scored columns of ALL rows of ALL dates:
  * regime_classifier/python/classifier.py:35-37, data_checks.py:78-80), as three calls so that several GPUs / processes can combine:
@@ -240,6 +249,7 @@ int mrp_fg_moments(mrp_fg_ctx* ctx, double* out, void* stream);
  *   mrp_fg_standardize    (z - mean) / scale for every bound row into a context-owned device array double [19][n_rows]
  *                         (*out_device, may be NULL) and / or a HOST buffer of the same layout (out_host, may be NULL). */
 int mrp_fg_norm_moments(mrp_fg_ctx* ctx, double* out, void* stream);
+int mrp_fg_norm_moments_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, double* out, void* stream);   /* own rows of a time shard */
 int mrp_fg_mean_scale(const double* moments, double* mean_scale);
 int mrp_fg_standardize(mrp_fg_ctx* ctx, const double* moments, double* out_host, const double** out_device, void* stream);
 

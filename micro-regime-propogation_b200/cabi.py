@@ -142,6 +142,10 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_download_vol_of_vol.argtypes = [vp, vp, vp, vp]
     lib.mrp_fg_moments.argtypes = [vp, vp, vp]
     lib.mrp_fg_norm_moments.argtypes = [vp, vp, vp]
+    lib.mrp_fg_moments_rows.argtypes = [vp, i64, i64, vp, vp]
+    lib.mrp_fg_norm_moments_rows.argtypes = [vp, i64, i64, vp, vp]
+    lib.mrp_fg_halo_rows.argtypes = [vp]
+    lib.mrp_fg_halo_rows_for.argtypes = [PP]
     lib.mrp_fg_mean_scale.argtypes = [vp, vp]
     lib.mrp_fg_standardize.argtypes = [vp, vp, vp, C.POINTER(vp), vp]
     lib.mrp_fg_sync.argtypes = [vp, vp]
@@ -266,16 +270,24 @@ class Engine:
         self.sync(stream)
         return raw, norm
 
-    def moments(self, stream: int = 0) -> np.ndarray:
+    def moments(self, stream: int = 0, rows: Optional[Sequence[int]] = None) -> np.ndarray:
+        """[19, 3] = {non-NaN count, sum x, sum x^2} of the raw columns over all bound rows or over rows = (begin, end)."""
         m = np.empty((NUM_FEATURES, 3), np.float64)
-        self._check(self.lib.mrp_fg_moments(self.ctx, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
+        a, b = rows if rows is not None else (0, self.n_rows)
+        self._check(self.lib.mrp_fg_moments_rows(self.ctx, a, b, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
         return m
 
+    def halo_rows(self) -> int:
+        """Rows of history a time shard / host chunk needs in front of its own rows (mrp_fg_halo_rows)."""
+        return int(self.lib.mrp_fg_halo_rows(self.ctx))
+
     # -- the Python stage's StandardScaler over the z-scored columns (classifier.py:35-37), combinable across GPUs
-    def norm_moments(self, stream: int = 0) -> np.ndarray:
-        """[19, 3] = {non-NaN count, sum z, sum z^2} per z-scored column; ADD these across contexts / ranks."""
+    def norm_moments(self, stream: int = 0, rows: Optional[Sequence[int]] = None) -> np.ndarray:
+        """[19, 3] = {non-NaN count, sum z, sum z^2} per z-scored column (over rows = (begin, end) when given: a time shard's
+        own rows); ADD these across contexts / ranks."""
         m = np.empty((NUM_FEATURES, 3), np.float64)
-        self._check(self.lib.mrp_fg_norm_moments(self.ctx, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
+        a, b = rows if rows is not None else (0, self.n_rows)
+        self._check(self.lib.mrp_fg_norm_moments_rows(self.ctx, a, b, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
         return m
 
     def standardize(self, moments: np.ndarray, stream: int = 0, download: bool = True):
@@ -300,6 +312,15 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.mrp_fg_launch_count(self.ctx))
+
+
+def halo_rows(params: Optional[Params] = None) -> int:
+    """mrp_fg_halo_rows_for: rows of history a time shard / host chunk needs in front of its own rows (host arithmetic, no GPU)."""
+    p = params or default_params()
+    h = int(load().mrp_fg_halo_rows_for(C.byref(p)))
+    if h < 0:
+        raise MrpError("invalid EMA parameters")
+    return h
 
 
 def mean_scale(moments: np.ndarray) -> np.ndarray:

@@ -20,11 +20,11 @@ cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, do
 size_t norm_poison_bytes(int);
 cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
 int col_moment_blocks(int64_t N);
-cudaError_t launch_col_moments(const double* x, int64_t N, double* part, cudaStream_t st);
+cudaError_t launch_col_moments(const double* x, int64_t col_stride, int64_t N, double* part, cudaStream_t st);
 cudaError_t launch_standardize(const double* x, double* out, int64_t N, const double* mean_scale_dev, cudaStream_t st);
 cudaError_t launch_rolling(const double* x, int64_t x_stride, double* out, int64_t out_stride, const void* tiles, int ntiles, double* tot,
                            const int32_t* windows_dev, int njobs, int tile_rows, int mode, cudaStream_t st);
-size_t win_smem_bytes(int);
+bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, int* trade_ring, int* chunk_trades, size_t* smem);
 }  // namespace mrp
 
 using namespace mrp;
@@ -76,6 +76,31 @@ struct DevBuf {
 
 }  // namespace
 
+// pinned host staging: the source of an asynchronous copy must stay valid (and unpaged) until the copy has run
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap && p) return MRP_FG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e != cudaSuccess) {
+            g_err = std::string("cudaMallocHost(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+            return MRP_FG_ERR_NOMEM;
+        }
+        cap = bytes;
+        return MRP_FG_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct mrp_fg_ctx {
     mrp_fg_params p{};
     int device = 0;
@@ -93,6 +118,11 @@ struct mrp_fg_ctx {
     // tables
     DevBuf b_segs, b_tiles, b_tile_tot, b_flags, b_tables, b_row_off, b_poison;
     int nseg = 0, ntiles = 0;
+    // the segment / tile / row-offset tables are built on the host at bind time and copied on the stream of the next run
+    PinBuf h_tables;
+    size_t h_seg_bytes = 0, h_tile_bytes = 0, h_off_bytes = 0;
+    bool tables_dirty = false;
+    cudaEvent_t tables_ready = nullptr;   // recorded after the copy: runs on other streams wait for it
     // vol-of-vol extension (mrp_fg_vol_of_vol)
     DevBuf b_vov_raw, b_vov_norm, b_vov_tiles, b_vov_tot, b_vov_win;
     // global standardisation (mrp_fg_norm_moments / mrp_fg_standardize)
@@ -158,6 +188,17 @@ int pick_tile_rows(int W, int64_t n_rows) {
     return 0;
 }
 
+// Rows after which both row-axis EMAs have forgotten their start (decay^rows < 1e-17 for the slower one; also covers the
+// return lag), rounded up to whole chunks of the book pass.  -1: the alphas are out of range.
+int ema_warm_rows_for(const mrp_fg_params& p) {
+    const double slow = std::max(1.0 - p.ofi_alpha, 1.0 - p.stress_alpha);
+    int warm = 0;
+    if (slow > 0.0 && slow < 1.0) warm = (int)std::ceil(std::log(1e-17) / std::log(slow));
+    else if (slow >= 1.0) return -1;
+    warm = std::max(warm, p.return_lag + 1);
+    return ((warm + kThreads - 1) / kThreads) * kThreads;
+}
+
 // Build device parameters, ring geometry and the host-computed constant tables.
 int setup_params(mrp_fg_ctx* c) {
     const mrp_fg_params& p = c->p;
@@ -182,32 +223,18 @@ int setup_params(mrp_fg_ctx* c) {
     d.stress_min_size = p.stress_min_size;
     d.stress_distance_decay = p.stress_distance_decay;
 
-    // window kernel geometry: the ring holds one window plus the new ticks of one chunk
+    // window kernel geometry: the prefix rings hold one window plus the new ticks / trades of one chunk
     if (p.mid_window > 32767 || p.dir_window > 32767) return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window must be <= 32767 (16-bit window counters)");
-    const int wmax = std::max(p.mid_window, p.dir_window + 1);
-    int ring = 4096;
-    while (ring < 2 * wmax + 16) ring <<= 1;
-    if (ring > 8192)
-        return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window too large for the on-chip window ring (limit about 4000 ticks)");
-    d.win_ring = ring;
-    d.win_pipeline = 1;
-    if (const char* e = std::getenv("MRP_FG_WIN_PIPELINE")) d.win_pipeline = std::atoi(e) != 0;
-    d.win_span_max = ring - wmax - 8;
-    // the exponentially weighted sum is carried rescaled by decay^-(ticks into the chunk): keep that factor below e^200
-    if (!(d.ewm_decay > 0.0 && d.ewm_decay < 1.0)) return fail(MRP_FG_ERR_INVALID, "ewm_span must be >= 2 (decay = 1 - 2/(span+1) in (0,1))");
     {
-        const double lim = 200.0 / -std::log(d.ewm_decay);
-        if (lim < (double)d.win_span_max) d.win_span_max = (int)lim;
-        if (d.win_span_max < wmax + 4) return fail(MRP_FG_ERR_INVALID, "ewm_span too small for this mid_window (the rescaled EW sum would overflow)");
+        size_t smem = 0;
+        if (!win_geometry(p.mid_window, p.dir_window, &d.win_ring, &d.win_chunk_ticks, &d.win_trade_ring, &d.win_chunk_trades, &smem))
+            return fail(MRP_FG_ERR_INVALID, "mid_window / dir_window too large for the on-chip prefix rings (limit about 4000 ticks)");
     }
+    if (!(d.ewm_decay > 0.0 && d.ewm_decay < 1.0)) return fail(MRP_FG_ERR_INVALID, "ewm_span must be >= 2 (decay = 1 - 2/(span+1) in (0,1))");
 
-    // EMA halo: decay^rows < 1e-17 for the slower of the two EMAs, rounded up to whole chunks; also covers the lag
-    const double slow = std::max(d.ofi_decay, d.stress_decay);
-    int warm = 0;
-    if (slow > 0.0 && slow < 1.0) warm = (int)std::ceil(std::log(1e-17) / std::log(slow));
-    else if (slow >= 1.0) return fail(MRP_FG_ERR_INVALID, "EMA alphas must be in (0,1]");
-    warm = std::max(warm, p.return_lag + 1);
-    d.ema_warm_rows = ((warm + kThreads - 1) / kThreads) * kThreads;
+    // EMA halo of the book pass
+    d.ema_warm_rows = ema_warm_rows_for(p);
+    if (d.ema_warm_rows < 0) return fail(MRP_FG_ERR_INVALID, "EMA alphas must be in (0,1]");
 
     if (pick_tile_rows(p.norm_window, 1 << 30) <= 0) return fail(MRP_FG_ERR_INVALID, "norm_window above 4096 needs a divisor in [16,4096]");
 
@@ -217,9 +244,6 @@ int setup_params(mrp_fg_ctx* c) {
     for (int i = 0; i < p.depth_levels; ++i) tab.push_back(std::exp(-i * p.ofi_depth_decay));  // feature_processor.cpp:121
     const size_t o_e = tab.size();
     for (int n = 0; n <= d.win_ring; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
-    const size_t o_ei = tab.size();
-    for (int n = 0; n <= d.win_ring; ++n)
-        tab.push_back(n <= d.win_span_max + 1 ? (double)powl((long double)d.ewm_decay, -(long double)n) : 0.0);
     const size_t o_o = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
     for (int k = 0; k < 6; ++k) {
@@ -239,15 +263,20 @@ int setup_params(mrp_fg_ctx* c) {
     int rc = c->b_tables.ensure(tab.size() * sizeof(double));
     if (rc) return rc;
     CU(cudaMemcpy(c->b_tables.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());   // pageable source on the legacy stream: landed before any non-blocking stream reads it (create time only)
     const double* t = static_cast<const double*>(c->b_tables.p);
     d.ofi_weight = t + o_w;
     d.ewm_pow = t + o_e;
-    d.ewm_ipow = t + o_ei;
     d.ofi_pow = t + o_o;
     d.stress_pow = t + o_s;
     d.inv_cnt_norm = t + o_i;
     d.clog2c = t + o_h;
     d.inv_cnt = t + o_c;
+    // the same table entries for full windows, as kernel parameters
+    d.inv_ret_full = tab[o_c + std::max(p.mid_window - 1, 0)];
+    d.pow_ret_full = tab[o_e + std::max(p.mid_window - 1, 0)];
+    d.inv_dir_full = tab[o_c + p.dir_window];
+    d.clog2c_dir_full = tab[o_h + p.dir_window];
     return MRP_FG_OK;
 }
 
@@ -303,8 +332,7 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     }
     if (c->p.emit_counts) {
         if ((rc = c->b_counts.ensure((size_t)N * MRP_FG_NUM_COUNTS * sizeof(int32_t)))) return rc;
-        c->out.counts = static_cast<int32_t*>(c->b_counts.p);
-        CU(cudaMemset(c->out.counts, 0, (size_t)N * MRP_FG_NUM_COUNTS * sizeof(int32_t)));
+        c->out.counts = static_cast<int32_t*>(c->b_counts.p);   // every count column of every row is written by the kernels
     }
 
     // row segments: enough CTAs to fill 148 SMs several times over, long enough to amortise the window halo
@@ -356,9 +384,33 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     if ((rc = c->b_flags.ensure((tiles.size() + 1) * sizeof(int)))) return rc;
     if ((rc = c->b_row_off.ensure((S + 1) * sizeof(int64_t)))) return rc;
     if ((rc = c->b_poison.ensure(norm_poison_bytes(S)))) return rc;
-    if (!segs.empty()) CU(cudaMemcpy(c->b_segs.p, segs.data(), segs.size() * sizeof(DevSegment), cudaMemcpyHostToDevice));
-    if (!tiles.empty()) CU(cudaMemcpy(c->b_tiles.p, tiles.data(), tiles.size() * sizeof(DevTile), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->b_row_off.p, c->row_off.data(), (S + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    // the tables go to pinned staging; upload_tables() copies them on the stream of the next run (no legacy-stream traffic)
+    c->h_seg_bytes = segs.size() * sizeof(DevSegment);
+    c->h_tile_bytes = tiles.size() * sizeof(DevTile);
+    c->h_off_bytes = (size_t)(S + 1) * sizeof(int64_t);
+    if (c->tables_ready) CU(cudaEventSynchronize(c->tables_ready));   // a previous copy may still be reading the staging
+    if ((rc = c->h_tables.ensure(c->h_seg_bytes + c->h_tile_bytes + c->h_off_bytes))) return rc;
+    unsigned char* h = static_cast<unsigned char*>(c->h_tables.p);
+    if (c->h_seg_bytes) std::memcpy(h, segs.data(), c->h_seg_bytes);
+    if (c->h_tile_bytes) std::memcpy(h + c->h_seg_bytes, tiles.data(), c->h_tile_bytes);
+    std::memcpy(h + c->h_seg_bytes + c->h_tile_bytes, c->row_off.data(), c->h_off_bytes);
+    c->tables_dirty = true;
+    return MRP_FG_OK;
+}
+
+// Copy the tables of the current shape on `st` (first run after a bind) or make `st` wait for the copy that did.
+int upload_tables(mrp_fg_ctx* c, cudaStream_t st) {
+    if (!c->tables_ready) CU(cudaEventCreateWithFlags(&c->tables_ready, cudaEventDisableTiming));
+    if (c->tables_dirty) {
+        const unsigned char* h = static_cast<const unsigned char*>(c->h_tables.p);
+        if (c->h_seg_bytes) CU(cudaMemcpyAsync(c->b_segs.p, h, c->h_seg_bytes, cudaMemcpyHostToDevice, st));
+        if (c->h_tile_bytes) CU(cudaMemcpyAsync(c->b_tiles.p, h + c->h_seg_bytes, c->h_tile_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->b_row_off.p, h + c->h_seg_bytes + c->h_tile_bytes, c->h_off_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->tables_ready, st));
+        c->tables_dirty = false;
+    } else {
+        CU(cudaStreamWaitEvent(st, c->tables_ready, 0));
+    }
     return MRP_FG_OK;
 }
 
@@ -436,6 +488,8 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
                       &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win, &c->b_mom_part, &c->b_scaled,
                       &c->b_mean_scale};
     for (DevBuf* b : bufs) b->release();
+    c->h_tables.release();
+    if (c->tables_ready) cudaEventDestroy(c->tables_ready);
     if (c->ev_made)
         for (auto& ev : c->ev) cudaEventDestroy(ev);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -475,6 +529,20 @@ int mrp_fg_bind_inputs(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
 
 namespace {
 
+// `rows` slices of `width` bytes between two pitched layouts.  The runtime rejects pitches above cudaDeviceProp::memPitch
+// (2^31 - 1 bytes: a [L][n_rows] host array of more than 268 M rows), so such layouts take one plain copy per slice.
+cudaError_t copy_pitched(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows, cudaMemcpyKind kind,
+                         cudaStream_t st) {
+    constexpr size_t kMaxPitch = 0x7fffffffull;
+    if (dpitch <= kMaxPitch && spitch <= kMaxPitch) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+    for (size_t r = 0; r < rows; ++r) {
+        cudaError_t e = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + r * dpitch, static_cast<const unsigned char*>(src) + r * spitch,
+                                        width, kind, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // Copy a HOST view into the context's device buffers and bind them.  `level_stride` = elements between consecutive
 // levels of the level-major host arrays (== n_rows for a self-contained view; larger when the view is a row slice of a
 // bigger batch, mrp_fg_process_host).
@@ -513,8 +581,8 @@ int upload_impl(mrp_fg_ctx* c, const mrp_fg_soa_view* v, int64_t level_stride, c
         if ((rc = cp.b->ensure(bytes))) return rc;
         if (!bytes) continue;
         if (cp.levels && level_stride != N)
-            CU(cudaMemcpy2DAsync(cp.b->p, (size_t)N * cp.elem, cp.src, (size_t)level_stride * cp.elem, (size_t)N * cp.elem, (size_t)L,
-                                 cudaMemcpyHostToDevice, st));
+            CU(copy_pitched(cp.b->p, (size_t)N * cp.elem, cp.src, (size_t)level_stride * cp.elem, (size_t)N * cp.elem, (size_t)L,
+                            cudaMemcpyHostToDevice, st));
         else
             CU(cudaMemcpyAsync(cp.b->p, cp.src, bytes, cudaMemcpyHostToDevice, st));
     }
@@ -561,7 +629,7 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
     const int S = v->n_streams, L = c->p.depth_levels;
     const int64_t NT = v->row_offsets[S];
     if (NT == 0) return MRP_FG_OK;
-    const int64_t H = (int64_t)c->p.norm_window + c->dp.ema_warm_rows + 32;
+    const int64_t H = mrp_fg_halo_rows(c);
     if (chunk_rows <= 0) chunk_rows = 4 << 20;
     const int64_t wmax = std::max(c->p.mid_window, c->p.dir_window + 1);
     for (int i = 0; i < 2; ++i) {
@@ -576,6 +644,14 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
     }
     bool busy[2] = {false, false};
     int li = 0;
+    // whatever way this function is left, nothing may still be reading the caller's inputs or writing the caller's outputs
+    struct Drain {
+        mrp_fg_ctx* c;
+        ~Drain() {
+            for (int i = 0; i < 2; ++i)
+                if (c->lane_stream[i]) cudaStreamSynchronize(c->lane_stream[i]);
+        }
+    } drain{c};
     for (int s = 0; s < S; ++s) {
         const int64_t r0 = v->row_offsets[s], r1 = v->row_offsets[s + 1];
         const int64_t k0 = v->tick_offsets[s], K = v->tick_offsets[s + 1] - k0;
@@ -635,10 +711,10 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
             if ((rc = upload_impl(ln, &sub, NT, st, false))) return rc;
             if ((rc = mrp_fg_run(ln, st))) return rc;
             const int64_t skip = a - e0, own = b - a;
-            CU(cudaMemcpy2DAsync(raw + a, (size_t)NT * 8, ln->out.raw + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
-                                 cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpy2DAsync(norm + a, (size_t)NT * 8, ln->out.norm + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
-                                 cudaMemcpyDeviceToHost, st));
+            CU(copy_pitched(raw + a, (size_t)NT * 8, ln->out.raw + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
+                            cudaMemcpyDeviceToHost, st));
+            CU(copy_pitched(norm + a, (size_t)NT * 8, ln->out.norm + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
+                            cudaMemcpyDeviceToHost, st));
             CU(cudaEventRecord(c->lane_done[li], st));
             busy[li] = true;
             c->launches += kNumKernels + 1;
@@ -658,6 +734,10 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
     CU(cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevSegment* segs = static_cast<const DevSegment*>(c->b_segs.p);
+    {
+        int rc = upload_tables(c, st);
+        if (rc) return rc;
+    }
     const bool tm = c->timing;
     if (tm && !c->ev_made) {
         for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
@@ -819,63 +899,82 @@ int mrp_fg_download_rows(mrp_fg_ctx* c, int64_t row_begin, int64_t row_end, doub
     const size_t N = (size_t)c->n_rows, n = (size_t)(row_end - row_begin);
     if (n == 0) return MRP_FG_OK;
     // one strided copy per feature matrix: 19 column slices of n rows each
-    if (raw) CU(cudaMemcpy2DAsync(raw, n * 8, c->out.raw + row_begin, N * 8, n * 8, MRP_FG_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
-    if (norm) CU(cudaMemcpy2DAsync(norm, n * 8, c->out.norm + row_begin, N * 8, n * 8, MRP_FG_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+    if (raw) CU(copy_pitched(raw, n * 8, c->out.raw + row_begin, N * 8, n * 8, MRP_FG_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
+    if (norm) CU(copy_pitched(norm, n * 8, c->out.norm + row_begin, N * 8, n * 8, MRP_FG_NUM_FEATURES, cudaMemcpyDeviceToHost, st));
     return MRP_FG_OK;
 }
 
-int mrp_fg_moments(mrp_fg_ctx* c, double* out, void* stream) {
-    if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
-    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
-    CU(cudaSetDevice(c->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // the normaliser's per-tile totals already hold sum x and sum x^2 of every tile: add them up in extended precision
-    std::vector<double> tot((size_t)c->ntiles * 2 * MRP_FG_NUM_FEATURES);
-    if (!tot.empty()) CU(cudaMemcpyAsync(tot.data(), c->b_tile_tot.p, tot.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    for (int f = 0; f < MRP_FG_NUM_FEATURES; ++f) {
-        long double s = 0, s2 = 0;
-        for (int t = 0; t < c->ntiles; ++t) {
-            s += tot[(size_t)t * 2 * MRP_FG_NUM_FEATURES + f];
-            s2 += tot[(size_t)t * 2 * MRP_FG_NUM_FEATURES + MRP_FG_NUM_FEATURES + f];
-        }
-        out[f * 3 + 0] = (double)c->n_rows;
-        out[f * 3 + 1] = (double)s;
-        out[f * 3 + 2] = (double)s2;
-    }
-    return MRP_FG_OK;
-}
+}  // extern "C"
 
-int mrp_fg_norm_moments(mrp_fg_ctx* c, double* out, void* stream) {
-    if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
-    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
-    CU(cudaSetDevice(c->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int64_t N = c->n_rows;
-    const int nb = col_moment_blocks(N);
+namespace {
+// {non-NaN count, sum, sum of squares} of the rows [row_begin, row_end) of every column of a [19][n_rows] matrix: deterministic
+// block partials on the device, added in block order in extended precision on the host
+int column_moments(mrp_fg_ctx* c, const double* matrix, int64_t row_begin, int64_t row_end, double* out, cudaStream_t st) {
+    if (row_begin < 0 || row_end < row_begin || row_end > c->n_rows) return fail(MRP_FG_ERR_INVALID, "row range outside the bound rows");
+    const int64_t n = row_end - row_begin;
+    const int nb = col_moment_blocks(n);
     std::vector<double> part((size_t)nb * MRP_FG_NUM_FEATURES * 3);
     if (nb > 0) {
         int rc = c->b_mom_part.ensure(part.size() * sizeof(double));
         if (rc) return rc;
-        CU(launch_col_moments(c->out.norm, N, static_cast<double*>(c->b_mom_part.p), st));
+        CU(launch_col_moments(matrix + row_begin, c->n_rows, n, static_cast<double*>(c->b_mom_part.p), st));
         c->launches += 1;
         CU(cudaMemcpyAsync(part.data(), c->b_mom_part.p, part.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
-    for (int f = 0; f < MRP_FG_NUM_FEATURES; ++f) {   // block partials, in block order, in extended precision
-        long double n = 0, s = 0, s2 = 0;
+    for (int f = 0; f < MRP_FG_NUM_FEATURES; ++f) {
+        long double cnt = 0, s = 0, s2 = 0;
         for (int b = 0; b < nb; ++b) {
             const double* p = &part[((size_t)b * MRP_FG_NUM_FEATURES + f) * 3];
-            n += p[0];
+            cnt += p[0];
             s += p[1];
             s2 += p[2];
         }
-        out[f * 3 + 0] = (double)n;
+        out[f * 3 + 0] = (double)cnt;
         out[f * 3 + 1] = (double)s;
         out[f * 3 + 2] = (double)s2;
     }
     return MRP_FG_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int mrp_fg_moments_rows(mrp_fg_ctx* c, int64_t row_begin, int64_t row_end, double* out, void* stream) {
+    if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    return column_moments(c, c->out.raw, row_begin, row_end, out, static_cast<cudaStream_t>(stream));
+}
+
+int mrp_fg_moments(mrp_fg_ctx* c, double* out, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    return mrp_fg_moments_rows(c, 0, c->n_rows, out, stream);
+}
+
+int mrp_fg_norm_moments_rows(mrp_fg_ctx* c, int64_t row_begin, int64_t row_end, double* out, void* stream) {
+    if (!c || !out) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    return column_moments(c, c->out.norm, row_begin, row_end, out, static_cast<cudaStream_t>(stream));
+}
+
+int mrp_fg_norm_moments(mrp_fg_ctx* c, double* out, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    return mrp_fg_norm_moments_rows(c, 0, c->n_rows, out, stream);
+}
+
+int mrp_fg_halo_rows_for(const mrp_fg_params* p) {
+    mrp_fg_params d;
+    if (!p) {
+        mrp_fg_default_params(&d);
+        p = &d;
+    }
+    const int warm = ema_warm_rows_for(*p);
+    return warm < 0 ? -1 : p->norm_window + warm + 32;
+}
+
+int mrp_fg_halo_rows(const mrp_fg_ctx* c) { return c ? mrp_fg_halo_rows_for(&c->p) : -1; }
 
 int mrp_fg_mean_scale(const double* moments, double* mean_scale) {
     if (!moments || !mean_scale) return fail(MRP_FG_ERR_INVALID, "NULL argument");

@@ -712,12 +712,12 @@ cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* ti
 constexpr int kMomRows = 8192, kMomThreads = 256;
 
 __global__ void __launch_bounds__(kMomThreads)
-k_col_moments(const double* __restrict__ x, const int64_t N, double* __restrict__ part) {
+k_col_moments(const double* __restrict__ x, const int64_t col_stride, const int64_t N, double* __restrict__ part) {
     __shared__ double sh[3][kMomThreads / 32];
     const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * kMomRows;
     const int64_t r1 = r0 + kMomRows < N ? r0 + kMomRows : N;
-    const double* __restrict__ col = x + (int64_t)c * N;
+    const double* __restrict__ col = x + (int64_t)c * col_stride;
     double cnt = 0.0, s = 0.0, s2 = 0.0;
     for (int64_t r = r0 + tid; r < r1; r += kMomThreads) {
         const double v = col[r];
@@ -755,9 +755,10 @@ k_standardize(const double* __restrict__ x, double* __restrict__ out, const int6
 
 int col_moment_blocks(int64_t N) { return (int)((N + kMomRows - 1) / kMomRows); }
 
-cudaError_t launch_col_moments(const double* x, int64_t N, double* part, cudaStream_t st) {
+// column c of the matrix starts at x + c * col_stride; N rows of it are summed
+cudaError_t launch_col_moments(const double* x, int64_t col_stride, int64_t N, double* part, cudaStream_t st) {
     if (N == 0) return cudaSuccess;
-    k_col_moments<<<dim3((unsigned)col_moment_blocks(N), kNF), kMomThreads, 0, st>>>(x, N, part);
+    k_col_moments<<<dim3((unsigned)col_moment_blocks(N), kNF), kMomThreads, 0, st>>>(x, col_stride, N, part);
     return cudaGetLastError();
 }
 

@@ -6,8 +6,9 @@
 //                 n = min(t + 1, h)                                  (0 when the variance is not positive)
 //     z_h(t)    = rolling z-score of vov_h over norm_window rows, arithmetic of feature_normalizer.cpp:61-69
 //                 (std = 1 when the variance is not positive)
-// A non-finite value makes the rows whose window contains it non-finite and nothing else (exact windows; the
-// reference's "poisoned for ever" running sums are a property of ITS normaliser, not of this extension).
+// A non-finite value makes the rows whose window contains it non-finite, plus the rest of the tile in which it leaves the
+// window (that tile's sliding sums carry it: at most tile_rows - 1 further rows); the reference's "poisoned for ever" running
+// sums are a property of ITS normaliser, not of this extension.
 //
 // Same sliding-window algebra as the z-score normaliser (kernels_norm.cu): tiles of `tile_rows` rows, tile_rows dividing every
 // window;  window sum(t) = [totals of the preceding window / tile_rows tiles] + sum_{i <= t in tile} (x_i - x_{i - window}).

@@ -5,51 +5,52 @@
 //   trade axis: reversal_rate, aggressor_bias, shannon_entropy
 //                                           (ref: feature_processor.cpp:231-247, :254-269; feature_engine.cpp:87-93)
 //
-// The reference re-walks a 1800-tick (1500-trade) deque for every snapshot.  Here every window quantity is
-// a SLIDING sum: going from snapshot t-1 to t the window gains the ticks [k_{t-1}, k_t) and loses the ticks
-// [k_{t-1}-W, k_t-W), so
-//        sum_t = sum_{t-1} + A_t - B_t
-// and a chunk of 128 consecutive snapshots needs one cooperative pass over its NEW ticks (one reciprocal and
-// a 6-term log1p series per tick instead of two logs), two short per-snapshot loops over a shared-memory ring
-// (the added and the evicted ticks) and one 128-wide scan per quantity.  Each tick is read from HBM once.
+// The reference re-walks a 1800-tick (1500-trade) deque for every snapshot.  Here every window quantity is a
+// DIFFERENCE OF TWO PREFIXES kept in shared-memory rings, so a snapshot costs a handful of shared loads, whatever the
+// window length, and every tick / trade is read from HBM exactly once:
 //
-// Per-tick ring entries (8 B each):
-//   y_k = +r_k^2 when the return r_k = log(M_k / M_{k-1}) is > 0, -r_k^2 otherwise (-0.0 for a flat tick), so that
-//         sum|y| = sum r^2, sum y = (up part) - (down part), sign/zero tests give the tick direction;
-//   d_k = spread_k - pivot (pivot: a spread value near the window, removes the cancellation against the level).
-// The restarted exponentially weighted variance (feature_processor.cpp:64-79) over a window with first return f is
-//        w = sum_{i>f} alpha (1-alpha)^(e-1-i) x_i + (1-alpha)^(cnt-1) x_f
-// i.e. an exponentially weighted window sum E plus a correction for the first term; E slides like the other sums
-// once it is rescaled by (1-alpha)^-(position in chunk)  (F = E * decay^-(k - k_chunk)).
+//   per tick k (the 50 ms sample M_k, s_k), with x_k = log(M_k / M_{k-1})^2 and d_k = s_k - pivot:
+//        QA[k+1] = QA[k] + x_k            QS[k+1] = QS[k] +- x_k   (+ when the midprice rose)
+//        QD1[k+1] = QD1[k] + d_k          QD2[k+1] = QD2[k] + d_k^2
+//        QG[k+1] = (1-alpha) QG[k] + alpha x_k                      (a plain EMA over all ticks)
+//        QC[k+1] = QC[k] + (did not rise | moved << 16)             (two 16-bit counters, wrapping)
+//   a snapshot with tick cursor e, s = max(e - 1800, 0), cnt = e - s - 1 returns:
+//        sum r^2 = QA[e] - QA[s+1],  up - down = QS[e] - QS[s+1],  spread sums = QD*[e] - QD*[s],
+//        restarted EW variance (feature_processor.cpp:64-79) = QG[e] - (1-alpha)^cnt QG[s+1] + (1-alpha)^cnt x_{s+1},
+//        direction counts = QC[e] - QC[e-1500].
+//   per trade j: QT[j+1] = QT[j] + (pos, neg, reversal, dir) as four wrapping 16-bit counters in one 64-bit word.
 //
-// Ticks the fast formulation cannot represent — a non-positive / non-finite midprice, a 50 ms move above 2^-10
-// relative (series range), a non-finite spread — are flagged; every snapshot whose window contains a flagged tick
-// is evaluated by direct_tick_row(), a plain transcription of the reference loops with true logs, and the sliding
-// state is rebuilt from a clean halo once the flagged tick has left all windows.  A snapshot that brings more new
-// ticks than the ring can hold is handled the same way.  There is no CPU path.
+// One CTA streams through one row segment in time order; the prefixes restart at the segment's first window (a halo
+// of 1802 ticks / 1502 trades — no halo ROWS), so their magnitude stays within ~100 window sums and a difference
+// keeps ~14 digits.  Work is split by warp role, two CTA barriers per chunk of <= 128 rows / 1280 ticks:
+//   warps 0-7  producers: the chunk's new ticks, 5 consecutive ticks per thread out of a staging buffer the copy engine
+//              filled (cp.async.bulk + mbarrier, requested one chunk ahead; no thread issues a global load for a tick):
+//              one reciprocal per two ticks and a 6-term log1p series instead of two logs, thread-local prefixes in
+//              registers, one warp scan + one cross-warp pass per quantity, results into the rings;
+//   warps 8-11 consumers: plan the next chunk (cursors, how many rows fit, request its ticks), finalise the previous
+//              chunk's rows from registers, then — between the two barriers — gather this chunk's prefix values;
+//   warp 12    the trade prefixes (8 trades per lane and pass).
+// A snapshot that brings more new ticks / trades than a chunk holds simply advances the rings in several steps.
+//
+// Ticks the fast formulation cannot represent — a non-positive / non-finite midprice, a 50 ms move of 2^-10 relative or
+// more (series range), a non-finite spread — contribute nothing to the prefixes and are flagged; every snapshot whose
+// window contains a flagged tick is evaluated by direct_tick_row(), a plain transcription of the reference loops with
+// true logs.  There is no CPU path.
 #include "mrp_device.cuh"
 
 namespace mrp {
 
-#ifndef MRP_WIN_MINB
-#define MRP_WIN_MINB 3
-#endif
-constexpr int kWinThreads = 256;
-constexpr int kWinRows = 128;            // snapshots per chunk: threads 0..127 add side, 128..255 evict side + trades
+constexpr int kProdWarps = 4, kConsWarps = 4;
+constexpr int kProd = kProdWarps * 32;             // producer threads
+constexpr int kCons = kConsWarps * 32;             // consumer threads == most rows of one chunk
+constexpr int kWinThreads = kProd + kCons + 32;    // + the trade warp
+constexpr int kRun = 11;                           // consecutive ticks per producer thread (odd: conflict-free 64-bit shared accesses); long
+                                                   // runs keep the per-thread scan overhead (~300 instructions) small next to the tick arithmetic
+constexpr int kTradeRun = 8;                       // consecutive trades per lane of the trade warp
+constexpr int kTradeStage = 1024 + 32;             // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
 // the log1p series covers relative moves below 2^-10 per tick (high word 0x3f500000)
 
-struct __align__(16) WinShared {
-    double A[5][kWinRows];      // per-row deltas, then (after the scan) per-row window values
-    int AI[2][kWinRows];        // up | down << 16 tick counts: [0] returns of the mid window, [1] direction window
-    int TD[2][kWinRows];        // trades: [0] pos | neg << 16, [1] reversals | dir-sum << 16
-    uint32_t LM[kWinRows];      // 1 + position of the last tick that moved the midprice (running max)
-    uint32_t E[kWinRows + 1];   // clamped tick cursors: E[0] = previous cursor, E[i+1] = row c0+i
-    uint32_t J[kWinRows + 1];   // clamped trade cursors
-    uint32_t excP1;             // 1 + position of the last flagged tick (0 = none)
-};
-
-// 1/a to full precision for a normal, positive a (same refinement as the compiler's division fast path,
-// without its special-case branch: callers flag non-positive / non-finite inputs themselves).
+// 1/a for a normal, positive a (callers flag other inputs themselves): seed + two Newton steps
 __device__ __forceinline__ double rcp_pos(double a) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
@@ -60,10 +61,9 @@ __device__ __forceinline__ double rcp_pos(double a) {
     return fma(r, e, r);
 }
 
-// log(1+u) for |u| <= 2^-10: truncation below 2^-60 relative.
+// log(1+u) for |u| <= 2^-10: truncation below u^5/6 = 2^-52 relative.
 __device__ __forceinline__ double log1p_small(double u) {
-    double q = -1.0 / 6.0;
-    q = fma(q, u, 1.0 / 5.0);
+    double q = 1.0 / 5.0;
     q = fma(q, u, -1.0 / 4.0);
     q = fma(q, u, 1.0 / 3.0);
     q = fma(q, u, -0.5);
@@ -72,41 +72,10 @@ __device__ __forceinline__ double log1p_small(double u) {
 }
 
 __device__ __forceinline__ uint32_t sub_floor0(uint32_t a, uint32_t w) { return a > w ? a - w : 0u; }
-
-// In-place inclusive scan of 128 doubles by one warp (lane owns 4 consecutive rows) + running carry.
-__device__ __forceinline__ void scan128(double* __restrict__ a, double& carry, int lane) {
-    double2 p = *reinterpret_cast<double2*>(a + lane * 4), q = *reinterpret_cast<double2*>(a + lane * 4 + 2);
-    p.y += p.x;
-    q.x += p.y;
-    q.y += q.x;
-    double s = q.y;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double t = shfl_up_d(s, d);
-        if (lane >= d) s += t;
-    }
-    const double off = carry + (s - q.y);
-    p.x += off; p.y += off; q.x += off; q.y += off;
-    *reinterpret_cast<double2*>(a + lane * 4) = p;
-    *reinterpret_cast<double2*>(a + lane * 4 + 2) = q;
-    carry = __shfl_sync(0xffffffffu, q.y, 31);
+__device__ __forceinline__ bool small_mag(double v, uint32_t hi_limit) {  // |v| < the double whose high word is hi_limit; NaN -> false
+    return ((uint32_t)__double2hiint(v) & 0x7fffffffu) < hi_limit;
 }
-__device__ __forceinline__ void scan128(int* __restrict__ a, int& carry, int lane) {
-    int4 v = *reinterpret_cast<int4*>(a + lane * 4);
-    v.y += v.x;
-    v.z += v.y;
-    v.w += v.z;
-    int s = v.w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, s, d);
-        if (lane >= d) s += t;
-    }
-    const int off = carry + (s - v.w);
-    v.x += off; v.y += off; v.z += off; v.w += off;
-    *reinterpret_cast<int4*>(a + lane * 4) = v;
-    carry = __shfl_sync(0xffffffffu, v.w, 31);
-}
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // ---- direct evaluation of one snapshot's tick-axis features: the reference loops, in the reference order
 //      (feature_processor.cpp:48-107, :215-229).  Used for windows that contain a flagged tick.
@@ -186,7 +155,6 @@ __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, con
     write_tick_row(o, N, r, o_ewm, o_rv, o_dv, o_sv, ent, count, up_count, up, down, (int)(e - d0));
 }
 
-// trade-axis features of one snapshot from its window counts (feature_processor.cpp:231-247, :254-269)
 // a / n for a count n inside the host's 1/n table: reciprocal, product, ONE correction step (the quotient's remainder is
 // exact in an fma) — the correctly rounded quotient for the small integers that meet here, for 4 instructions and a load
 __device__ __forceinline__ double div_by_count(double a, int n, const double* __restrict__ inv_cnt) {
@@ -195,21 +163,14 @@ __device__ __forceinline__ double div_by_count(double a, int n, const double* __
     return fma(fma(-q, b, a), r, q);
 }
 
-// inv_cnt == nullptr: plain divisions (the direct path)
+// trade-axis features of one snapshot from its window counts (feature_processor.cpp:231-247, :254-269)
 __device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N, int64_t r, const double* __restrict__ clog2c,
                                                 const double* __restrict__ inv_cnt, int nd, int pos, int neg, int rev, int isum) {
     const int tot = pos + neg;                                  // :261-269
-    double rr, ab, ent;
-    if (inv_cnt) {
-        rr = nd > 1 ? div_by_count((double)rev, nd, inv_cnt) : 0.0;                                   // :239 — divides by size, not size-1
-        ab = nd > 0 ? div_by_count((double)isum, nd, inv_cnt) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
-        // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T with c*log2(c) tabulated by the host
-        ent = tot > 0 ? div_by_count((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg), tot, inv_cnt) : 0.0;
-    } else {
-        rr = nd > 1 ? (double)rev / (double)nd : 0.0;
-        ab = (double)isum / (double)nd;
-        ent = tot > 0 ? ((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg)) / (double)tot : 0.0;
-    }
+    const double rr = nd > 1 ? div_by_count((double)rev, nd, inv_cnt) : 0.0;                                   // :239 — divides by size, not size-1
+    const double ab = nd > 0 ? div_by_count((double)isum, nd, inv_cnt) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
+    // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T with c*log2(c) tabulated by the host
+    const double ent = tot > 0 ? div_by_count((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg), tot, inv_cnt) : 0.0;
     out.raw[(int64_t)MRP_F_REVERSAL_RATE * N + r] = rr;
     out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * N + r] = ab;
     out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + r] = ent;
@@ -222,121 +183,46 @@ __device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N
     }
 }
 
-__device__ __noinline__ void direct_trade_row(const int8_t* __restrict__ tdir, uint32_t je, uint32_t dir_window,
-                                              const double* __restrict__ clog2c, double* __restrict__ raw, int32_t* __restrict__ counts,
-                                              int64_t N, int64_t r) {
-    const uint32_t jb = sub_floor0(je, dir_window);
-    int pos = 0, neg = 0, rev = 0, isum = 0;
-    for (uint32_t j = jb; j < je; ++j) {
-        const int d = tdir[j];
-        pos += d > 0;
-        neg += d < 0;
-        isum += d;
-        if (j > jb && d != 0 && d == -(int)tdir[j - 1]) ++rev;
-    }
-    DevOutputs o{};
-    o.raw = raw;
-    o.counts = counts;
-    write_trade_row(o, N, r, clog2c, nullptr, (int)(je - jb), pos, neg, rev, isum);
-}
+// What a consumer thread lifts out of the rings for its row between the two barriers of a chunk.
+struct RowGather {
+    double SA, SS;        // sum x, sum +-x over the returns (s, e)
+    double D1, D2;        // sum d, sum d^2 over the spreads [s, e)
+    double Ge, Gs1;       // the running EMA at e and at s + 1
+    double xf;            // x of the window's first return (tick s + 1)
+    int negs, movm;       // sign-set / moved counts over the returns (s, e)
+    int negd, movd;       // the same over the direction window [d0, e)
+    int pos, neg, rev, isum;   // trade window counts
+    uint32_t e, je;
+    long long row;        // -1: nothing gathered
+    bool flagged;
+};
 
-// explicit 32-bit shared-window accessors for the ring (keeps address formation out of the inner loops)
-__device__ __forceinline__ double lds_f64(uint32_t a) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ double lds_f64_off(uint32_t a) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_hi32(uint32_t a) {  // high word of the double at a
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(v) : "r"(a));
-    return v;
-}
-template <int OFF>
-__device__ __forceinline__ void sts_f64_off(uint32_t a, double v) {
-    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
-}
-
-// y = +-r^2 of the return log(M / Mprev) = sgn * log1p(sgn * v) written with ONE reciprocal per pair of ticks:
-// v = (M - Mprev) * rcp with rcp = 1/Mprev (sgn = +1) or 1/M (sgn = -1, log(M/Mprev) = -log1p((Mprev - M)/M)).
-// t = Mprev - M; the sign bit of y is set unless the midprice rose (t < 0).
-__device__ __forceinline__ double signed_sq_return(double t, double v_signed) {
-    const double r = log1p_small(v_signed);
-    const double x = r * r;
-    const int hi = __double2hiint(x) | (~__double2hiint(t) & 0x80000000);
-    return __hiloint2double(hi, __double2loint(x));
-}
-__device__ __forceinline__ bool small_mag(double v, uint32_t hi_limit) {  // |v| < the double whose high word is hi_limit; NaN -> false
-    return ((uint32_t)__double2hiint(v) & 0x7fffffffu) < hi_limit;
-}
-
-// visit the ring slots of the positions [k0, k1) in order (at most one wrap): body(shared address, position)
-template <int RING, typename F>
-__device__ __forceinline__ void for_ring(uint32_t ring_base, uint32_t k0, uint32_t k1, F&& body) {
-    while (k0 < k1) {
-        const uint32_t slot = k0 & (RING - 1);
-        const uint32_t n = min(k1 - k0, (uint32_t)RING - slot);
-        uint32_t a = ring_base + slot * 8u;
-        const uint32_t aend = a + n * 8u;
-#pragma unroll 1
-        for (; a < aend; a += 8u) body(a);
-        k0 += n;
-    }
-}
-
-__device__ __forceinline__ void scan128_max(uint32_t* __restrict__ a, uint32_t& carry, int lane) {
-    uint4 v = *reinterpret_cast<uint4*>(a + lane * 4);
-    v.y = max(v.y, v.x);
-    v.z = max(v.z, v.y);
-    v.w = max(v.w, v.z);
-    uint32_t s = v.w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, s, d);
-        if (lane >= d) s = max(s, t);
-    }
-    uint32_t off = __shfl_up_sync(0xffffffffu, s, 1);
-    off = lane == 0 ? carry : max(carry, off);
-    v.x = max(v.x, off); v.y = max(v.y, off); v.z = max(v.z, off); v.w = max(v.w, off);
-    *reinterpret_cast<uint4*>(a + lane * 4) = v;
-    carry = __shfl_sync(0xffffffffu, v.w, 31);
-}
-
-// One snapshot's five tick-axis features from its window values.  The sliding sums cover the ticks [s, e) of the mid window
-// (SA = sum |y|, SS = sum y, D1 / D2 = sums of d and d^2, Eall = exponentially weighted sum, negs = sign-set count) and [d0, e) of
-// the direction window (dirw = sign-set | moved << 16); ys / yf are the ring entries of ticks s and s + 1; lm = 1 + position
-// of the last tick that moved the midprice.
-__device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int64_t N, const int64_t row, const DevParams& P,
-                                                const uint32_t e, const double pivot, const double SAall, const double SSall,
-                                                const double D1, const double D2, const double Eall, const int negs, const int dirw,
-                                                const uint32_t lm, const double ys, const double yf) {
+// One snapshot's five tick-axis features from its window values (see the file header).
+__device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int64_t N, const DevParams& P, const double pivot,
+                                                const RowGather& g) {
     double ewm = 0.0, rv = 0.0, dv = 0.0, sv = 0.0, tent = 0.0;
     int cnt = 0, nUp = 0, t_up = 0, t_dn = 0, t_tot = 0;
+    const uint32_t e = g.e;
     if (e > 0u) {
         const uint32_t s = sub_floor0(e, (uint32_t)P.mid_window);
         cnt = (int)(e - s) - 1;
         if (cnt > 0) {
-            // the window's returns are (s, e): take tick s out of the sums again
-            const double SA = SAall - fabs(ys), SS = SSall - ys;
-            nUp = cnt - (negs - (int)((uint32_t)__double2hiint(ys) >> 31));
-            // a window of flat ticks only is exactly zero in the reference; do not let rounding residue of the sliding sums
-            // through the square roots
-            const bool moved = lm > s + 1u;
-            const double tot = (SA > 0.0 && moved) ? SA : 0.0;
-            rv = tot * __ldg(P.inv_cnt + cnt);  // feature_processor.cpp:61 (tabulated 1/count)
+            nUp = cnt - g.negs;
+            // a window of flat ticks only is exactly zero in the reference; do not let rounding residue of the prefix
+            // differences through the square roots
+            const bool moved = g.movm > 0;
+            const double tot = (g.SA > 0.0 && moved) ? g.SA : 0.0;
+            const bool full = cnt == P.mid_window - 1;   // the steady state: the window's constants sit in the kernel parameters
+            rv = tot * (full ? P.inv_ret_full : __ldg(P.inv_cnt + cnt));  // feature_processor.cpp:61 (tabulated 1/count)
             double w = 0.0;
             if (tot != 0.0) {
-                // :64-79, see the file header: E over (s, e) plus the restart correction of the first return
-                w = Eall + __ldg(P.ewm_pow + cnt) * (fabs(yf) - P.ewm_alpha * fabs(ys));
+                // :64-79: sum_{i>=1} alpha decay^(cnt-i) x_i + decay^cnt x_1  (the restart takes x_1 with weight decay^(cnt-1))
+                const double pw = full ? P.pow_ret_full : __ldg(P.ewm_pow + cnt);
+                w = fma(pw, g.xf - g.Gs1, g.Ge);
                 if (!(w > 0.0)) w = 0.0;
             }
             ewm = sqrt(w);
-            double sumU = 0.5 * (SA + SS), sumD = 0.5 * (SA - SS);
+            double sumU = 0.5 * (g.SA + g.SS), sumD = 0.5 * (g.SA - g.SS);
             if (!(sumU > 0.0) || !moved) sumU = 0.0;
             if (!(sumD > 0.0) || !moved) sumD = 0.0;
             const double au = sumU * __ldg(P.inv_cnt + nUp);          // :95-98 (inv_cnt[0] = 0: empty side)
@@ -346,693 +232,574 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
         }
         {   // :101-107 with s_k = pivot + d_k: mean = (sum s)/1500, var = sum (s_k - mean)^2 / 1500
             const double n = (double)(e - s);
-            const double mean = (D1 + n * pivot) * P.inv_spread_divisor;
+            const double mean = (g.D1 + n * pivot) * P.inv_spread_divisor;
             const double delta = mean - pivot;
-            double ss = D2 - 2.0 * delta * D1 + n * delta * delta;
+            double ss = g.D2 - 2.0 * delta * g.D1 + n * delta * delta;
             if (!(ss > 0.0)) ss = 0.0;
             sv = sqrt(ss * P.inv_spread_divisor);
         }
         const uint32_t d0 = sub_floor0(e, (uint32_t)P.dir_window);
         t_tot = (int)(e - d0);
-        const int negd = dirw & 0xffff, movd = (dirw >> 16) & 0xffff;
-        t_up = t_tot - negd;            // sign clear <=> the midprice rose
-        t_dn = negd + movd - t_tot;     // sign set and moved
-        const int zero = t_tot - movd;
+        t_up = t_tot - g.negd;            // sign clear <=> the midprice rose
+        t_dn = g.negd + g.movd - t_tot;   // sign set and moved
+        const int zero = t_tot - g.movd;
         // :222-229: -sum p log2 p = (T log2 T - sum c log2 c) / T, c*log2(c) tabulated by the host
-        tent = ((__ldg(P.clog2c + t_tot) - __ldg(P.clog2c + t_up)) - __ldg(P.clog2c + t_dn) - __ldg(P.clog2c + zero)) *
-               __ldg(P.inv_cnt + t_tot);
+        const bool dfull = t_tot == P.dir_window;
+        tent = (((dfull ? P.clog2c_dir_full : __ldg(P.clog2c + t_tot)) - __ldg(P.clog2c + t_up)) - __ldg(P.clog2c + t_dn) - __ldg(P.clog2c + zero)) *
+               (dfull ? P.inv_dir_full : __ldg(P.inv_cnt + t_tot));
         if (cnt < 0) cnt = 0;
     }
-    write_tick_row(out, N, row, ewm, rv, dv, sv, tent, cnt, nUp, t_up, t_dn, t_tot);
+    write_tick_row(out, N, g.row, ewm, rv, dv, sv, tent, cnt, nUp, t_up, t_dn, t_tot);
 }
 
-// ================================================================================================
-// Pipelined chunk loop for clean data: warps 4-7 (producers) fetch the cursors, run the tick phase and the trade deltas
-// of chunk q+1 while warps 0-3 (consumers) run the row loops, the scans and the finalisation of chunk q.  The global-load
-// latency of the tick phase is thereby hidden behind shared-memory / ALU work instead of stalling the whole CTA at a
-// barrier.  Two chunks of new ticks must fit the ring next to one window, so a pipelined chunk holds at most 112 rows.
-// Anything irregular — a flagged tick, a snapshot with more new ticks than fit — makes the producers publish BAIL; the
-// kernel then continues from that row with the sequential chunk loop below, which owns all the special cases.
-// Named barriers: 1 producers, 2 consumers, 3/4 "descriptor b is full", 5/6 "descriptor b is free again".
-// ================================================================================================
-constexpr int kPipeRows = 112;
-enum { PIPE_RUN = 0, PIPE_END = 1, PIPE_BAIL = 2 };
-
-struct __align__(16) PipeDesc {
-    int TD[2][kWinRows];        // trade deltas of the chunk's rows, scanned in place by the consumers
-    uint32_t E[kWinRows + 1];   // clamped tick cursors, E[0] = the previous chunk's last
-    uint32_t J[kWinRows];       // clamped trade cursor of each row
-    long long c0;               // first row of the chunk
-    uint32_t Elast;
-    int nr, mode;
-};
-struct __align__(16) PipeShared {
-    double A[5][kWinRows];
-    int AI[2][kWinRows];
-    uint32_t LM[kWinRows];
-    PipeDesc d[2];
-    uint32_t exc;
-    int cnt[4];
-};
-
-__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// returns (through ps.d[..]) the first row it did not process; called by all 256 threads with a freshly restarted state
-template <int RING>
-__device__ __forceinline__ int64_t pipelined_chunks(PipeShared& ps, const uint32_t ring_base, const DevInputs& in, const DevOutputs& out,
-                                                    const DevSegment& sg, const DevParams& P, int64_t c0, const int64_t out_from,
-                                                    uint32_t Eprev, uint32_t Jprev, const uint32_t baseK, const uint32_t baseJ,
-                                                    const double pivot) {
-    constexpr uint32_t mask = RING - 1;
-    constexpr int kD = RING * 8;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t rb = sg.row_end, N = in.n_rows;
-    const double* __restrict__ mid = in.mid + sg.tick0;
-    const double* __restrict__ spread = in.spread + sg.tick0;
-    const int8_t* __restrict__ tdir = in.tdir + sg.trade0;
-    const uint32_t Wm = (uint32_t)P.mid_window, Wd = (uint32_t)P.dir_window;
-    const uint32_t Wmax = max(Wm, Wd + 1);
-    const uint32_t span_pipe = ((uint32_t)RING - Wmax - 8u) / 2u;
-    const double decay = P.ewm_decay;
-    if (tid == 0) ps.exc = 0u;
-    __syncthreads();
-
-    if (warp >= 4) {
-        // ------------------------------------------------------------------------------------ producers
-        const int pt = tid - kWinRows, pw = warp - 4;
-        int q = 0, published = 0;
-        // the cursors of a round are requested one round ahead
-        uint32_t nce = 0xffffffffu, ncj = 0xffffffffu;
-        if (c0 + pt < rb && pt < kPipeRows) {
-            nce = __ldg(in.kcur + c0 + pt);
-            ncj = __ldg(in.jcur + c0 + pt);
-        }
-        for (;; ++q) {
-            const int b = q & 1;
-            PipeDesc& D = ps.d[b];
-            if (q >= 2) bar_sync_n(5 + b, kWinThreads);   // the consumers have released this descriptor (chunk q-2)
-            int mode = PIPE_RUN, nr = 0;
-            uint32_t Elast = Eprev;
-            if (c0 >= rb) mode = PIPE_END;
-            else {
-                const int64_t row = c0 + pt;
-                uint32_t ce = 0xffffffffu, cj = 0xffffffffu;
-                if (row < rb && pt < kPipeRows) {
-                    ce = max(nce, baseK);
-                    cj = max(ncj, baseJ);
-                }
-                const bool fits = row < rb && pt < kPipeRows && ce - Eprev <= span_pipe;   // monotone in pt
-                const unsigned bal = __ballot_sync(0xffffffffu, fits);
-                if (lane == 0) ps.cnt[pw] = __popc(bal);
-                D.E[pt + 1] = ce;
-                D.J[pt] = cj;
-                if (pt == 0) D.E[0] = Eprev;
-                bar_sync_n(1, kWinRows);
-                nr = ps.cnt[0] + ps.cnt[1] + ps.cnt[2] + ps.cnt[3];
-                if (nr == 0) mode = PIPE_BAIL;
-                else {
-                    Elast = D.E[nr];
-                    {   // next round's cursors: in flight during this round's work
-                        const int64_t nrow = c0 + nr + pt;
-                        nce = ncj = 0xffffffffu;
-                        if (nrow < rb && pt < kPipeRows) {
-                            nce = __ldg(in.kcur + nrow);
-                            ncj = __ldg(in.jcur + nrow);
-                        }
-                    }
-                    // trade window boundaries of this thread's row: requested before the tick phase, used after it
-                    const uint32_t j0 = pt > 0 ? D.J[pt - 1] : Jprev, j1 = cj;
-                    uint32_t q0 = 0, q1 = 0;
-                    int dprev = 0, dq = 0;
-                    if (pt < nr) {
-                        q0 = max(baseJ, sub_floor0(j0, Wd));
-                        q1 = max(baseJ, sub_floor0(j1, Wd));
-                        if (j0 > baseJ) dprev = (int)tdir[j0 - 1];   // the trade at the base (trade 0) closes no pair
-                        if (q1 > q0) dq = (int)tdir[q0];
-                    }
-                    // tick phase: new ticks -> ring, two per thread (see the sequential loop for the derivation)
-                    uint32_t k = (Eprev & ~1u) + 2u * pt;
-                    double Ma = 1.0, Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
-                    auto fetch = [&](uint32_t kk, double& fMa, double& fMp, double& fMb, double& fSa, double& fSb) {
-                        if (kk < Elast) {
-                            // (defaults must not copy fMa: that would wait for its load before the others are even issued)
-                            fMa = __ldg(mid + kk);
-                            fSa = fSb = pivot;
-                            if (kk != baseK) fMp = __ldg(mid + kk - 1);
-                            if (kk >= Eprev) fSa = __ldg(spread + kk);
-                            if (kk + 1u < Elast) {
-                                fMb = __ldg(mid + kk + 1);
-                                fSb = __ldg(spread + kk + 1);
-                            }
-                        }
-                    };
-                    // two pairs ahead: the loads of pairs k+256 and k+512 are in flight while pair k is worked on.  The three
-                    // register sets rotate by unrolling, not by copying (a copy would wait for the load it copies).
-                    auto work = [&](const uint32_t kk, double wMa, double wMp, double wMb, const double wSa, const double wSb) {
-                        const bool va = kk >= Eprev, vb = kk + 1u < Elast;
-                        if (kk == baseK) wMp = wMa;
-                        if (!vb) wMb = wMa;
-                        const double ra = rcp_pos(wMa);
-                        const double ta = wMp - wMa, tb = wMa - wMb;
-                        const double va_ = ta * ra, vb_ = -tb * ra;
-                        const double ya = signed_sq_return(ta, va_), yb = signed_sq_return(tb, vb_);
-                        const double da = wSa - pivot, db = wSb - pivot;
-                        const bool ok = (uint32_t)(__double2hiint(wMa) - 0x00100000) < 0x7fe00000u && small_mag(va_, 0x3f500000u) &&
-                                        small_mag(vb_, 0x3f500000u) && small_mag(da, 0x5f138d35u) && small_mag(db, 0x5f138d35u);
-                        const uint32_t a = ring_base + (kk & mask) * 8u;
-                        if (va) { sts_f64_off<0>(a, ya); sts_f64_off<kD>(a, da); }
-                        if (vb) { sts_f64_off<8>(a, yb); sts_f64_off<kD + 8>(a, db); }
-                        if (!ok) ps.exc = 1u;
-                    };
-                    constexpr uint32_t S = 2u * kWinRows;
-                    double Ma1 = 1.0, Mp1 = 1.0, Mb1 = 1.0, Sa1 = pivot, Sb1 = pivot;
-                    double Ma2 = 1.0, Mp2 = 1.0, Mb2 = 1.0, Sa2 = pivot, Sb2 = pivot;
-                    fetch(k, Ma, Mp, Mb, Sa, Sb);
-                    fetch(k + S, Ma1, Mp1, Mb1, Sa1, Sb1);
-                    while (k < Elast) {
-                        fetch(k + 2u * S, Ma2, Mp2, Mb2, Sa2, Sb2);
-                        work(k, Ma, Mp, Mb, Sa, Sb);
-                        if (k + S >= Elast) break;
-                        fetch(k + 3u * S, Ma, Mp, Mb, Sa, Sb);
-                        work(k + S, Ma1, Mp1, Mb1, Sa1, Sb1);
-                        if (k + 2u * S >= Elast) break;
-                        fetch(k + 4u * S, Ma1, Mp1, Mb1, Sa1, Sb1);
-                        work(k + 2u * S, Ma2, Mp2, Mb2, Sa2, Sb2);
-                        k += 3u * S;
-                    }
-                    // trade deltas of this chunk's rows, read straight from global memory
-                    int w0 = 0, w1 = 0;
-                    if (pt < nr) {
-                        for (uint32_t j = j0; j < j1; ++j) {
-                            const int d = tdir[j];
-                            w0 += (d > 0 ? 1 : 0) + (d < 0 ? 65536 : 0);
-                            w1 += ((d != 0 && d == -dprev) ? 1 : 0) + (d << 16);   // feature_processor.cpp:235
-                            dprev = d;
-                        }
-                        int d = dq;
-                        for (uint32_t j = q0; j < q1; ++j) {
-                            const int dn = tdir[j + 1];
-                            w0 -= (d > 0 ? 1 : 0) + (d < 0 ? 65536 : 0);
-                            w1 -= ((dn != 0 && dn == -d) ? 1 : 0) + (d << 16);   // the pair (j, j+1) leaves with trade j
-                            d = dn;
-                        }
-                    }
-                    D.TD[0][pt] = w0;
-                    D.TD[1][pt] = w1;
-                    bar_sync_n(1, kWinRows);
-                    if (ps.exc != 0u) mode = PIPE_BAIL;   // a flagged tick: the sequential loop takes over from this chunk
-                }
-            }
-            if (pt == 0) {
-                D.c0 = c0;
-                D.Elast = Elast;
-                D.nr = nr;
-                D.mode = mode;
-            }
-            __threadfence_block();
-            bar_arrive_n(3 + b, kWinThreads);
-            if (mode != PIPE_RUN) break;
-            ++published;
-            const uint32_t jn = D.J[nr - 1];
-            bar_sync_n(1, kWinRows);      // everybody has read what it needs from D before the next round may overwrite its twin
-            Eprev = Elast;
-            Jprev = jn;
-            c0 += nr;
-        }
-        // drain: the "free again" arrival of the last processed chunk has no later round to consume it
-        if (published >= 1) bar_sync_n(5 + ((q - 1) & 1), kWinThreads);
-    } else {
-        // ------------------------------------------------------------------------------------ consumers
-        const int ct = tid;
-        // scan ownership: warp 0: A0, A4, TD0 | warp 1: A1, AI0, TD1 | warp 2: A2, AI1 | warp 3: A3, LM
-        double carry_a = 0.0, carry_b = 0.0;
-        int carry_i = 0, carry_t = 0;
-        uint32_t carry_lm = 0;
-        for (int q = 0;; ++q) {
-            const int b = q & 1;
-            PipeDesc& D = ps.d[b];
-            bar_sync_n(3 + b, kWinThreads);
-            if (D.mode != PIPE_RUN) break;
-            const int nr = D.nr;
-            const int64_t row = D.c0 + ct;
-            const uint32_t E0 = D.E[0], Elast = D.Elast;
-            uint32_t e0 = 0, e1 = 0;
-            if (ct < nr) { e0 = D.E[ct]; e1 = D.E[ct + 1]; }
-            {   // ticks that arrive: [e0, e1)
-                double sAll = 0.0, sSgn = 0.0, hh = 0.0, d1 = 0.0, d2 = 0.0;
-                uint32_t neg = 0, mov = 0, lm = 0;
-                uint32_t k0 = e0;
-                while (k0 < e1) {
-                    const uint32_t slot = k0 & mask;
-                    const uint32_t n = min(e1 - k0, (uint32_t)RING - slot);
-                    const uint32_t a0 = ring_base + slot * 8u, aend = a0 + n * 8u;
-                    uint32_t am = 0;
-#pragma unroll 1
-                    for (uint32_t a = a0; a < aend; a += 8u) {
-                        const double y = lds_f64(a), d = lds_f64_off<kD>(a);
-                        sAll += fabs(y);
-                        sSgn += y;
-                        hh = fma(hh, decay, fabs(y));
-                        neg += (uint32_t)__double2hiint(y) >> 31;
-                        if (((uint32_t)__double2hiint(y) << 1) != 0u) { ++mov; am = a; }
-                        d1 += d;
-                        d2 = fma(d, d, d2);
-                    }
-                    if (am != 0u) lm = k0 + ((am - a0) >> 3) + 1u;
-                    k0 += n;
-                }
-                // ticks that leave the direction window: [q0, q1)
-                const uint32_t q0 = max(baseK, sub_floor0(e0, Wd)), q1 = max(baseK, sub_floor0(e1, Wd));
-                uint32_t qneg = 0, qmov = 0;
-                for_ring<RING>(ring_base, q0, q1, [&](uint32_t a) {
-                    const uint32_t hi = lds_hi32(a);
-                    qneg += hi >> 31;
-                    if ((hi << 1) != 0u) ++qmov;
-                });
-                ps.A[0][ct] = sAll;
-                ps.A[1][ct] = sSgn;
-                ps.A[2][ct] = d1;
-                ps.A[3][ct] = d2;
-                ps.A[4][ct] = (ct < nr) ? P.ewm_alpha * hh * __ldg(P.ewm_ipow + (e1 - E0)) : 0.0;
-                ps.AI[0][ct] = (int)neg;
-                ps.AI[1][ct] = (int)(neg - qneg) + ((int)(mov - qmov) << 16);
-                ps.LM[ct] = lm;
-            }
-            {   // ticks that leave the mid window: [s0, s1) — same thread, same slots: no exchange needed
-                const uint32_t s0 = max(baseK, sub_floor0(e0, Wm)), s1 = max(baseK, sub_floor0(e1, Wm));
-                double bAll = 0.0, bSgn = 0.0, b1 = 0.0, b2 = 0.0, hE = 0.0;
-                uint32_t neg = 0;
-                for_ring<RING>(ring_base, s0, s1, [&](uint32_t a) {
-                    const double y = lds_f64(a), d = lds_f64_off<kD>(a);
-                    bAll += fabs(y);
-                    bSgn += y;
-                    hE = fma(hE, decay, fabs(y));
-                    neg += (uint32_t)__double2hiint(y) >> 31;
-                    b1 += d;
-                    b2 = fma(d, d, b2);
-                });
-                if (s1 > s0) {
-                    ps.A[0][ct] -= bAll;
-                    ps.A[1][ct] -= bSgn;
-                    ps.A[2][ct] -= b1;
-                    ps.A[3][ct] -= b2;
-                    ps.A[4][ct] -= P.ewm_alpha * hE * __ldg(P.ewm_pow + (e1 - s1)) * __ldg(P.ewm_ipow + (e1 - E0));
-                    ps.AI[0][ct] -= (int)neg;
-                }
-            }
-            bar_sync_n(2, kWinRows);
-            if (warp == 0) {
-                scan128(ps.A[0], carry_a, lane);
-                scan128(ps.A[4], carry_b, lane);
-                carry_b *= __ldg(P.ewm_pow + (Elast - E0));   // F is relative to the chunk's first tick
-                scan128(D.TD[0], carry_t, lane);
-            } else if (warp == 1) {
-                scan128(ps.A[1], carry_a, lane);
-                scan128(ps.AI[0], carry_i, lane);
-                scan128(D.TD[1], carry_t, lane);
-            } else if (warp == 2) {
-                scan128(ps.A[2], carry_a, lane);
-                scan128(ps.AI[1], carry_i, lane);
-            } else {
-                scan128(ps.A[3], carry_a, lane);
-                scan128_max(ps.LM, carry_lm, lane);
-            }
-            bar_sync_n(2, kWinRows);
-            if (ct < nr && row >= out_from) {
-                const uint32_t e = e1;
-                finish_tick_row(out, N, row, P, e, pivot, ps.A[0][ct], ps.A[1][ct], ps.A[2][ct], ps.A[3][ct],
-                                ps.A[4][ct] * __ldg(P.ewm_pow + (e - E0)), ps.AI[0][ct], ps.AI[1][ct], ps.LM[ct],
-                                lds_f64(ring_base + (sub_floor0(e, Wm) & mask) * 8u),
-                                lds_f64(ring_base + ((sub_floor0(e, Wm) + 1u) & mask) * 8u));
-                const uint32_t je = D.J[ct];
-                const uint32_t jb = sub_floor0(je, Wd);
-                const int w0 = D.TD[0][ct], w1 = D.TD[1][ct];
-                const int pos = w0 & 0xffff, neg = (w0 >> 16) & 0xffff, rev = w1 & 0xffff;
-                const int isum = (w1 - rev) >> 16;
-                write_trade_row(out, N, row, P.clog2c, P.inv_cnt, (int)(je - jb), pos, neg, rev, isum);
-            }
-            bar_sync_n(2, kWinRows);      // the A arrays and this descriptor are free again
-            bar_arrive_n(5 + b, kWinThreads);
-        }
-    }
-    __syncthreads();
-    // exactly one of the two descriptors carries the terminating mode; it names the first unprocessed row
-    const int64_t resume = ps.d[0].mode != PIPE_RUN ? (int64_t)ps.d[0].c0 : (int64_t)ps.d[1].c0;
-    __syncthreads();
-    return resume;
+// four wrapping 16-bit counters in one word: field-wise a + b
+__device__ __forceinline__ unsigned long long add4x16(unsigned long long a, unsigned long long b) {
+    const unsigned long long H = 0x8000800080008000ull;
+    return ((a & ~H) + (b & ~H)) ^ ((a ^ b) & H);
 }
 
-template <int RING>
-__global__ void __launch_bounds__(kWinThreads, MRP_WIN_MINB)
+enum { PLAN_RUN = 0, PLAN_END = 1 };
+struct __align__(16) WinPlan {
+    long long c0;              // first row of the chunk
+    uint32_t TFprev, TF;       // tick frontier before / after the chunk: the chunk's new ticks are [TFprev, TF)
+    uint32_t JFprev, JF;       // trade frontier
+    uint32_t slotT, slotJ;     // ring slots of the positions TFprev / JFprev
+    uint32_t stg0;             // tick position of the first staged element
+    int shM, shS, shT;         // element shift of the staged mids / spreads / trade bytes (16-byte rounding of the copy)
+    int nr, mode;              // rows finalised by this chunk (0: the rings only advance)
+};
+struct __align__(16) WinStatic {
+    WinPlan plan[2];
+    uint64_t full[2];                  // mbarriers of the two staging buffers
+    double wt[kProdWarps][6];          // per-warp totals: x, +-x, d, d^2, EMA, counts (bit pattern)
+    __align__(16) unsigned char stgT[2][kTradeStage];   // staged trade directions of the chunk (position JFprev - 1 onwards)
+    double carryG;                     // the EMA after the chunk's last tick
+    uint32_t excP1;                    // 1 + position of the last flagged tick (0 = none)
+    int cnt[kConsWarps];
+};
+
+__global__ void __launch_bounds__(kWinThreads, 1)
 k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
-    extern __shared__ __align__(16) double ring[];  // y: ring[0, RING)   d: ring[RING, 2 RING)
-    __shared__ __align__(16) unsigned char shraw[sizeof(PipeShared) > sizeof(WinShared) ? sizeof(PipeShared) : sizeof(WinShared)];
-    WinShared& sh = *reinterpret_cast<WinShared*>(shraw);
-    PipeShared& ps = *reinterpret_cast<PipeShared*>(shraw);   // the pipelined and the sequential loop never overlap in time
-    bool try_pipeline = P.win_pipeline != 0;
-    constexpr uint32_t mask = RING - 1;
-    constexpr int kD = RING * 8;  // byte offset of the d ring
-    const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
+    extern __shared__ __align__(16) unsigned char win_dyn[];
+    __shared__ WinStatic sh;
+    const int R = P.win_ring, RJ = P.win_trade_ring, CT = P.win_chunk_ticks, CJ = P.win_chunk_trades, CTS = CT + 4;
+    double* __restrict__ QA = reinterpret_cast<double*>(win_dyn);
+    double* __restrict__ QS = QA + R;
+    double* __restrict__ QD1 = QS + R;
+    double* __restrict__ QD2 = QD1 + R;
+    double* __restrict__ QG = QD2 + R;
+    double* __restrict__ stgM = QG + R;            // [2][CTS]
+    double* __restrict__ stgS = stgM + 2 * CTS;    // [2][CTS]
+    unsigned long long* __restrict__ QT = reinterpret_cast<unsigned long long*>(stgS + 2 * CTS);   // [RJ]
+    uint32_t* __restrict__ QC = reinterpret_cast<uint32_t*>(QT + RJ);                                // [R]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = tid & (kWinRows - 1);
-    const bool addside = tid < kWinRows;
     const DevSegment sg = segs[blockIdx.x];
-    const int64_t ra = sg.row_begin, rb = sg.row_end, sr0 = sg.stream_row0, N = in.n_rows;
+    const int64_t ra = sg.row_begin, rb = sg.row_end, N = in.n_rows;
     const double* __restrict__ mid = in.mid + sg.tick0;
     const double* __restrict__ spread = in.spread + sg.tick0;
     const int8_t* __restrict__ tdir = in.tdir + sg.trade0;
     const uint32_t* __restrict__ kcur = in.kcur;
     const uint32_t* __restrict__ jcur = in.jcur;
+    const uint32_t nTicks = (uint32_t)sg.n_ticks, nTrades = (uint32_t)sg.n_trades;
     const uint32_t Wm = (uint32_t)P.mid_window, Wd = (uint32_t)P.dir_window;
     const uint32_t Wmax = max(Wm, Wd + 1);
-    const uint32_t span_max = (uint32_t)P.win_span_max;
-    const double decay = P.ewm_decay;
-    DirectParams dp;
-    dp.mid_window = Wm;
-    dp.dir_window = Wd;
-    dp.spread_divisor = P.spread_divisor;
-    dp.ewm_alpha = P.ewm_alpha;
-    dp.ewm_decay = P.ewm_decay;
+    const double decay = P.ewm_decay, alpha = P.ewm_alpha;
 
-    // block-uniform sliding state
-    int64_t c0 = ra, out_from = ra, restart_at = ra;  // next row, first row to write, row the state is rebuilt for
-    bool need_restart = true;
-    uint32_t Eprev = 0, Jprev = 0, baseK = 0, baseJ = 0;
+    // the prefixes start one window before the segment's first row
+    const uint32_t e_first = min(__ldg(kcur + ra), nTicks), j_first = min(__ldg(jcur + ra), nTrades);
+    const uint32_t baseK = sub_floor0(e_first, Wmax + 2), baseJ = sub_floor0(j_first, Wd + 2);
     double pivot = 0.0;
-    double carry = 0.0;              // the scan carry of the quantity this warp owns (warps 0..4)
-    int carry_i0 = 0, carry_i1 = 0;  // warp 5: tick counts, warp 6: trade counts
-    uint32_t carry_lm = 0;           // warp 7: 1 + position of the last tick that moved the midprice
-    uint32_t pre_e = 0, pre_j = 0;   // cursors of the NEXT chunk's row, requested one chunk ahead
-    bool pre_valid = false;
-    if (tid == 0) sh.excP1 = 0u;
+    if (baseK < nTicks) {
+        const double s0 = __ldg(spread + baseK);
+        if (fabs(s0) <= 1e150) pivot = s0;
+    }
+    if (tid == 0) {
+        sh.excP1 = 0u;
+        sh.carryG = 0.0;
+        QA[0] = QS[0] = QD1[0] = QD2[0] = QG[0] = 0.0;
+        QC[0] = 0u;
+        QT[0] = 0ull;
+        mbar_init(&sh.full[0], 1);
+        mbar_init(&sh.full[1], 1);
+        mbar_init_fence();
+    }
     __syncthreads();
 
-    while (c0 < rb) {
-        // ------------------------------------------------------------------ (re)start from a clean halo
-        if (need_restart) {
-            const int64_t rs = restart_at;
-            int64_t h = sr0;
-            baseK = 0;
-            baseJ = 0;
-            if (rs > sr0) {
-                const uint32_t e = kcur[rs], j = jcur[rs];
-                baseK = sub_floor0(e, Wmax + 1) & ~1u;  // even: tick pairs never straddle the base
-                baseJ = sub_floor0(j, Wd + 1);
-                // first row whose cursors lie beyond the bases (cursors are non-decreasing): 256-ary search
-                int64_t lo = sr0, hi = rs;
-                while (lo < hi) {
-                    const int64_t step = (hi - lo + kWinThreads - 1) / kWinThreads;
-                    const int64_t p = lo + (int64_t)tid * step;
-                    const bool below = p < hi && !(kcur[p] > baseK || jcur[p] > baseJ);
-                    const int c = __syncthreads_count(below);
-                    if (c == 0) hi = lo;
-                    else {
-                        const int64_t nlo = lo + (int64_t)(c - 1) * step + 1;
-                        const int64_t nhi = lo + (int64_t)c * step;
-                        lo = nlo;
-                        hi = nhi < hi ? nhi : hi;
+    if (warp < kProdWarps) {
+        // ================================================================================ producers: ticks -> prefix rings
+        double cA = 0.0, cS = 0.0, cD1 = 0.0, cD2 = 0.0, cG = 0.0;   // the prefixes at the tick frontier
+        unsigned long long cC = 0ull;                               // ... of the two counters: did-not-rise | moved << 32
+        // decay^(11*2^k), decay^(11*lane), decay^352: the EMA composes over whole thread runs / warps
+        double pw2[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) pw2[k] = __ldg(P.ewm_pow + (kRun << k));
+        const double plane = __ldg(P.ewm_pow + kRun * lane), pwarp = __ldg(P.ewm_pow + kRun * 32);
+        __syncthreads();   // plan 0 is visible
+        for (int q = 0;; ++q) {
+            const WinPlan& pl = sh.plan[q & 1];
+            if (pl.mode != PLAN_RUN) break;
+            const uint32_t TFp = pl.TFprev, TF = pl.TF;
+            mbar_wait(&sh.full[q & 1], (uint32_t)((q >> 1) & 1));
+            if (TF > TFp) {
+                const double* __restrict__ sm = stgM + (q & 1) * CTS + pl.shM;
+                const double* __restrict__ ss = stgS + (q & 1) * CTS + pl.shS;
+                const uint32_t k0 = TFp + (uint32_t)(kRun * tid);
+                const int i0 = (int)(k0 - pl.stg0);
+                const int nv = k0 < TF ? (int)min(TF - k0, (uint32_t)kRun) : 0;   // valid ticks of this thread
+                // mids m[0] = M_{k0-1}, m[1..11] = M_{k0..k0+10}; d = spread - pivot
+                double m[kRun + 1], d[kRun];
+                if (nv == kRun && k0 > pl.stg0) {
+#pragma unroll
+                    for (int i = 0; i <= kRun; ++i) m[i] = sm[i0 - 1 + i];
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) d[i] = ss[i0 + i] - pivot;
+                } else {   // a partial run (the chunk's last thread), no run at all, or the tick at the base (no predecessor: flat)
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) {
+                        m[i + 1] = i < nv ? sm[i0 + i] : 0.0;
+                        d[i] = i < nv ? ss[i0 + i] - pivot : 0.0;
+                    }
+                    m[0] = (nv > 0 && k0 > pl.stg0) ? sm[i0 - 1] : m[1];
+                    if (nv == 0) m[0] = m[1] = 1.0;
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i)
+                        if (i >= nv) m[i + 1] = m[i];   // ticks past the frontier repeat their predecessor: flat, no contribution
+                }
+                // one reciprocal per two returns: log(M_k / M_{k-1}) = -log1p((M_{k-1} - M_k) / M_k) = log1p((M_k - M_{k-1}) / M_{k-1});
+                // x = +-r^2, the sign set unless the midprice rose (-0.0 for a flat tick)
+                double x[kRun];
+                uint32_t umax = 0u, dmax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
+#pragma unroll
+                for (int j = 0; j < (kRun + 1) / 2; ++j) {
+                    const double rc = rcp_pos(m[2 * j + 1]);
+                    rsign |= (uint32_t)__double2hiint(rc);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int i = 2 * j + h;
+                        if (i < kRun) {
+                            const double u = h == 0 ? (m[i] - m[i + 1]) * rc : (m[i + 1] - m[i]) * rc;   // h == 0: rose <=> u < 0
+                            const double r = log1p_small(u);
+                            const double xx = r * r;
+                            const uint32_t uh = (uint32_t)__double2hiint(u);
+                            umax = max(umax, uh & 0x7fffffffu);
+                            dmax = max(dmax, (uint32_t)__double2hiint(d[i]) & 0x7fffffffu);
+                            const bool mv = u != 0.0;
+                            const bool up = h == 0 ? u < 0.0 : u > 0.0;
+                            nneg += up ? 0u : 1u;
+                            nmov += mv ? 1u : 0u;
+                            x[i] = up ? xx : -xx;
+                        }
                     }
                 }
-                h = lo;
+                nneg -= (uint32_t)(kRun - nv);   // the padding ticks of a partial run are flat: they counted as "did not rise"
+                // flagged: a midprice that is not a positive normal number (its reciprocal is negative, or the returns round it are huge / NaN),
+                // a move beyond the series range, a spread that is not finite (or absurd)
+                if (!(umax < 0x3f500000u && dmax < 0x5f138d35u && (rsign >> 31) == 0u)) {
+                    if (nv > 0) atomicMax(&sh.excP1, k0 + (uint32_t)nv);
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) { x[i] = 0.0; d[i] = 0.0; }
+                    nneg = nmov = 0u;
+                }
+                // thread totals
+                double va = 0.0, vs = 0.0, v1 = 0.0, v2 = 0.0, vg = 0.0;
+#pragma unroll
+                for (int i = 0; i < kRun; ++i) {
+                    const double ax = fabs(x[i]);
+                    va += ax;
+                    vs += x[i];
+                    v1 += d[i];
+                    v2 = fma(d[i], d[i], v2);
+                    vg = fma(decay, vg, alpha * ax);
+                }
+                uint32_t vc = nneg | (nmov << 16);
+                // warp scans of the thread totals (inclusive), the EMA as a scan of y -> decay^11 y + b
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int dd = 1 << k;
+                    const double ua = shfl_up_d(va, dd), us = shfl_up_d(vs, dd), u1 = shfl_up_d(v1, dd), u2 = shfl_up_d(v2, dd),
+                                 ug = shfl_up_d(vg, dd);
+                    const uint32_t uc = __shfl_up_sync(0xffffffffu, vc, dd);
+                    if (lane >= dd) {
+                        va += ua; vs += us; v1 += u1; v2 += u2;
+                        vg = fma(pw2[k], ug, vg);
+                        vc += uc;
+                    }
+                }
+                if (lane == 31) {
+                    sh.wt[warp][0] = va; sh.wt[warp][1] = vs; sh.wt[warp][2] = v1; sh.wt[warp][3] = v2; sh.wt[warp][4] = vg;
+                    sh.wt[warp][5] = __longlong_as_double((long long)(((unsigned long long)(vc >> 16) << 32) | (vc & 0xffffu)));
+                }
+                // exclusive within the warp (by shuffle, not by subtraction)
+                double xa = shfl_up_d(va, 1), xs = shfl_up_d(vs, 1), x1 = shfl_up_d(v1, 1), x2 = shfl_up_d(v2, 1), xg = shfl_up_d(vg, 1);
+                uint32_t xc = __shfl_up_sync(0xffffffffu, vc, 1);
+                if (lane == 0) { xa = xs = x1 = x2 = xg = 0.0; xc = 0u; }
+                bar_sync_n(1, kProd);
+                // across the warps: lane l (< 6) walks quantity l over the warp totals; the four sums and the EMA share one
+                // fused multiply-add (factor 1 or decay^352), the counters an integer add
+                double mine_d = 0.0, acc_d;
+                long long mine_i = 0, acc_i = (long long)cC;
+                {
+                    const int ql = lane < 6 ? lane : 0;
+                    acc_d = ql == 0 ? cA : ql == 1 ? cS : ql == 2 ? cD1 : ql == 3 ? cD2 : cG;
+                    const double mul = ql == 4 ? pwarp : 1.0;
+#pragma unroll
+                    for (int w = 0; w < kProdWarps; ++w) {
+                        if (w == warp) { mine_d = acc_d; mine_i = acc_i; }
+                        const double t = sh.wt[w][ql];
+                        acc_d = fma(mul, acc_d, t);
+                        acc_i += __double_as_longlong(t);
+                    }
+                }
+                double gA = __shfl_sync(0xffffffffu, mine_d, 0) + xa, gS = __shfl_sync(0xffffffffu, mine_d, 1) + xs,
+                       g1 = __shfl_sync(0xffffffffu, mine_d, 2) + x1, g2 = __shfl_sync(0xffffffffu, mine_d, 3) + x2;
+                double gG = fma(plane, __shfl_sync(0xffffffffu, mine_d, 4), xg);   // the EMA entering this thread's first tick
+                const unsigned long long mC = (unsigned long long)__shfl_sync(0xffffffffu, mine_i, 5);
+                uint32_t gNeg = (uint32_t)mC + (xc & 0xffffu), gMov = (uint32_t)(mC >> 32) + (xc >> 16);
+                cA = __shfl_sync(0xffffffffu, acc_d, 0);
+                cS = __shfl_sync(0xffffffffu, acc_d, 1);
+                cD1 = __shfl_sync(0xffffffffu, acc_d, 2);
+                cD2 = __shfl_sync(0xffffffffu, acc_d, 3);
+                cC = (unsigned long long)__shfl_sync(0xffffffffu, acc_i, 5);
+                // into the rings: the prefix AFTER tick k lives at position k + 1.  The running sums continue from the offsets.
+                uint32_t slot = pl.slotT + (uint32_t)(kRun * tid) + 1u;
+                if (slot >= (uint32_t)R) slot -= (uint32_t)R;
+                if (nv == kRun && slot + (uint32_t)kRun <= (uint32_t)R) {
+                    double* __restrict__ pA = QA + slot;
+                    double* __restrict__ pS = QS + slot;
+                    double* __restrict__ p1 = QD1 + slot;
+                    double* __restrict__ p2 = QD2 + slot;
+                    double* __restrict__ pG = QG + slot;
+                    uint32_t* __restrict__ pC = QC + slot;
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) {
+                        const double ax = fabs(x[i]);
+                        gA += ax;
+                        gS += x[i];
+                        g1 += d[i];
+                        g2 = fma(d[i], d[i], g2);
+                        gG = fma(decay, gG, alpha * ax);
+                        gNeg += (uint32_t)__double2hiint(x[i]) >> 31;
+                        gMov += ax != 0.0 ? 1u : 0u;
+                        pA[i] = gA; pS[i] = gS; p1[i] = g1; p2[i] = g2; pG[i] = gG;
+                        pC[i] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
+                    }
+                    if (k0 + (uint32_t)kRun == TF) sh.carryG = gG;
+                } else if (nv > 0) {
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) {
+                        if (i < nv) {
+                            const double ax = fabs(x[i]);
+                            gA += ax;
+                            gS += x[i];
+                            g1 += d[i];
+                            g2 = fma(d[i], d[i], g2);
+                            gG = fma(decay, gG, alpha * ax);
+                            gNeg += (uint32_t)__double2hiint(x[i]) >> 31;
+                            gMov += ax != 0.0 ? 1u : 0u;
+                            QA[slot] = gA; QS[slot] = gS; QD1[slot] = g1; QD2[slot] = g2; QG[slot] = gG;
+                            QC[slot] = (gNeg & 0xffffu) | (gMov << 16);
+                            if (++slot == (uint32_t)R) slot = 0u;
+                        }
+                    }
+                    if (k0 + (uint32_t)nv == TF) sh.carryG = gG;
+                }
             }
-            c0 = h;
-            out_from = rs;
-            Eprev = baseK;
-            Jprev = baseJ;
-            pivot = 0.0;
-            if ((int64_t)baseK < sg.n_ticks) {
-                const double s0 = __ldg(spread + baseK);
-                if (fabs(s0) <= 1e150) pivot = s0;
-            }
-            carry = 0.0;
-            carry_i0 = carry_i1 = 0;
-            carry_lm = 0;
-            need_restart = false;
-            pre_valid = false;
-            if (try_pipeline) {
-                // clean data runs through the producer / consumer pipeline; it hands back the first row it left alone
-                try_pipeline = false;
-                const int64_t resume = pipelined_chunks<RING>(ps, ring_base, in, out, sg, P, c0, out_from, Eprev, Jprev, baseK, baseJ, pivot);
-                if (tid == 0) sh.excP1 = 0u;
-                __syncthreads();
-                c0 = resume;
-                if (c0 >= rb) break;
-                out_from = c0 > out_from ? c0 : out_from;
-                restart_at = out_from;
-                need_restart = true;
-                continue;
-            }
+            __syncthreads();   // S1: the rings hold the chunk
+            if (TF > TFp) cG = sh.carryG;
+            __syncthreads();   // S0: the consumers have gathered
         }
-
-        // ------------------------------------------------------------------ cursors of up to 128 rows
-        const int64_t row = c0 + i;
-        uint32_t ce = 0xffffffffu, cj = 0xffffffffu;
-        if (row < rb) {
-            ce = max(pre_valid ? pre_e : __ldg(kcur + row), baseK);
-            cj = max(pre_valid ? pre_j : __ldg(jcur + row), baseJ);
-        }
-        if (addside) {
-            sh.E[i + 1] = ce;
-            sh.J[i + 1] = cj;
-            if (i == 0) { sh.E[0] = Eprev; sh.J[0] = Jprev; }
-        }
-        // rows whose new ticks still fit the ring (monotone in i)
-        int nr = __syncthreads_count(addside && row < rb && ce - Eprev <= span_max);
-        if (nr == 0) {
-            // one snapshot with more new ticks than the ring holds: evaluate it directly, then start over behind it
-            if (c0 >= out_from) {
-                if (tid == 0) direct_tick_row(mid, spread, __ldg(kcur + c0), dp, out.raw, out.counts, N, c0);
-                else if (tid == kWinRows) direct_trade_row(tdir, __ldg(jcur + c0), Wd, P.clog2c, out.raw, out.counts, N, c0);
+    } else if (warp < kProdWarps + kConsWarps) {
+        // ================================================================================ consumers: plan, finalise, gather
+        const int ci = tid - kProd, cw = warp - kProdWarps;
+        DirectParams dpm;
+        dpm.mid_window = Wm;
+        dpm.dir_window = Wd;
+        dpm.spread_divisor = P.spread_divisor;
+        dpm.ewm_alpha = P.ewm_alpha;
+        dpm.ewm_decay = P.ewm_decay;
+        uint32_t cur_e = 0, cur_j = 0;   // this thread's row of the chunk about to be gathered
+        // plan the chunk that follows (TFq, JFq) and starts at row c0n, from this thread's candidate cursors; request its ticks
+        auto make_plan = [&](const int slot_idx, const long long c0n, const uint32_t TFq, const uint32_t JFq, const uint32_t slotT,
+                             const uint32_t slotJ, const uint32_t pe, const uint32_t pj) {
+            const long long row = c0n + ci;
+            const bool inr = row < rb;
+            const uint32_t ce = inr ? min(max(pe, TFq), nTicks) : 0xffffffffu, cj = inr ? min(max(pj, JFq), nTrades) : 0xffffffffu;
+            const bool fits = inr && ce - TFq <= (uint32_t)CT && cj - JFq <= (uint32_t)CJ;   // monotone in ci
+            const unsigned bal = __ballot_sync(0xffffffffu, fits);
+            if (lane == 0) sh.cnt[cw] = __popc(bal);
+            bar_sync_n(2, kCons);
+            const int nr = sh.cnt[0] + sh.cnt[1] + sh.cnt[2] + sh.cnt[3];
+            if (ci == (nr > 0 ? nr - 1 : 0)) {
+                WinPlan& np = sh.plan[slot_idx];
+                const bool end = c0n >= rb;
+                uint32_t TFn = TFq, JFn = JFq;
+                if (!end) {
+                    TFn = nr > 0 ? ce : min(ce, TFq + (uint32_t)CT);
+                    JFn = nr > 0 ? cj : min(cj, JFq + (uint32_t)CJ);
+                }
+                np.c0 = c0n;
+                np.TFprev = TFq;
+                np.TF = TFn;
+                np.JFprev = JFq;
+                np.JF = JFn;
+                np.slotT = slotT;
+                np.slotJ = slotJ;
+                np.nr = nr;
+                np.mode = end ? PLAN_END : PLAN_RUN;
+                const uint32_t s0 = TFq > baseK ? TFq - 1u : baseK;
+                np.stg0 = s0;
+                np.shM = np.shS = np.shT = 0;
+                uint64_t* bar = &sh.full[slot_idx];
+                // what the copy engine stages for the chunk: mids and spreads from the tick before the frontier, trade directions from
+                // the trade before the frontier; 16-byte rounding on both ends, the element shifts are published with the plan
+                uintptr_t qm = 0, qs = 0, qt = 0;
+                uint32_t bm = 0, bs = 0, bt = 0;
+                if (!end && TFn > TFq) {
+                    const uintptr_t am = reinterpret_cast<uintptr_t>(mid + s0), as = reinterpret_cast<uintptr_t>(spread + s0);
+                    const uintptr_t bytes = (uintptr_t)(TFn - s0) * 8u;
+                    qm = am & ~(uintptr_t)15;
+                    qs = as & ~(uintptr_t)15;
+                    bm = (uint32_t)(((am + bytes + 15) & ~(uintptr_t)15) - qm);
+                    bs = (uint32_t)(((as + bytes + 15) & ~(uintptr_t)15) - qs);
+                    np.shM = (int)((am - qm) >> 3);
+                    np.shS = (int)((as - qs) >> 3);
+                }
+                if (!end && JFn > JFq) {
+                    const uint32_t t0 = JFq > baseJ ? JFq - 1u : baseJ;
+                    const uintptr_t at = reinterpret_cast<uintptr_t>(tdir + t0);
+                    qt = at & ~(uintptr_t)15;
+                    bt = (uint32_t)(((at + (JFn - t0) + 15) & ~(uintptr_t)15) - qt);
+                    np.shT = (int)(at - qt);
+                }
+                if (bm + bt != 0u) {
+                    fence_proxy_async_smem();   // the readers of this buffer (two barriers ago) precede the engine's writes
+                    mbar_expect_tx(bar, bm + bs + bt);
+                    if (bm) {
+                        bulk_g2s(stgM + slot_idx * CTS, reinterpret_cast<const void*>(qm), bm, bar);
+                        bulk_g2s(stgS + slot_idx * CTS, reinterpret_cast<const void*>(qs), bs, bar);
+                    }
+                    if (bt) bulk_g2s(sh.stgT[slot_idx], reinterpret_cast<const void*>(qt), bt, bar);
+                } else {
+                    mbar_arrive(bar);           // nothing to stage: the phase completes at once
+                }
             }
-            restart_at = c0 + 1;
-            out_from = c0 + 1;
-            c0 = c0 + 1;
-            need_restart = true;
-            __syncthreads();
-            continue;
-        }
-        uint32_t Elast = sh.E[nr];
-
-        // ------------------------------------------------------------------ tick phase: new ticks -> ring, two per thread
-        for (uint32_t k = (Eprev & ~1u) + 2u * tid; k < Elast; k += 2u * kWinThreads) {
-            // ticks a = k (new unless k < Eprev) and b = k + 1 (new unless past the chunk); k is even
-            const bool va = k >= Eprev, vb = k + 1u < Elast;
-            // all five loads are issued before any value is touched (a default such as `Mp = Ma` would wait for Ma's load first)
-            const double Ma = __ldg(mid + k);
-            double Mp = 1.0, Mb = 1.0, Sa = pivot, Sb = pivot;
-            if (k != baseK) Mp = __ldg(mid + k - 1);
-            if (va) Sa = __ldg(spread + k);
-            if (vb) {
-                Mb = __ldg(mid + k + 1);
-                Sb = __ldg(spread + k + 1);
-            }
-            if (k == baseK) Mp = Ma;   // the tick at the base (tick 0) has no return: flat
-            if (!vb) Mb = Ma;          // defaults give flat, unflagged ticks
-            const double ra = rcp_pos(Ma);
-            const double ta = Mp - Ma, tb = Ma - Mb;
-            const double va_ = ta * ra, vb_ = -tb * ra;        // (Mp-Ma)/Ma and (Mb-Ma)/Ma
-            const double ya = signed_sq_return(ta, va_), yb = signed_sq_return(tb, vb_);
-            const double da = Sa - pivot, db = Sb - pivot;
-            // flagged: a midprice that is not a positive normal number, a move beyond the series range, a spread that is
-            // not finite (or absurd).  One flag per pair, attributed to tick b (conservative by one position).
-            const bool ok = (uint32_t)(__double2hiint(Ma) - 0x00100000) < 0x7fe00000u && small_mag(va_, 0x3f500000u) &&
-                            small_mag(vb_, 0x3f500000u) && small_mag(da, 0x5f138d35u) && small_mag(db, 0x5f138d35u);
-            const uint32_t a = ring_base + (k & mask) * 8u;
-            if (va) { sts_f64_off<0>(a, ya); sts_f64_off<kD>(a, da); }
-            if (vb) { sts_f64_off<8>(a, yb); sts_f64_off<kD + 8>(a, db); }
-            if (!ok) atomicMax(&sh.excP1, k + 2u);
-        }
-        __syncthreads();
-        const uint32_t excP1 = sh.excP1;
-        if (excP1 != 0u && excP1 - 1u >= baseK) {
-            // The sliding state has absorbed (or is about to absorb) a flagged tick.  Rows whose window may still
-            // contain it are evaluated directly; the first row past it restarts the state from a clean halo.
-            const int nflag = __syncthreads_count(addside && i < nr && (int64_t)ce - (int64_t)Wmax - 2 <= (int64_t)(excP1 - 1u));
-            if (nflag == 0) {
-                restart_at = c0;
-                need_restart = true;
-                continue;
-            }
-            nr = nflag;
-            Elast = sh.E[nr];
-        }
-        // request the next chunk's cursors now; they are consumed at the top of the next iteration
-        {
-            const int64_t nrow = c0 + nr + i;
-            pre_valid = true;
-            if (nrow < rb) {
-                pre_e = __ldg(kcur + nrow);
-                pre_j = __ldg(jcur + nrow);
-            }
-            // and pull the next chunk's ticks towards the L2
-            const int64_t pf = (int64_t)Elast + (int64_t)tid * 16;
-            if (tid < 96 && pf < sg.n_ticks) {
+            cur_e = ce;
+            cur_j = cj;
+            // pull the ticks of the chunk after that one towards the L2
+            const uint32_t pf = TFq + (uint32_t)CT + (uint32_t)ci * 16u;
+            if (ci * 16 < CT && pf < nTicks) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(mid + pf));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(spread + pf));
             }
+        };
+        uint32_t pre_e = 0, pre_j = 0;
+        if (ra + ci < rb) {
+            pre_e = __ldg(kcur + ra + ci);
+            pre_j = __ldg(jcur + ra + ci);
         }
-
-        // ------------------------------------------------------------------ row phase: per-row deltas
-        uint32_t e0 = 0, e1 = 0;
-        if (i < nr) { e0 = sh.E[i]; e1 = sh.E[i + 1]; }
-        const uint32_t E0 = sh.E[0];
-        double bAll = 0.0, bSgn = 0.0, b1 = 0.0, b2 = 0.0, bF = 0.0;
-        int bNeg = 0;
-        if (addside) {
-            // ticks that arrive: [e0, e1)
-            double sAll = 0.0, sSgn = 0.0, hh = 0.0, d1 = 0.0, d2 = 0.0;
-            uint32_t neg = 0, mov = 0, lm = 0;
-            {
-                uint32_t k0 = e0;
-                while (k0 < e1) {
-                    const uint32_t slot = k0 & mask;
-                    const uint32_t n = min(e1 - k0, (uint32_t)RING - slot);
-                    const uint32_t a0 = ring_base + slot * 8u, aend = a0 + n * 8u;
-                    uint32_t am = 0;
-#pragma unroll 1
-                    for (uint32_t a = a0; a < aend; a += 8u) {
-                        const double y = lds_f64(a), d = lds_f64_off<kD>(a);
-                        sAll += fabs(y);
-                        sSgn += y;
-                        hh = fma(hh, decay, fabs(y));
-                        neg += (uint32_t)__double2hiint(y) >> 31;
-                        if (((uint32_t)__double2hiint(y) << 1) != 0u) { ++mov; am = a; }  // r^2 of a move is normal: high word suffices
-                        d1 += d;
-                        d2 = fma(d, d, d2);
-                    }
-                    if (am != 0u) lm = k0 + ((am - a0) >> 3) + 1u;
-                    k0 += n;
-                }
+        make_plan(0, ra, baseK, baseJ, 0u, 0u, pre_e, pre_j);
+        uint32_t my_e = cur_e, my_j = cur_j;     // rows of chunk 0
+        {   // candidates of chunk 1 (needs plan 0)
+            bar_sync_n(2, kCons);
+            const long long c1 = sh.plan[0].c0 + sh.plan[0].nr;
+            pre_e = pre_j = 0;
+            if (c1 + ci < rb) {
+                pre_e = __ldg(kcur + c1 + ci);
+                pre_j = __ldg(jcur + c1 + ci);
             }
-            // ticks that leave the direction window: [q0, q1)
-            const uint32_t q0 = max(baseK, sub_floor0(e0, Wd)), q1 = max(baseK, sub_floor0(e1, Wd));
-            uint32_t qneg = 0, qmov = 0;
-            for_ring<RING>(ring_base, q0, q1, [&](uint32_t a) {
-                const uint32_t hi = lds_hi32(a);
-                qneg += hi >> 31;
-                // r^2 of a real move is far above 2^-1022: the high word alone tells zero from non-zero
-                if ((hi << 1) != 0u) ++qmov;
-            });
-            sh.A[0][i] = sAll;
-            sh.A[1][i] = sSgn;
-            sh.A[2][i] = d1;
-            sh.A[3][i] = d2;
-            sh.A[4][i] = (i < nr) ? P.ewm_alpha * hh * __ldg(P.ewm_ipow + (e1 - E0)) : 0.0;
-            sh.AI[0][i] = (int)neg;
-            sh.AI[1][i] = (int)(neg - qneg) + ((int)(mov - qmov) << 16);
-            sh.LM[i] = lm;
-        } else {
-            // trades first (independent of the ring): deltas of this row's trade window, read straight from global
-            int w0 = 0, w1 = 0;
-            if (i < nr) {
-                const uint32_t j0 = sh.J[i], j1 = sh.J[i + 1];
-                int dprev = j0 > baseJ ? (int)tdir[j0 - 1] : 0;  // the trade at the base (trade 0) closes no pair
-                for (uint32_t j = j0; j < j1; ++j) {
-                    const int d = tdir[j];
-                    w0 += (d > 0 ? 1 : 0) + (d < 0 ? 65536 : 0);
-                    w1 += ((d != 0 && d == -dprev) ? 1 : 0) + (d << 16);  // feature_processor.cpp:235
-                    dprev = d;
-                }
-                const uint32_t q0 = max(baseJ, sub_floor0(j0, Wd)), q1 = max(baseJ, sub_floor0(j1, Wd));
-                if (q1 > q0) {
-                    int d = tdir[q0];
-                    for (uint32_t j = q0; j < q1; ++j) {
-                        const int dn = tdir[j + 1];
-                        w0 -= (d > 0 ? 1 : 0) + (d < 0 ? 65536 : 0);
-                        w1 -= ((dn != 0 && dn == -d) ? 1 : 0) + (d << 16);  // the pair (j, j+1) leaves with trade j
-                        d = dn;
-                    }
-                }
+        }
+        __syncthreads();   // plan 0 is visible to everybody
+        RowGather gat;
+        gat.row = -1;
+        for (int q = 0;; ++q) {
+            const WinPlan& pl = sh.plan[q & 1];
+            if (pl.mode != PLAN_RUN) break;
+            const uint32_t TF = pl.TF, JF = pl.JF, TFp = pl.TFprev, JFp = pl.JFprev;
+            uint32_t slotTe = pl.slotT + (TF - TFp), slotJe = pl.slotJ + (JF - JFp);   // slots of the new frontiers
+            if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
+            if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
+            const int nr = pl.nr;
+            const long long c0 = pl.c0;
+            // ---- phase 1: the next chunk's plan first (its ticks then have a whole phase to arrive), then the previous chunk's rows
+            make_plan((q + 1) & 1, c0 + nr, TF, JF, slotTe, slotJe, pre_e, pre_j);
+            const uint32_t nxt_e = cur_e, nxt_j = cur_j;
+            if (gat.row >= 0) {
+                if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
+                else finish_tick_row(out, N, P, pivot, gat);
+                const uint32_t jb = sub_floor0(gat.je, Wd);
+                write_trade_row(out, N, gat.row, P.clog2c, P.inv_cnt, (int)(gat.je - jb), gat.pos, gat.neg, gat.rev, gat.isum);
+                gat.row = -1;
             }
-            sh.TD[0][i] = w0;
-            sh.TD[1][i] = w1;
-            // ticks that leave the mid window: [s0, s1)
-            const uint32_t s0 = max(baseK, sub_floor0(e0, Wm)), s1 = max(baseK, sub_floor0(e1, Wm));
-            double hE = 0.0;
-            uint32_t neg = 0;
-            for_ring<RING>(ring_base, s0, s1, [&](uint32_t a) {
-                const double y = lds_f64(a), d = lds_f64_off<kD>(a);
-                bAll += fabs(y);
-                bSgn += y;
-                hE = fma(hE, decay, fabs(y));
-                neg += (uint32_t)__double2hiint(y) >> 31;
-                b1 += d;
-                b2 = fma(d, d, b2);
-            });
-            bNeg = (int)neg;
-            if (s1 > s0) bF = P.ewm_alpha * hE * __ldg(P.ewm_pow + (e1 - s1)) * __ldg(P.ewm_ipow + (e1 - E0));
-        }
-        __syncthreads();
-        if (!addside) {
-            sh.A[0][i] -= bAll;
-            sh.A[1][i] -= bSgn;
-            sh.A[2][i] -= b1;
-            sh.A[3][i] -= b2;
-            sh.A[4][i] -= bF;
-            sh.AI[0][i] -= bNeg;
-        }
-        __syncthreads();
-
-        // ------------------------------------------------------------------ one warp per quantity: 128-wide scans
-        if (warp < 5) {
-            scan128(sh.A[warp], carry, lane);
-            if (warp == 4) carry *= __ldg(P.ewm_pow + (Elast - E0));  // F is relative to the chunk's first tick
-        } else if (warp == 5) {
-            scan128(sh.AI[0], carry_i0, lane);
-            scan128(sh.AI[1], carry_i1, lane);
-        } else if (warp == 6) {
-            scan128(sh.TD[0], carry_i0, lane);
-            scan128(sh.TD[1], carry_i1, lane);
-        } else {
-            scan128_max(sh.LM, carry_lm, lane);
-        }
-        __syncthreads();
-
-        // ------------------------------------------------------------------ finalise and write rows >= out_from
-        if (i < nr && row >= out_from) {
-            if (addside) {
-                const uint32_t e = e1;  // == the row's own cursor (clamping only affects halo rows)
-                const bool flagged = excP1 != 0u && excP1 - 1u >= baseK && (int64_t)e - (int64_t)Wmax - 2 <= (int64_t)(excP1 - 1u);
-                if (flagged) {
-                    direct_tick_row(mid, spread, e, dp, out.raw, out.counts, N, row);
-                } else {
-                    finish_tick_row(out, N, row, P, e, pivot, sh.A[0][i], sh.A[1][i], sh.A[2][i], sh.A[3][i],
-                                    sh.A[4][i] * __ldg(P.ewm_pow + (e - E0)), sh.AI[0][i], sh.AI[1][i], sh.LM[i],
-                                    lds_f64(ring_base + (sub_floor0(e, Wm) & mask) * 8u),
-                                    lds_f64(ring_base + ((sub_floor0(e, Wm) + 1u) & mask) * 8u));
+            __syncthreads();   // S1: the rings hold chunk q; plan q + 1 is visible
+            // ---- phase 2: gather this chunk's rows
+            if (ci < nr) {
+                const uint32_t e = my_e, je = my_j;
+                auto slot_of = [&](uint32_t p) {   // ring slot of tick position p <= TF
+                    int sl = (int)slotTe - (int)(TF - p);
+                    return sl < 0 ? sl + R : sl;
+                };
+                const uint32_t s = sub_floor0(e, Wm), d0 = sub_floor0(e, Wd);
+                const int se = slot_of(e), ss0 = slot_of(s), sd = slot_of(d0);
+                const int cnt = (int)(e - s) - 1;
+                const double Ae = QA[se], Se = QS[se], D1e = QD1[se], D2e = QD2[se];
+                const uint32_t Ce = QC[se], Cd = QC[sd];
+                gat.Ge = QG[se];
+                gat.D1 = D1e - QD1[ss0];
+                gat.D2 = D2e - QD2[ss0];
+                gat.SA = gat.SS = gat.Gs1 = gat.xf = 0.0;
+                gat.negs = gat.movm = 0;
+                if (cnt > 0) {
+                    int s1 = ss0 + 1, s2;
+                    if (s1 == R) s1 = 0;
+                    s2 = s1 + 1;
+                    if (s2 == R) s2 = 0;
+                    const double A1 = QA[s1];
+                    const uint32_t C1 = QC[s1];
+                    gat.SA = Ae - A1;
+                    gat.SS = Se - QS[s1];
+                    gat.Gs1 = QG[s1];
+                    gat.xf = QA[s2] - A1;
+                    gat.negs = (int)((Ce - C1) & 0xffffu);
+                    gat.movm = (int)(((Ce >> 16) - (C1 >> 16)) & 0xffffu);
                 }
-            } else {
-                const uint32_t je = sh.J[i + 1];
+                gat.negd = (int)((Ce - Cd) & 0xffffu);
+                gat.movd = (int)(((Ce >> 16) - (Cd >> 16)) & 0xffffu);
+                // trades: [jb, je), reversal pairs (i-1, i) for i in (jb, je)
                 const uint32_t jb = sub_floor0(je, Wd);
-                const int w0 = sh.TD[0][i], w1 = sh.TD[1][i];
-                const int pos = w0 & 0xffff, neg = (w0 >> 16) & 0xffff, rev = w1 & 0xffff;
-                const int isum = (w1 - rev) >> 16;
-                write_trade_row(out, N, row, P.clog2c, P.inv_cnt, (int)(je - jb), pos, neg, rev, isum);
+                auto tslot = [&](uint32_t p) {
+                    int sl = (int)slotJe - (int)(JF - p);
+                    return sl < 0 ? sl + RJ : sl;
+                };
+                const int tb = tslot(jb);
+                const unsigned long long Te = QT[tslot(je)], Tb = QT[tb];
+                gat.pos = (int)((uint32_t)(Te - Tb) & 0xffffu);
+                gat.neg = (int)((uint32_t)((Te >> 16) - (Tb >> 16)) & 0xffffu);
+                gat.isum = (int)(int16_t)(uint16_t)((Te >> 48) - (Tb >> 48));
+                gat.rev = 0;
+                if (je - jb >= 2u) {
+                    const unsigned long long T1 = QT[tb + 1 == RJ ? 0 : tb + 1];
+                    gat.rev = (int)((uint32_t)((Te >> 32) - (T1 >> 32)) & 0xffffu);
+                }
+                gat.e = e;
+                gat.je = je;
+                gat.row = c0 + ci;
+                const uint32_t exc = sh.excP1;
+                gat.flagged = exc != 0u && e <= exc + Wmax + 1u;   // the window (or the entry just before it) may hold a flagged tick
             }
+            // candidates of chunk q + 2
+            {
+                const WinPlan& pn = sh.plan[(q + 1) & 1];
+                const long long c2 = pn.c0 + pn.nr;
+                pre_e = pre_j = 0;
+                if (pn.mode == PLAN_RUN && c2 + ci < rb) {
+                    pre_e = __ldg(kcur + c2 + ci);
+                    pre_j = __ldg(jcur + c2 + ci);
+                }
+            }
+            my_e = nxt_e;
+            my_j = nxt_j;
+            __syncthreads();   // S0
         }
-        Eprev = Elast;
-        Jprev = sh.J[nr];
-        c0 += nr;
-        __syncthreads();
+        if (gat.row >= 0) {
+            if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
+            else finish_tick_row(out, N, P, pivot, gat);
+            const uint32_t jb = sub_floor0(gat.je, Wd);
+            write_trade_row(out, N, gat.row, P.clog2c, P.inv_cnt, (int)(gat.je - jb), gat.pos, gat.neg, gat.rev, gat.isum);
+        }
+    } else {
+        // ================================================================================ the trade warp: trades -> QT
+        unsigned long long cJ = 0ull;    // the counters at the trade frontier
+        __syncthreads();   // plan 0 is visible
+        for (int q = 0;; ++q) {
+            const WinPlan& pl = sh.plan[q & 1];
+            if (pl.mode != PLAN_RUN) break;
+            const uint32_t JFp = pl.JFprev, JF = pl.JF;
+            uint32_t slot0 = pl.slotJ;
+            if (JF > JFp) mbar_wait(&sh.full[q & 1], (uint32_t)((q >> 1) & 1));   // the chunk's trade directions have landed
+            const uint32_t t0 = JFp > baseJ ? JFp - 1u : baseJ;
+            const signed char* __restrict__ sb = reinterpret_cast<const signed char*>(sh.stgT[q & 1]) + pl.shT;   // sb[j - t0] = direction of trade j
+            for (uint32_t jp = JFp; jp < JF; jp += 32u * kTradeRun) {
+                const uint32_t j0 = jp + (uint32_t)(lane * kTradeRun);
+                int dprev = (j0 > baseJ && j0 < JF) ? (int)sb[j0 - 1u - t0] : 0;   // the trade at the base (trade 0) closes no pair
+                int dv[kTradeRun];
+#pragma unroll
+                for (int i = 0; i < kTradeRun; ++i) dv[i] = j0 + (uint32_t)i < JF ? (int)sb[j0 + (uint32_t)i - t0] : 0;
+                unsigned long long c[kTradeRun], t = 0ull;
+#pragma unroll
+                for (int i = 0; i < kTradeRun; ++i) {
+                    const int d = dv[i];
+                    // fields: pos | neg << 16 | reversal << 32 | dir << 48 (feature_processor.cpp:235, :242-245, :255-259); within a pass
+                    // no field but the top one can carry
+                    t += (unsigned long long)(d > 0 ? 1 : 0) + ((unsigned long long)(d < 0 ? 1 : 0) << 16) +
+                         ((unsigned long long)((d != 0 && d == -dprev) ? 1 : 0) << 32) + ((unsigned long long)(long long)d << 48);
+                    dprev = d;
+                    c[i] = t;
+                }
+                unsigned long long v = t;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const unsigned long long uv = shfl_up_u64(v, 1 << k);
+                    if (lane >= (1 << k)) v += uv;
+                }
+                unsigned long long ex = shfl_up_u64(v, 1);
+                if (lane == 0) ex = 0ull;
+                const unsigned long long base = add4x16(cJ, ex);
+                uint32_t slot = slot0 + (uint32_t)(lane * kTradeRun) + 1u;
+                if (slot >= (uint32_t)RJ) slot -= (uint32_t)RJ;
+#pragma unroll
+                for (int i = 0; i < kTradeRun; ++i) {
+                    if (j0 + (uint32_t)i < JF) {
+                        QT[slot] = add4x16(base, c[i]);
+                        if (++slot == (uint32_t)RJ) slot = 0u;
+                    }
+                }
+                cJ = add4x16(cJ, __shfl_sync(0xffffffffu, v, 31));
+                slot0 += 32u * kTradeRun;
+                if (slot0 >= (uint32_t)RJ) slot0 -= (uint32_t)RJ;
+            }
+            __syncthreads();   // S1
+            __syncthreads();   // S0
+        }
     }
 }
 
-size_t win_smem_bytes(int ring) { return (size_t)ring * 16u; }
+// ring geometry for given windows: the tick ring holds one window + one chunk, likewise the trade ring; everything must fit
+// the 227 KB a CTA can opt into.  Returns false when the windows are too long for the on-chip rings.
+bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, int* trade_ring, int* chunk_trades, size_t* smem) {
+    const int wmax = mid_window > dir_window + 1 ? mid_window : dir_window + 1;
+    const size_t budget = 232448 - 1024;   // static shared memory (plans, warp totals) and slack
+    int cj = 1024;
+    int rj = ((dir_window + 2 + cj + 8 + 1) / 2) * 2;
+    for (int ct = kProd * kRun; ct >= 40 * kRun; ct -= 10 * kRun) {   // multiples of 10: even (16-byte staging rows) and whole thread runs
+        const int r = ((wmax + 2 + ct + 8 + 1) / 2) * 2;
+        const size_t bytes = (size_t)r * 44 + (size_t)4 * (ct + 4) * 8 + (size_t)rj * 8;
+        if (bytes <= budget) {
+            *ring = r;
+            *chunk_ticks = ct;
+            *trade_ring = rj;
+            *chunk_trades = cj;
+            *smem = bytes;
+            return true;
+        }
+    }
+    return false;
+}
 
 cudaError_t launch_windows(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg, const DevParams& P,
                            cudaStream_t st) {
-    const size_t smem = win_smem_bytes(P.win_ring);
-    auto go = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)P.win_ring * 44 + (size_t)4 * (P.win_chunk_ticks + 4) * 8 + (size_t)P.win_trade_ring * 8;
+    static int ready_for[64];   // the opt-in is per device (idempotent; a race only repeats the call)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (ready_for[dev & 63] < (int)smem) {
+        e = cudaFuncSetAttribute(k_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<nseg, kWinThreads, smem, st>>>(in, out, segs, P);
-        return cudaGetLastError();
-    };
-    if (P.win_ring == 4096) return go(k_windows<4096>);
-    if (P.win_ring == 8192) return go(k_windows<8192>);
-    return cudaErrorInvalidValue;
+        ready_for[dev & 63] = (int)smem;
+    }
+    k_windows<<<nseg, kWinThreads, smem, st>>>(in, out, segs, P);
+    return cudaGetLastError();
 }
 
 }  // namespace mrp

@@ -70,16 +70,17 @@ struct DevParams {
     double stress_alpha, stress_decay, stress_min_size, stress_distance_decay;
     const double* ofi_weight;   // [L]  exp(-i*depth_decay), computed by the host libm
     const double* ewm_pow;      // [win_ring+1]    decay^n
-    const double* ewm_ipow;     // [win_ring+1]    decay^-n (n <= win_span_max keeps it far from overflow)
     const double* ofi_pow;      // [257]           ofi_decay^n
     double ofi_pw2[6], stress_pw2[6];  // decay^(1,2,4,8,16,32) again, as kernel-parameter constants (the scan steps)
     const double* stress_pow;   // [257]           stress_decay^n
     const double* inv_cnt_norm; // [norm_window+1] 1/n, [0] = 0
     const double* clog2c;       // [max(dir_window, mid_window)+2]  c*log2(c), [0] = 0
     const double* inv_cnt;      // [max(mid_window, dir_window)+2]  1/n, [0] = 0
-    // window kernel: shared-memory ring entries (power of two) and the most new ticks one chunk may bring
-    int32_t win_ring, win_span_max;
-    int32_t win_pipeline;       // 1: producer / consumer chunk pipeline for clean data (kernels_window.cu)
+    // the window constants of the steady state (full windows), so that the common row needs no table look-up
+    double inv_ret_full, pow_ret_full;      // 1/(mid_window-1), decay^(mid_window-1)
+    double inv_dir_full, clog2c_dir_full;   // 1/dir_window, dir_window*log2(dir_window)
+    // window kernel: entries of the tick / trade prefix rings and the most new ticks / trades one chunk may bring
+    int32_t win_ring, win_chunk_ticks, win_trade_ring, win_chunk_trades;
     int32_t ema_warm_rows;      // halo rows that warm the two row-axis EMAs
     int32_t tile_rows;          // normaliser tile (divides norm_window, or == norm_window)
     int32_t tiles_back;         // norm_window / tile_rows

@@ -57,13 +57,9 @@ void GpuFeatureProcessor::stage(const FeatureInputSnapshot& s, std::uint64_t gri
 FeatureSet GpuFeatureProcessor::GetRawFeatureSet(const FeatureInputSnapshot& snapshot) {
     stage(snapshot, snapshot.timestamp_ns);
     const std::int64_t t = (std::int64_t)ts_.size() - 1;
-    // rows that can still influence row t: its z-score window, the EMA warm-up of the window's first row (both EMAs have
-    // forgotten their start to < 1e-17 after `warm` rows), the lag-21 midprice and the previous row of the book deltas
-    const double slow = std::max(1.0 - params_.ofi_alpha, 1.0 - params_.stress_alpha);
-    std::int64_t warm = slow > 0.0 && slow < 1.0 ? (std::int64_t)std::ceil(std::log(1e-17) / std::log(slow)) : 0;
-    warm = std::max<std::int64_t>(warm, params_.return_lag + 1);
-    warm = ((warm + 255) / 256) * 256;
-    const std::int64_t H = (std::int64_t)params_.norm_window + warm + 32;
+    // rows that can still influence row t: its z-score window, the EMA warm-up of the window's first row, the lag-21 midprice
+    // and the previous row of the book deltas — the engine's own rule (mrp_fg_halo_rows_for)
+    const std::int64_t H = mrp_fg_halo_rows_for(&params_);
     const std::int64_t a = std::max<std::int64_t>(0, t - H);
     const std::int64_t n = t - a + 1;
     // ticks / trades those rows can see

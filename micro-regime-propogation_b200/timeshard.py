@@ -5,7 +5,7 @@ of the feature path has finite memory (30 000 rows for the z-scor
 1 row for the book-delta directions and the arrival rate, 1800 ticks, 1500 trades, EMAs that forget to < 1e-17 in 372 rows),
 so a rank reproduces its rows exactly from its own slice plus a HALO taken from its left neighbour:
 
-    rows   : the last  H = norm_window + ema_warm + 32  rows of the neighbour (inputs, not features: recomputing the
+    rows   : the last  H = mrp_fg_halo_rows() = norm_window + EMA warm-up + 32  rows of the neighbour (inputs, not features: recomputing the
              neighbour's last 30 000 raw feature rows costs 0.06 % extra work at 50 M rows per GPU and needs no second
              exchange step and no extra kernel entry point)
     ticks  : from (tick cursor of the halo's first row) - max(mid_window, dir_window + 1) - 2
@@ -29,15 +29,12 @@ TICK_KEYS = ("mid", "spread")
 TRADE_KEYS = ("trade_dir",)
 
 
-def ema_warm_rows(ofi_alpha: float = 0.2, stress_alpha: float = 0.1, return_lag: int = 20) -> int:
-    """Rows after which both EMAs have forgotten their start (decay^rows < 1e-17), as the kernels size their own halo."""
-    slow = max(1.0 - ofi_alpha, 1.0 - stress_alpha)
-    warm = max(int(math.ceil(math.log(1e-17) / math.log(slow))), return_lag + 1)
-    return ((warm + 255) // 256) * 256
+def halo_rows(norm_window: int = 30000, params=None) -> int:
+    """Rows of history a shard needs from its left neighbour: the engine's own rule (mrp_fg_halo_rows_for — the ONE definition)."""
+    from . import cabi
 
-
-def halo_rows(norm_window: int = 30000, ofi_alpha: float = 0.2, stress_alpha: float = 0.1, return_lag: int = 20) -> int:
-    return norm_window + ema_warm_rows(ofi_alpha, stress_alpha, return_lag) + 32
+    p = params or cabi.default_params(norm_window=norm_window)
+    return cabi.halo_rows(p)
 
 
 def shard_bounds(n_rows: int, world: int, rank: int):

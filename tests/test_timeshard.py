@@ -103,8 +103,9 @@ def test_two_rank_time_shards_reproduce_the_whole_stream(variable):
 
 
 def test_halo_geometry():
-    assert timeshard.ema_warm_rows() == 512                 # 0.9^372 < 1e-17, rounded up to whole 256-row chunks
-    assert timeshard.halo_rows() == 30000 + 512 + 32
+    # 0.9^372 < 1e-17, rounded up to whole 384-row chunks of the book pass: the engine's rule, one definition for every caller
+    assert timeshard.halo_rows() == mrp_b200.halo_rows() == 30000 + 384 + 32
+    assert timeshard.halo_rows(2000) == mrp_b200.halo_rows(mrp_b200.default_params(norm_window=2000)) == 2000 + 384 + 32
     assert [timeshard.shard_bounds(10, 3, r) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
     full = synth.make_batch([synth.SynthSpec(n_rows=600, seed=3)])
     sh = timeshard.shard_of(full, 200, 400)
