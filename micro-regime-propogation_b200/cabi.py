@@ -119,7 +119,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("MRP_FG_LIB") or LIB_PATH   # MRP_FG_LIB: an experiment build of the same ABI
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: the CUDA extension is not built (run `python -c 'import __graft_entry__ as g; g.build()'`). "

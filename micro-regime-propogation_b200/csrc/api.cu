@@ -244,6 +244,8 @@ int setup_params(mrp_fg_ctx* c) {
     for (int i = 0; i < p.depth_levels; ++i) tab.push_back(std::exp(-i * p.ofi_depth_decay));  // feature_processor.cpp:121
     const size_t o_e = tab.size();
     for (int n = 0; n <= d.win_ring; ++n) tab.push_back((double)powl((long double)d.ewm_decay, (long double)n));
+    const size_t o_ei = tab.size();
+    for (int n = 0; n <= 512; ++n) tab.push_back((double)powl((long double)d.ewm_decay, -(long double)n));
     const size_t o_o = tab.size();
     for (int n = 0; n <= 256; ++n) tab.push_back((double)powl((long double)d.ofi_decay, (long double)n));
     for (int k = 0; k < 6; ++k) {
@@ -267,6 +269,7 @@ int setup_params(mrp_fg_ctx* c) {
     const double* t = static_cast<const double*>(c->b_tables.p);
     d.ofi_weight = t + o_w;
     d.ewm_pow = t + o_e;
+    d.ewm_ipow = t + o_ei;
     d.ofi_pow = t + o_o;
     d.stress_pow = t + o_s;
     d.inv_cnt_norm = t + o_i;

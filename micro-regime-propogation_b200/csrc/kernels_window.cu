@@ -40,11 +40,17 @@
 
 namespace mrp {
 
-constexpr int kProdWarps = 4, kConsWarps = 4;
+#ifndef MRP_WIN_PROD_WARPS
+#define MRP_WIN_PROD_WARPS 4
+#endif
+#ifndef MRP_WIN_RUN
+#define MRP_WIN_RUN 11
+#endif
+constexpr int kProdWarps = MRP_WIN_PROD_WARPS, kConsWarps = 4;
 constexpr int kProd = kProdWarps * 32;             // producer threads
 constexpr int kCons = kConsWarps * 32;             // consumer threads == most rows of one chunk
 constexpr int kWinThreads = kProd + kCons + 32;    // + the trade warp
-constexpr int kRun = 11;                           // consecutive ticks per producer thread (odd: conflict-free 64-bit shared accesses); long
+constexpr int kRun = MRP_WIN_RUN;                  // consecutive ticks per producer thread (odd: conflict-free 64-bit shared accesses); long
                                                    // runs keep the per-thread scan overhead (~300 instructions) small next to the tick arithmetic
 constexpr int kTradeRun = 8;                       // consecutive trades per lane of the trade warp
 constexpr int kTradeStage = 1024 + 32;             // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
@@ -155,22 +161,23 @@ __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, con
     write_tick_row(o, N, r, o_ewm, o_rv, o_dv, o_sv, ent, count, up_count, up, down, (int)(e - d0));
 }
 
-// a / n for a count n inside the host's 1/n table: reciprocal, product, ONE correction step (the quotient's remainder is
-// exact in an fma) — the correctly rounded quotient for the small integers that meet here, for 4 instructions and a load
-__device__ __forceinline__ double div_by_count(double a, int n, const double* __restrict__ inv_cnt) {
-    const double b = (double)n, r = __ldg(inv_cnt + n);
+// a / n for a positive count n: reciprocal, product, ONE correction step (the quotient's remainder is exact in an fma) — the
+// correctly rounded quotient for the small integers that meet here, without a division and without a table
+__device__ __forceinline__ double div_by_count(double a, int n) {
+    const double b = (double)n, r = rcp_pos(b);
     const double q = a * r;
     return fma(fma(-q, b, a), r, q);
 }
 
 // trade-axis features of one snapshot from its window counts (feature_processor.cpp:231-247, :254-269)
-__device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N, int64_t r, const double* __restrict__ clog2c,
-                                                const double* __restrict__ inv_cnt, int nd, int pos, int neg, int rev, int isum) {
+// clog2c: the host's c*log2(c) table, copied to shared memory
+__device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N, int64_t r, const double* __restrict__ clog2c, int nd, int pos,
+                                                int neg, int rev, int isum) {
     const int tot = pos + neg;                                  // :261-269
-    const double rr = nd > 1 ? div_by_count((double)rev, nd, inv_cnt) : 0.0;                                   // :239 — divides by size, not size-1
-    const double ab = nd > 0 ? div_by_count((double)isum, nd, inv_cnt) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
-    // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T with c*log2(c) tabulated by the host
-    const double ent = tot > 0 ? div_by_count((__ldg(clog2c + tot) - __ldg(clog2c + pos)) - __ldg(clog2c + neg), tot, inv_cnt) : 0.0;
+    const double rr = nd > 1 ? div_by_count((double)rev, nd) : 0.0;                                   // :239 — divides by size, not size-1
+    const double ab = nd > 0 ? div_by_count((double)isum, nd) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
+    // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T
+    const double ent = tot > 0 ? div_by_count((clog2c[tot] - clog2c[pos]) - clog2c[neg], tot) : 0.0;
     out.raw[(int64_t)MRP_F_REVERSAL_RATE * N + r] = rr;
     out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * N + r] = ab;
     out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + r] = ent;
@@ -198,8 +205,8 @@ struct RowGather {
 };
 
 // One snapshot's five tick-axis features from its window values (see the file header).
-__device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int64_t N, const DevParams& P, const double pivot,
-                                                const RowGather& g) {
+__device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int64_t N, const DevParams& P, const double* __restrict__ clog2c,
+                                                const double pivot, const RowGather& g) {
     double ewm = 0.0, rv = 0.0, dv = 0.0, sv = 0.0, tent = 0.0;
     int cnt = 0, nUp = 0, t_up = 0, t_dn = 0, t_tot = 0;
     const uint32_t e = g.e;
@@ -213,7 +220,7 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
             const bool moved = g.movm > 0;
             const double tot = (g.SA > 0.0 && moved) ? g.SA : 0.0;
             const bool full = cnt == P.mid_window - 1;   // the steady state: the window's constants sit in the kernel parameters
-            rv = tot * (full ? P.inv_ret_full : __ldg(P.inv_cnt + cnt));  // feature_processor.cpp:61 (tabulated 1/count)
+            rv = tot * (full ? P.inv_ret_full : rcp_pos((double)cnt));  // feature_processor.cpp:61
             double w = 0.0;
             if (tot != 0.0) {
                 // :64-79: sum_{i>=1} alpha decay^(cnt-i) x_i + decay^cnt x_1  (the restart takes x_1 with weight decay^(cnt-1))
@@ -225,8 +232,8 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
             double sumU = 0.5 * (g.SA + g.SS), sumD = 0.5 * (g.SA - g.SS);
             if (!(sumU > 0.0) || !moved) sumU = 0.0;
             if (!(sumD > 0.0) || !moved) sumD = 0.0;
-            const double au = sumU * __ldg(P.inv_cnt + nUp);          // :95-98 (inv_cnt[0] = 0: empty side)
-            const double ad = sumD * __ldg(P.inv_cnt + (cnt - nUp));
+            const double au = nUp > 0 ? sumU * rcp_pos((double)nUp) : 0.0;          // :95-98 (an empty side counts 0)
+            const double ad = cnt > nUp ? sumD * rcp_pos((double)(cnt - nUp)) : 0.0;
             const double diff = au - ad;
             dv = sqrt(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
         }
@@ -245,8 +252,8 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
         const int zero = t_tot - g.movd;
         // :222-229: -sum p log2 p = (T log2 T - sum c log2 c) / T, c*log2(c) tabulated by the host
         const bool dfull = t_tot == P.dir_window;
-        tent = (((dfull ? P.clog2c_dir_full : __ldg(P.clog2c + t_tot)) - __ldg(P.clog2c + t_up)) - __ldg(P.clog2c + t_dn) - __ldg(P.clog2c + zero)) *
-               (dfull ? P.inv_dir_full : __ldg(P.inv_cnt + t_tot));
+        tent = (((dfull ? P.clog2c_dir_full : clog2c[t_tot]) - clog2c[t_up]) - clog2c[t_dn] - clog2c[zero]) *
+               (dfull ? P.inv_dir_full : rcp_pos((double)t_tot));
         if (cnt < 0) cnt = 0;
     }
     write_tick_row(out, N, g.row, ewm, rv, dv, sv, tent, cnt, nUp, t_up, t_dn, t_tot);
@@ -269,7 +276,7 @@ struct __align__(16) WinPlan {
     int nr, mode;              // rows finalised by this chunk (0: the rings only advance)
 };
 struct __align__(16) WinStatic {
-    WinPlan plan[2];
+    WinPlan plan[4];                   // chunk q lives in slot q & 3: planned in iteration q - 1, produced in q, gathered in q + 1
     uint64_t full[2];                  // mbarriers of the two staging buffers
     double wt[kProdWarps][6];          // per-warp totals: x, +-x, d, d^2, EMA, counts (bit pattern)
     __align__(16) unsigned char stgT[2][kTradeStage];   // staged trade directions of the chunk (position JFprev - 1 onwards)
@@ -277,6 +284,9 @@ struct __align__(16) WinStatic {
     uint32_t excP1;                    // 1 + position of the last flagged tick (0 = none)
     int cnt[kConsWarps];
 };
+// named barriers: 1 the producers (cross-warp scan), 2 the consumers (plan), 3 "the previous chunk has been gathered":
+// the consumers arrive, the producers and the trade warp wait before they overwrite ring entries
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __global__ void __launch_bounds__(kWinThreads, 1)
 k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
@@ -291,7 +301,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
     double* __restrict__ stgM = QG + R;            // [2][CTS]
     double* __restrict__ stgS = stgM + 2 * CTS;    // [2][CTS]
     unsigned long long* __restrict__ QT = reinterpret_cast<unsigned long long*>(stgS + 2 * CTS);   // [RJ]
-    uint32_t* __restrict__ QC = reinterpret_cast<uint32_t*>(QT + RJ);                                // [R]
+    double* __restrict__ sLog = reinterpret_cast<double*>(QT + RJ);                                 // [dir_window + 2]  c*log2(c), from the host
+    uint32_t* __restrict__ QC = reinterpret_cast<uint32_t*>(sLog + P.dir_window + 2);                // [R]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevSegment sg = segs[blockIdx.x];
@@ -314,6 +325,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         const double s0 = __ldg(spread + baseK);
         if (fabs(s0) <= 1e150) pivot = s0;
     }
+    for (int i = tid; i < P.dir_window + 2; i += kWinThreads) sLog[i] = __ldg(P.clog2c + i);   // window counts never exceed dir_window
     if (tid == 0) {
         sh.excP1 = 0u;
         sh.carryG = 0.0;
@@ -337,9 +349,10 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         const double plane = __ldg(P.ewm_pow + kRun * lane), pwarp = __ldg(P.ewm_pow + kRun * 32);
         __syncthreads();   // plan 0 is visible
         for (int q = 0;; ++q) {
-            const WinPlan& pl = sh.plan[q & 1];
+            const WinPlan& pl = sh.plan[q & 3];
             if (pl.mode != PLAN_RUN) break;
             const uint32_t TFp = pl.TFprev, TF = pl.TF;
+            cG = sh.carryG;   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
             mbar_wait(&sh.full[q & 1], (uint32_t)((q >> 1) & 1));
             if (TF > TFp) {
                 const double* __restrict__ sm = stgM + (q & 1) * CTS + pl.shM;
@@ -347,29 +360,29 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 const uint32_t k0 = TFp + (uint32_t)(kRun * tid);
                 const int i0 = (int)(k0 - pl.stg0);
                 const int nv = k0 < TF ? (int)min(TF - k0, (uint32_t)kRun) : 0;   // valid ticks of this thread
-                // mids m[0] = M_{k0-1}, m[1..11] = M_{k0..k0+10}; d = spread - pivot
+                const bool has_prev = k0 > pl.stg0;
+                // mids m[0] = M_{k0-1}, m[1..11] = M_{k0..k0+10}; d = spread - pivot.  One path for whole and partial runs: every
+                // element is loaded — the staging rows are CT + 4 long, a stale element is never used — then ticks past the frontier
+                // repeat their predecessor (flat, no contribution) with d = 0.
                 double m[kRun + 1], d[kRun];
-                if (nv == kRun && k0 > pl.stg0) {
-#pragma unroll
-                    for (int i = 0; i <= kRun; ++i) m[i] = sm[i0 - 1 + i];
-#pragma unroll
-                    for (int i = 0; i < kRun; ++i) d[i] = ss[i0 + i] - pivot;
-                } else {   // a partial run (the chunk's last thread), no run at all, or the tick at the base (no predecessor: flat)
+                {
+                    const int ib = nv > 0 ? i0 : 1;          // threads without a run read the buffer's head
 #pragma unroll
                     for (int i = 0; i < kRun; ++i) {
-                        m[i + 1] = i < nv ? sm[i0 + i] : 0.0;
-                        d[i] = i < nv ? ss[i0 + i] - pivot : 0.0;
+                        m[i + 1] = sm[ib + i];
+                        d[i] = ss[ib + i] - pivot;
                     }
-                    m[0] = (nv > 0 && k0 > pl.stg0) ? sm[i0 - 1] : m[1];
-                    if (nv == 0) m[0] = m[1] = 1.0;
+                    m[0] = sm[ib - 1];
+                    if (nv == 0) m[1] = 1.0;
+                    if (!(nv > 0 && has_prev)) m[0] = m[1];   // the tick at the base has no predecessor: flat
 #pragma unroll
                     for (int i = 0; i < kRun; ++i)
-                        if (i >= nv) m[i + 1] = m[i];   // ticks past the frontier repeat their predecessor: flat, no contribution
+                        if (i >= nv) { m[i + 1] = m[i]; d[i] = 0.0; }
                 }
                 // one reciprocal per two returns: log(M_k / M_{k-1}) = -log1p((M_{k-1} - M_k) / M_k) = log1p((M_k - M_{k-1}) / M_{k-1});
                 // x = +-r^2, the sign set unless the midprice rose (-0.0 for a flat tick)
                 double x[kRun];
-                uint32_t umax = 0u, dmax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
+                uint32_t umax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
 #pragma unroll
                 for (int j = 0; j < (kRun + 1) / 2; ++j) {
                     const double rc = rcp_pos(m[2 * j + 1]);
@@ -381,26 +394,18 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                             const double u = h == 0 ? (m[i] - m[i + 1]) * rc : (m[i + 1] - m[i]) * rc;   // h == 0: rose <=> u < 0
                             const double r = log1p_small(u);
                             const double xx = r * r;
-                            const uint32_t uh = (uint32_t)__double2hiint(u);
-                            umax = max(umax, uh & 0x7fffffffu);
-                            dmax = max(dmax, (uint32_t)__double2hiint(d[i]) & 0x7fffffffu);
-                            const bool mv = u != 0.0;
-                            const bool up = h == 0 ? u < 0.0 : u > 0.0;
-                            nneg += up ? 0u : 1u;
-                            nmov += mv ? 1u : 0u;
-                            x[i] = up ? xx : -xx;
+                            const uint32_t uh = (uint32_t)__double2hiint(u), um = uh & 0x7fffffffu;
+                            umax = max(umax, um);
+                            // a real move is a normal number: its high word alone tells it from zero
+                            const uint32_t mv = um != 0u ? 1u : 0u;
+                            const uint32_t up = h == 0 ? (uh >> 31) : (mv & ~(uh >> 31));
+                            nneg += 1u - up;
+                            nmov += mv;
+                            x[i] = __hiloint2double((int)((uint32_t)__double2hiint(xx) | ((1u - up) << 31)), __double2loint(xx));
                         }
                     }
                 }
                 nneg -= (uint32_t)(kRun - nv);   // the padding ticks of a partial run are flat: they counted as "did not rise"
-                // flagged: a midprice that is not a positive normal number (its reciprocal is negative, or the returns round it are huge / NaN),
-                // a move beyond the series range, a spread that is not finite (or absurd)
-                if (!(umax < 0x3f500000u && dmax < 0x5f138d35u && (rsign >> 31) == 0u)) {
-                    if (nv > 0) atomicMax(&sh.excP1, k0 + (uint32_t)nv);
-#pragma unroll
-                    for (int i = 0; i < kRun; ++i) { x[i] = 0.0; d[i] = 0.0; }
-                    nneg = nmov = 0u;
-                }
                 // thread totals
                 double va = 0.0, vs = 0.0, v1 = 0.0, v2 = 0.0, vg = 0.0;
 #pragma unroll
@@ -411,6 +416,15 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     v1 += d[i];
                     v2 = fma(d[i], d[i], v2);
                     vg = fma(decay, vg, alpha * ax);
+                }
+                // flagged: a midprice that is not a positive normal number (its reciprocal is negative, or the returns round it are huge / NaN),
+                // a move beyond the series range, a spread that is not finite or absurd (its square leaves the range)
+                if (!(umax < 0x3f500000u && (rsign >> 31) == 0u && v2 < 1e300)) {
+                    if (nv > 0) atomicMax(&sh.excP1, k0 + (uint32_t)nv);
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) { x[i] = 0.0; d[i] = 0.0; }
+                    nneg = nmov = 0u;
+                    va = vs = v1 = v2 = vg = 0.0;
                 }
                 uint32_t vc = nneg | (nmov << 16);
                 // warp scans of the thread totals (inclusive), the EMA as a scan of y -> decay^11 y + b
@@ -461,10 +475,12 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 cD1 = __shfl_sync(0xffffffffu, acc_d, 2);
                 cD2 = __shfl_sync(0xffffffffu, acc_d, 3);
                 cC = (unsigned long long)__shfl_sync(0xffffffffu, acc_i, 5);
+                // the consumers have lifted the previous chunk's values out of the rings: its far-end entries may be overwritten
+                bar_sync_n(3, kWinThreads);
                 // into the rings: the prefix AFTER tick k lives at position k + 1.  The running sums continue from the offsets.
                 uint32_t slot = pl.slotT + (uint32_t)(kRun * tid) + 1u;
                 if (slot >= (uint32_t)R) slot -= (uint32_t)R;
-                if (nv == kRun && slot + (uint32_t)kRun <= (uint32_t)R) {
+                if (slot + (uint32_t)kRun <= (uint32_t)R) {   // no wrap inside the run (all but one thread in ~300): immediate offsets
                     double* __restrict__ pA = QA + slot;
                     double* __restrict__ pS = QS + slot;
                     double* __restrict__ p1 = QD1 + slot;
@@ -481,11 +497,13 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                         gG = fma(decay, gG, alpha * ax);
                         gNeg += (uint32_t)__double2hiint(x[i]) >> 31;
                         gMov += ax != 0.0 ? 1u : 0u;
-                        pA[i] = gA; pS[i] = gS; p1[i] = g1; p2[i] = g2; pG[i] = gG;
-                        pC[i] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
+                        if (i < nv) {
+                            pA[i] = gA; pS[i] = gS; p1[i] = g1; p2[i] = g2; pG[i] = gG;
+                            pC[i] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
+                            if (k0 + (uint32_t)i + 1u == TF) sh.carryG = gG;
+                        }
                     }
-                    if (k0 + (uint32_t)kRun == TF) sh.carryG = gG;
-                } else if (nv > 0) {
+                } else {
 #pragma unroll
                     for (int i = 0; i < kRun; ++i) {
                         if (i < nv) {
@@ -499,18 +517,18 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                             gMov += ax != 0.0 ? 1u : 0u;
                             QA[slot] = gA; QS[slot] = gS; QD1[slot] = g1; QD2[slot] = g2; QG[slot] = gG;
                             QC[slot] = (gNeg & 0xffffu) | (gMov << 16);
+                            if (k0 + (uint32_t)i + 1u == TF) sh.carryG = gG;
                             if (++slot == (uint32_t)R) slot = 0u;
                         }
                     }
-                    if (k0 + (uint32_t)nv == TF) sh.carryG = gG;
                 }
+            } else {
+                bar_sync_n(3, kWinThreads);
             }
-            __syncthreads();   // S1: the rings hold the chunk
-            if (TF > TFp) cG = sh.carryG;
-            __syncthreads();   // S0: the consumers have gathered
+            __syncthreads();   // the rings hold chunk q; plan q + 1 is visible
         }
     } else if (warp < kProdWarps + kConsWarps) {
-        // ================================================================================ consumers: plan, finalise, gather
+        // ================================================================================ consumers: plan, gather, finalise
         const int ci = tid - kProd, cw = warp - kProdWarps;
         DirectParams dpm;
         dpm.mid_window = Wm;
@@ -518,9 +536,10 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         dpm.spread_divisor = P.spread_divisor;
         dpm.ewm_alpha = P.ewm_alpha;
         dpm.ewm_decay = P.ewm_decay;
-        uint32_t cur_e = 0, cur_j = 0;   // this thread's row of the chunk about to be gathered
-        // plan the chunk that follows (TFq, JFq) and starts at row c0n, from this thread's candidate cursors; request its ticks
-        auto make_plan = [&](const int slot_idx, const long long c0n, const uint32_t TFq, const uint32_t JFq, const uint32_t slotT,
+        uint32_t cur_e = 0, cur_j = 0;   // this thread's candidate row of the chunk just planned
+        int plan_nr = 0;
+        // plan the chunk that follows (TFq, JFq) and starts at row c0n, from this thread's candidate cursors; request its ticks / trades
+        auto make_plan = [&](const int q_new, const long long c0n, const uint32_t TFq, const uint32_t JFq, const uint32_t slotT,
                              const uint32_t slotJ, const uint32_t pe, const uint32_t pj) {
             const long long row = c0n + ci;
             const bool inr = row < rb;
@@ -530,8 +549,10 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             if (lane == 0) sh.cnt[cw] = __popc(bal);
             bar_sync_n(2, kCons);
             const int nr = sh.cnt[0] + sh.cnt[1] + sh.cnt[2] + sh.cnt[3];
+            plan_nr = nr;
             if (ci == (nr > 0 ? nr - 1 : 0)) {
-                WinPlan& np = sh.plan[slot_idx];
+                WinPlan& np = sh.plan[q_new & 3];
+                const int sbuf = q_new & 1;
                 const bool end = c0n >= rb;
                 uint32_t TFn = TFq, JFn = JFq;
                 if (!end) {
@@ -550,7 +571,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 const uint32_t s0 = TFq > baseK ? TFq - 1u : baseK;
                 np.stg0 = s0;
                 np.shM = np.shS = np.shT = 0;
-                uint64_t* bar = &sh.full[slot_idx];
+                uint64_t* bar = &sh.full[sbuf];
                 // what the copy engine stages for the chunk: mids and spreads from the tick before the frontier, trade directions from
                 // the trade before the frontier; 16-byte rounding on both ends, the element shifts are published with the plan
                 uintptr_t qm = 0, qs = 0, qt = 0;
@@ -573,13 +594,13 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     np.shT = (int)(at - qt);
                 }
                 if (bm + bt != 0u) {
-                    fence_proxy_async_smem();   // the readers of this buffer (two barriers ago) precede the engine's writes
+                    fence_proxy_async_smem();   // the readers of this buffer (a chunk barrier ago) precede the engine's writes
                     mbar_expect_tx(bar, bm + bs + bt);
                     if (bm) {
-                        bulk_g2s(stgM + slot_idx * CTS, reinterpret_cast<const void*>(qm), bm, bar);
-                        bulk_g2s(stgS + slot_idx * CTS, reinterpret_cast<const void*>(qs), bs, bar);
+                        bulk_g2s(stgM + sbuf * CTS, reinterpret_cast<const void*>(qm), bm, bar);
+                        bulk_g2s(stgS + sbuf * CTS, reinterpret_cast<const void*>(qs), bs, bar);
                     }
-                    if (bt) bulk_g2s(sh.stgT[slot_idx], reinterpret_cast<const void*>(qt), bt, bar);
+                    if (bt) bulk_g2s(sh.stgT[sbuf], reinterpret_cast<const void*>(qt), bt, bar);
                 } else {
                     mbar_arrive(bar);           // nothing to stage: the phase completes at once
                 }
@@ -593,48 +614,15 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(spread + pf));
             }
         };
-        uint32_t pre_e = 0, pre_j = 0;
-        if (ra + ci < rb) {
-            pre_e = __ldg(kcur + ra + ci);
-            pre_j = __ldg(jcur + ra + ci);
-        }
-        make_plan(0, ra, baseK, baseJ, 0u, 0u, pre_e, pre_j);
-        uint32_t my_e = cur_e, my_j = cur_j;     // rows of chunk 0
-        {   // candidates of chunk 1 (needs plan 0)
-            bar_sync_n(2, kCons);
-            const long long c1 = sh.plan[0].c0 + sh.plan[0].nr;
-            pre_e = pre_j = 0;
-            if (c1 + ci < rb) {
-                pre_e = __ldg(kcur + c1 + ci);
-                pre_j = __ldg(jcur + c1 + ci);
-            }
-        }
-        __syncthreads();   // plan 0 is visible to everybody
-        RowGather gat;
-        gat.row = -1;
-        for (int q = 0;; ++q) {
-            const WinPlan& pl = sh.plan[q & 1];
-            if (pl.mode != PLAN_RUN) break;
-            const uint32_t TF = pl.TF, JF = pl.JF, TFp = pl.TFprev, JFp = pl.JFprev;
-            uint32_t slotTe = pl.slotT + (TF - TFp), slotJe = pl.slotJ + (JF - JFp);   // slots of the new frontiers
+        // gather the rows of a produced chunk out of the rings and finalise them
+        auto gather_finish = [&](const WinPlan& pg, const uint32_t e, const uint32_t je, const bool arrive) {
+            const uint32_t TF = pg.TF, JF = pg.JF;
+            uint32_t slotTe = pg.slotT + (TF - pg.TFprev), slotJe = pg.slotJ + (JF - pg.JFprev);   // slots of the chunk's frontiers
             if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
             if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
-            const int nr = pl.nr;
-            const long long c0 = pl.c0;
-            // ---- phase 1: the next chunk's plan first (its ticks then have a whole phase to arrive), then the previous chunk's rows
-            make_plan((q + 1) & 1, c0 + nr, TF, JF, slotTe, slotJe, pre_e, pre_j);
-            const uint32_t nxt_e = cur_e, nxt_j = cur_j;
-            if (gat.row >= 0) {
-                if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
-                else finish_tick_row(out, N, P, pivot, gat);
-                const uint32_t jb = sub_floor0(gat.je, Wd);
-                write_trade_row(out, N, gat.row, P.clog2c, P.inv_cnt, (int)(gat.je - jb), gat.pos, gat.neg, gat.rev, gat.isum);
-                gat.row = -1;
-            }
-            __syncthreads();   // S1: the rings hold chunk q; plan q + 1 is visible
-            // ---- phase 2: gather this chunk's rows
-            if (ci < nr) {
-                const uint32_t e = my_e, je = my_j;
+            RowGather gat;
+            gat.row = -1;
+            if (ci < pg.nr) {
                 auto slot_of = [&](uint32_t p) {   // ring slot of tick position p <= TF
                     int sl = (int)slotTe - (int)(TF - p);
                     return sl < 0 ? sl + R : sl;
@@ -683,42 +671,77 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 }
                 gat.e = e;
                 gat.je = je;
-                gat.row = c0 + ci;
+                gat.row = pg.c0 + ci;
                 const uint32_t exc = sh.excP1;
                 gat.flagged = exc != 0u && e <= exc + Wmax + 1u;   // the window (or the entry just before it) may hold a flagged tick
             }
-            // candidates of chunk q + 2
-            {
-                const WinPlan& pn = sh.plan[(q + 1) & 1];
-                const long long c2 = pn.c0 + pn.nr;
+            if (arrive) bar_arrive_n(3, kWinThreads);   // the values are in registers: the rings may move on
+            if (gat.row >= 0) {
+                if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
+                else finish_tick_row(out, N, P, sLog, pivot, gat);
+                const uint32_t jb = sub_floor0(gat.je, Wd);
+                write_trade_row(out, N, gat.row, sLog, (int)(gat.je - jb), gat.pos, gat.neg, gat.rev, gat.isum);
+            }
+        };
+        uint32_t pre_e = 0, pre_j = 0;
+        if (ra + ci < rb) {
+            pre_e = __ldg(kcur + ra + ci);
+            pre_j = __ldg(jcur + ra + ci);
+        }
+        make_plan(0, ra, baseK, baseJ, 0u, 0u, pre_e, pre_j);
+        uint32_t e_next = cur_e, j_next = cur_j;   // this thread's row of chunk 0 (to be produced in iteration 0, gathered in iteration 1)
+        uint32_t e_gat = 0, j_gat = 0;             // ... of the chunk to be gathered in the current iteration
+        {   // candidates of chunk 1
+            const long long c1 = ra + plan_nr;
+            pre_e = pre_j = 0;
+            if (c1 + ci < rb) {
+                pre_e = __ldg(kcur + c1 + ci);
+                pre_j = __ldg(jcur + c1 + ci);
+            }
+        }
+        __syncthreads();   // plan 0 is visible to everybody
+        int q = 0;
+        for (;; ++q) {
+            const WinPlan& pl = sh.plan[q & 3];
+            if (pl.mode != PLAN_RUN) break;
+            const uint32_t TF = pl.TF, JF = pl.JF;
+            uint32_t slotTe = pl.slotT + (TF - pl.TFprev), slotJe = pl.slotJ + (JF - pl.JFprev);
+            if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
+            if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
+            const long long c0n = pl.c0 + pl.nr;
+            // the plan of chunk q + 1 first: its ticks then have the whole iteration to arrive
+            make_plan(q + 1, c0n, TF, JF, slotTe, slotJe, pre_e, pre_j);
+            {   // candidates of chunk q + 2: in flight during the gather
+                const long long c2 = c0n + plan_nr;
                 pre_e = pre_j = 0;
-                if (pn.mode == PLAN_RUN && c2 + ci < rb) {
+                if (c2 + ci < rb) {
                     pre_e = __ldg(kcur + c2 + ci);
                     pre_j = __ldg(jcur + c2 + ci);
                 }
             }
-            my_e = nxt_e;
-            my_j = nxt_j;
-            __syncthreads();   // S0
+            // chunk q - 1 is in the rings (the producers are busy with chunk q's arithmetic and will not store before barrier 3)
+            if (q > 0) gather_finish(sh.plan[(q - 1) & 3], e_gat, j_gat, true);
+            else bar_arrive_n(3, kWinThreads);
+            e_gat = e_next;
+            j_gat = j_next;
+            e_next = cur_e;
+            j_next = cur_j;
+            __syncthreads();   // the rings hold chunk q; plan q + 1 is visible
         }
-        if (gat.row >= 0) {
-            if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
-            else finish_tick_row(out, N, P, pivot, gat);
-            const uint32_t jb = sub_floor0(gat.je, Wd);
-            write_trade_row(out, N, gat.row, P.clog2c, P.inv_cnt, (int)(gat.je - jb), gat.pos, gat.neg, gat.rev, gat.isum);
-        }
+        if (q > 0) gather_finish(sh.plan[(q - 1) & 3], e_gat, j_gat, false);   // the last chunk
     } else {
         // ================================================================================ the trade warp: trades -> QT
         unsigned long long cJ = 0ull;    // the counters at the trade frontier
         __syncthreads();   // plan 0 is visible
         for (int q = 0;; ++q) {
-            const WinPlan& pl = sh.plan[q & 1];
+            const WinPlan& pl = sh.plan[q & 3];
             if (pl.mode != PLAN_RUN) break;
             const uint32_t JFp = pl.JFprev, JF = pl.JF;
             uint32_t slot0 = pl.slotJ;
             if (JF > JFp) mbar_wait(&sh.full[q & 1], (uint32_t)((q >> 1) & 1));   // the chunk's trade directions have landed
             const uint32_t t0 = JFp > baseJ ? JFp - 1u : baseJ;
             const signed char* __restrict__ sb = reinterpret_cast<const signed char*>(sh.stgT[q & 1]) + pl.shT;   // sb[j - t0] = direction of trade j
+            bar_sync_n(3, kWinThreads);   // the previous chunk has been gathered
             for (uint32_t jp = JFp; jp < JF; jp += 32u * kTradeRun) {
                 const uint32_t j0 = jp + (uint32_t)(lane * kTradeRun);
                 int dprev = (j0 > baseJ && j0 < JF) ? (int)sb[j0 - 1u - t0] : 0;   // the trade at the base (trade 0) closes no pair
@@ -758,28 +781,29 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 slot0 += 32u * kTradeRun;
                 if (slot0 >= (uint32_t)RJ) slot0 -= (uint32_t)RJ;
             }
-            __syncthreads();   // S1
-            __syncthreads();   // S0
+            __syncthreads();   // the rings hold chunk q
         }
     }
 }
 
-// ring geometry for given windows: the tick ring holds one window + one chunk, likewise the trade ring; everything must fit
-// the 227 KB a CTA can opt into.  Returns false when the windows are too long for the on-chip rings.
+// Ring geometry for given windows: the tick ring holds one window + one chunk, likewise the trade ring; everything must fit the
+// 227 KB a CTA can opt into.  Returns false when the windows are too long for the on-chip rings.
+static size_t win_smem(int ring, int chunk_ticks, int trade_ring, int dir_window) {
+    return (size_t)ring * 44 + (size_t)4 * (chunk_ticks + 4) * 8 + (size_t)trade_ring * 8 + (size_t)(dir_window + 2) * 8;
+}
 bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, int* trade_ring, int* chunk_trades, size_t* smem) {
     const int wmax = mid_window > dir_window + 1 ? mid_window : dir_window + 1;
-    const size_t budget = 232448 - 1024;   // static shared memory (plans, warp totals) and slack
-    int cj = 1024;
-    int rj = ((dir_window + 2 + cj + 8 + 1) / 2) * 2;
-    for (int ct = kProd * kRun; ct >= 40 * kRun; ct -= 10 * kRun) {   // multiples of 10: even (16-byte staging rows) and whole thread runs
+    const size_t budget = 232448 - sizeof(WinStatic) - 1024;
+    const int cj = 1024;
+    const int rj = ((dir_window + 2 + cj + 8 + 1) / 2) * 2;
+    for (int ct = kProd * kRun; ct >= 4 * kRun; ct -= 2 * kRun) {   // even (16-byte staging rows), whole thread runs
         const int r = ((wmax + 2 + ct + 8 + 1) / 2) * 2;
-        const size_t bytes = (size_t)r * 44 + (size_t)4 * (ct + 4) * 8 + (size_t)rj * 8;
-        if (bytes <= budget) {
+        if (win_smem(r, ct, rj, dir_window) <= budget) {
             *ring = r;
             *chunk_ticks = ct;
             *trade_ring = rj;
             *chunk_trades = cj;
-            *smem = bytes;
+            *smem = win_smem(r, ct, rj, dir_window);
             return true;
         }
     }
@@ -788,7 +812,7 @@ bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, i
 
 cudaError_t launch_windows(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg, const DevParams& P,
                            cudaStream_t st) {
-    const size_t smem = (size_t)P.win_ring * 44 + (size_t)4 * (P.win_chunk_ticks + 4) * 8 + (size_t)P.win_trade_ring * 8;
+    const size_t smem = win_smem(P.win_ring, P.win_chunk_ticks, P.win_trade_ring, P.dir_window);
     static int ready_for[64];   // the opt-in is per device (idempotent; a race only repeats the call)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

@@ -70,6 +70,7 @@ struct DevParams {
     double stress_alpha, stress_decay, stress_min_size, stress_distance_decay;
     const double* ofi_weight;   // [L]  exp(-i*depth_decay), computed by the host libm
     const double* ewm_pow;      // [win_ring+1]    decay^n
+    const double* ewm_ipow;     // [513]           decay^-n
     const double* ofi_pow;      // [257]           ofi_decay^n
     double ofi_pw2[6], stress_pw2[6];  // decay^(1,2,4,8,16,32) again, as kernel-parameter constants (the scan steps)
     const double* stress_pow;   // [257]           stress_decay^n
