@@ -137,7 +137,7 @@ def run_reference_arm(args, rank: int, world: int):
             ob.run_oracle(hv, nthreads=threads, want_dirs=False, want_counts=False)
         return time.perf_counter() - t0
 
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    for _ in range(max(0, args.warmup)):
         one()
     times = [one() for _ in range(max(1, args.steps))]
     sec = sum(times) / len(times)
@@ -146,7 +146,7 @@ def run_reference_arm(args, rank: int, world: int):
     sample = f"{threads} streams x {rows_each} rows (prefix of the 50 M-row instrument-day shape), {threads} host threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, args.steps),
-        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(0, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"single instrument-day, {FULL_ROWS} snapshots x {LEVELS} levels (BASELINE.json configs[1])",
                    "levels": LEVELS, "ticks_per_row": TICKS_PER_ROW, "sample": sample},
@@ -178,6 +178,72 @@ def cpu_baseline(levels: int, budget_rows: int):
             "sample": f"{threads} streams x {budget_rows} rows, one host thread per stream, {sec:.1f} s"}
 
 
+def timeshard_leg(args, rank: int, world: int, dev, rows_per_gpu: int, steps: int, warmup: int):
+    """BASELINE.json configs[4]: ONE stream of rows_per_gpu * world snapshots split by time.  Every rank generates only its own
+    rows (range-restartable generator), binds them with headroom for the left neighbour's tail, and per step: packs its tail
+    (mrp_fg_halo_export), ships it as ONE message over NVLink (NCCL send / recv), unpacks the neighbour's (mrp_fg_halo_import)
+    and runs the pass.  Returns the sub-record (identical on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    import mrp_b200
+    from mrp_b200 import synth
+    from mrp_b200 import timeshard as tsh
+
+    total = rows_per_gpu * world
+    spec = synth.SynthSpec(n_rows=total, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED)
+    r0, r1 = tsh.shard_bounds(total, world, rank)
+    shard = synth.make_stream_range(spec, r0, r1, device=dev)
+    shard.pop("trade_size", None)
+    eng = mrp_b200.Engine(mrp_b200.default_params(), device=dev.index)
+    ts = tsh.TimeShard(eng, shard, rank, world)
+    del shard
+    torch.cuda.empty_cache()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        ts.exchange()
+        eng.run(stream)
+    barrier()
+    launches0 = eng.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    ev[0].record()
+    sent = 0
+    for i in range(steps):
+        sent = ts.exchange()
+        ev[2 * i + 1].record()
+        eng.run(stream)
+        ev[2 * i + 2].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[-1]) / steps
+    ex_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)) / steps
+    launches = eng.launch_count() - launches0
+    t = torch.tensor([ms, ex_ms, float(sent)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ex_ms, sent_max = (float(x) for x in t.tolist())
+    # the one collective of the path: global column moments of the z-scores over every rank's OWN rows
+    own = ts.own_rows
+    nm = torch.from_numpy(eng.norm_moments(stream, rows=own)).to(dev)
+    dist.all_reduce(nm, op=dist.ReduceOp.SUM)
+    rec = {
+        "rows_total": total, "rows_per_gpu": rows_per_gpu, "ms_per_step": ms, "value": total / (ms * 1e-3), "unit": UNIT,
+        "exchange_ms": ex_ms, "nvlink_bytes_per_rank_per_step": int(sent_max), "halo_rows": int(eng.halo_rows()),
+        "halo_extra_work": eng.halo_rows() / rows_per_gpu, "gpu_launches": launches, "steps": steps, "warmup": warmup,
+        "global_rows_in_moments": float(nm[0, 0].item()),
+        "sharding": ("ONE stream split by time; per step each rank packs its last %d rows (+ one window of ticks / trades) with mrp_fg_halo_export, "
+                     "ships them to its right neighbour as ONE NCCL message over NVLink, unpacks the left neighbour's with mrp_fg_halo_import and "
+                     "recomputes them as halo; one all-reduce of the column moments of the own rows" % eng.halo_rows()),
+    }
+    eng.close()
+    del ts
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +261,7 @@ def main():
                     help="also run the vol-of-vol extension over 3 horizons (600 / 3000 / 30000 rows) inside every step (BASELINE.json configs[3]; no reference counterpart)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-timeshard", action="store_true", help="N > 1: skip the time-shard sub-record (one stream of rows*N snapshots with the halo exchange)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -224,48 +291,22 @@ def main():
     step_pre = None   # per-step work ahead of the kernels (time-sharded mode: the halo exchange)
     skip = 0
     if args.timeshard and world > 1:
-        # ONE stream of rows*world snapshots; every rank keeps only its time slice (+ the halo its left neighbour sends)
-        from mrp_b200 import timeshard as tsh
-
-        total = rows * world
-        if total > 120_000_000:
-            raise SystemExit("--timeshard generates the whole stream on every rank before slicing it: use --rows <= 120e6 / N")
-        spec = synth.SynthSpec(n_rows=total, levels=LEVELS, ticks_per_row=TICKS_PER_ROW, seed=0x5EED)
-        full = synth.make_batch([spec], device=dev)
-        full.pop("trade_size", None)
-        r0, r1 = tsh.shard_bounds(total, world, rank)
-        shard = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in tsh.shard_of(full, r0, r1).items()}
-        del full
-        torch.cuda.empty_cache()
-        H = tsh.halo_rows()
-        halo = tsh.exchange_halo(shard, rank, world, H)
-        batch, skip = tsh.extend(shard, halo)
-        tail = tsh.tail_for_right(shard, H) if rank + 1 < world else None
-        hk, hj = (halo["mid"].shape[0], halo["trade_dir"].shape[0]) if halo is not None else (0, 0)
-        t_base, j_base = (halo["tick0"], halo["trade0"]) if halo is not None else (0, 0)
-        del shard, halo
-
-        def step_pre():
-            # the per-step exchange: pack the tail, NVLink P2P, unpack into the front of the extended arrays
-            ops, tmp = [], {}
-            if tail is not None:
-                for k in tsh._ALL:
-                    ops.append(dist.P2POp(dist.isend, tail[k], rank + 1))
-            if rank > 0:
-                for k in tsh._ALL:
-                    n = hk if k in tsh.TICK_KEYS else (hj if k in tsh.TRADE_KEYS else skip)
-                    shape = (LEVELS, n) if k in tsh.ROW_KEYS_2D else (n,)
-                    tmp[k] = torch.empty(shape, dtype=batch[k].dtype, device=dev)
-                    ops.append(dist.P2POp(dist.irecv, tmp[k], rank - 1))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            for k, v in tmp.items():
-                if k == "tick_cursor":
-                    v = (v.to(torch.int64) - t_base).to(batch[k].dtype)
-                elif k == "trade_cursor":
-                    v = (v.to(torch.int64) - j_base).to(batch[k].dtype)
-                batch[k][..., :v.shape[-1]].copy_(v)
-    else:
+        # ONE stream of rows*world snapshots split by time: handled by timeshard_leg() below (the instrument-day leg is skipped)
+        line = timeshard_leg(args, rank, world, dev, rows, max(args.steps, 1), max(args.warmup, 3))
+        if rank == 0:
+            peak, peak_src = measured_peaks()
+            bytes_row = algorithmic_bytes_per_row(LEVELS, TICKS_PER_ROW, 2.0)
+            gbs = line["rows_total"] / world * bytes_row / (line["ms_per_step"] * 1e-3) / 1e9
+            _emit({"metric": METRIC, "value": line["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                   "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                   "config": {"workload": "ONE stream of %d snapshots x %d levels split by time over %d GPUs (BASELINE.json configs[4])" % (line["rows_total"], LEVELS, world),
+                              "rows_per_gpu": rows, "levels": LEVELS, "sharding": line["sharding"], "l2": "inputs far exceed the 126 MB L2; no explicit flush"},
+                   "roofline": {"bound": "hbm", "kernel": "whole pass incl. halo exchange", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                "traffic": None, "peak_source": peak_src},
+                   "cpu_baseline": None, "e2e": None, "gpu_launches": line["gpu_launches"], "timeshard": line})
+        dist.destroy_process_group()
+        return
+    if True:
         # `--days D`: D independent instrument-days of `rows` snapshots each in one batch on this rank (day d of the job's
         # D*world days lives on rank d mod world, scripts/multidate_feature_to_csv.sh:24 -> one GPU per instrument-day)
         specs = [synth.SynthSpec(n_rows=rows, levels=args.levels, ticks_per_row=TICKS_PER_ROW, seed=0x5EED + rank + world * d)
@@ -450,12 +491,28 @@ def main():
                "rows_per_gpu": e2e_rows, "ms_per_step": e_ms,
                "checksum": float(norm_h[0, :1000].sum().item())}
         eng2.close()
+        del host, hv, raw_h, norm_h   # 37 GB of pinned memory per rank: released before anything else is staged
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if _ALL_CPUS:   # the CPU baseline gets every host core the launcher gave this process, not just the GPU's neighbours
             os.sched_setaffinity(0, _ALL_CPUS)
         cpu = cpu_baseline(args.levels, args.ref_rows)
+
+    tshard = None
+    if world > 1 and not args.no_timeshard and args.days == 1 and args.levels == LEVELS:
+        # the interconnect-bearing curve (BASELINE.json configs[4]) beside the instrument-day value: free the instrument-day first
+        try:
+            del eng
+        except NameError:
+            pass
+        try:
+            del batch
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        tshard = timeshard_leg(args, rank, world, dev, args.rows, max(2, min(args.steps, 3)), 3)
+        tshard["efficiency_vs_instrument_day_rate"] = tshard["value"] / value   # value = N x this box's per-GPU instrument-day rate
 
     if rank == 0:
         line = {
@@ -466,12 +523,10 @@ def main():
                                    + (" (BASELINE.json configs[1])" if (rows == FULL_ROWS and args.days == 1 and args.levels == LEVELS) else " (not the headline config)")
                                    + (" + vol-of-vol over %s rows (extension, no reference counterpart)" % (VOV_HORIZONS,) if args.vol_of_vol else ""),
                        "rows_per_gpu": rows, "levels": args.levels, "days_per_gpu": args.days,
-                       "sharding": ("ONE stream split by time; per step each rank sends its last %d rows (+ window of ticks / trades) to its right "
-                                    "neighbour over NVLink P2P and recomputes them as halo; all-reduce of the column moments" % tsh.halo_rows())
-                       if (args.timeshard and world > 1) else "instrument-day per GPU, no data-path collective",
+                       "sharding": "instrument-day per GPU, no data-path collective (the `timeshard` sub-record is the one stream split by time)",
                        "l2": "inputs (>= 20 GB at 50 M rows) far exceed the 126 MB L2; no explicit flush"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "host_affinity": numa, "global_standardisation": scaler,
-            "global_moments_midprice": [float(x) for x in mom[0]],
+            "global_moments_midprice": [float(x) for x in mom[0]], "timeshard": tshard,
         }
         _emit(line)
     if world > 1:

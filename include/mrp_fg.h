@@ -49,9 +49,10 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 6   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
+#define MRP_FG_ABI_VERSION 7   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
                                   5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize;
-                                  6: + mrp_fg_halo_rows(_for), mrp_fg_moments_rows, mrp_fg_norm_moments_rows */
+                                  6: + mrp_fg_halo_rows(_for), mrp_fg_moments_rows, mrp_fg_norm_moments_rows;
+                                  7: + mrp_fg_halo_query, mrp_fg_halo_export, mrp_fg_halo_import */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -211,6 +212,35 @@ int mrp_fg_download(mrp_fg_ctx* ctx, double* raw, double* norm, int8_t* bid_dir,
 /* Copy the rows [row_begin, row_end) of the RAW and z-scored features to HOST buffers laid out [19][row_end - row_begin]
  * (what a time shard keeps after dropping its halo, or the newest row of a trailing window); NULL = skip. */
 int mrp_fg_download_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, double* raw, double* norm, void* stream);
+
+/* ONE STREAM SPLIT BY TIME ACROSS GPUs (BASELINE.json configs[4]).  Every state of the path has finite memory, so a shard that
+ * is preceded by mrp_fg_halo_rows() rows of its stream (and one window of ticks / trades in front of those) reproduces the
+ * whole-stream result on its own rows.  The halo is the TAIL of the left neighbour's shard; these two calls move it as ONE
+ * contiguous device buffer, which the caller ships with whatever it has (cudaMemcpyPeerAsync, ncclSend / ncclRecv, MPI):
+ *
+ *   mrp_fg_halo_query   what the export will hold (info->bytes sizes the caller's message buffer).  The geometry is read from the
+ *                       device once per bind (one small synchronous copy).
+ *   mrp_fg_halo_export  packs the last mrp_fg_halo_rows() rows of the bound stream (ONE stream), the ticks from
+ *                       (tick cursor of the first of those rows) - max(mid_window, dir_window + 1) - 2 and the trades from
+ *                       (its trade cursor) - dir_window - 2 into dst_device (dst_capacity bytes; NULL = a context-owned
+ *                       buffer, returned through *packed_device); cursors are rebased to the packed ticks / trades.
+ *                       Asynchronous on `stream` once the geometry is known.
+ *   mrp_fg_halo_import  writes a packed halo into the FRONT of the bound stream: its first info->n_rows rows, first
+ *                       info->n_ticks ticks and first info->n_trades trades are overwritten (the bound arrays must be
+ *                       writable, and the caller lays out its shard with that headroom: own rows from row info->n_rows on,
+ *                       own ticks from tick info->n_ticks on, own cursors = info->n_ticks / n_trades + counts within the shard).
+ *                       After mrp_fg_run the rows [info->n_rows, n_rows) are the shard's own (mrp_fg_download_rows,
+ *                       mrp_fg_moments_rows).
+ * Replaces: nothing in the reference (a single process walks the whole stream, dual_feature_pipeline.cpp:67-120). */
+typedef struct mrp_fg_halo_info {
+    int64_t n_rows;    /* halo rows                                   */
+    int64_t n_ticks;   /* ticks the halo rows (and the shard's first rows) can see */
+    int64_t n_trades;  /* trades likewise                             */
+    int64_t bytes;     /* size of the packed buffer                   */
+} mrp_fg_halo_info;
+int mrp_fg_halo_query(mrp_fg_ctx* ctx, mrp_fg_halo_info* info, void* stream);
+int mrp_fg_halo_export(mrp_fg_ctx* ctx, void* dst_device, int64_t dst_capacity, const void** packed_device, mrp_fg_halo_info* info, void* stream);
+int mrp_fg_halo_import(mrp_fg_ctx* ctx, const void* packed_device, const mrp_fg_halo_info* info, void* stream);
 
 /* EXTENSION WITHOUT A REFERENCE COUNTERPART (BASELINE.json configs[3]: "vol-of-vol over 3 horizons"; the reference has no
  * such feature, SURVEY.md 0.1 D2 — PARITY UNPINNED: its only checker is the restatement of this definition in oracle/).

@@ -43,6 +43,10 @@ class Params(C.Structure):
     ]
 
 
+class HaloInfo(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_ticks", C.c_int64), ("n_trades", C.c_int64), ("bytes", C.c_int64)]
+
+
 class SoaView(C.Structure):
     _fields_ = [
         ("n_streams", C.c_int32), ("memory", C.c_int32),
@@ -145,6 +149,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_moments_rows.argtypes = [vp, i64, i64, vp, vp]
     lib.mrp_fg_norm_moments_rows.argtypes = [vp, i64, i64, vp, vp]
     lib.mrp_fg_halo_rows.argtypes = [vp]
+    lib.mrp_fg_halo_query.argtypes = [vp, C.POINTER(HaloInfo), vp]
+    lib.mrp_fg_halo_export.argtypes = [vp, vp, i64, C.POINTER(vp), C.POINTER(HaloInfo), vp]
+    lib.mrp_fg_halo_import.argtypes = [vp, vp, C.POINTER(HaloInfo), vp]
     lib.mrp_fg_halo_rows_for.argtypes = [PP]
     lib.mrp_fg_mean_scale.argtypes = [vp, vp]
     lib.mrp_fg_standardize.argtypes = [vp, vp, vp, C.POINTER(vp), vp]
@@ -276,6 +283,23 @@ class Engine:
         a, b = rows if rows is not None else (0, self.n_rows)
         self._check(self.lib.mrp_fg_moments_rows(self.ctx, a, b, C.c_void_p(m.ctypes.data), C.c_void_p(stream)))
         return m
+
+    # -- one stream split by time: the tail of this shard as one packed device buffer / a neighbour's tail into the headroom
+    def halo_query(self, stream: int = 0) -> "HaloInfo":
+        """What the packed tail of the bound stream holds (mrp_fg_halo_query); .bytes sizes the message buffer."""
+        info = HaloInfo()
+        self._check(self.lib.mrp_fg_halo_query(self.ctx, C.byref(info), C.c_void_p(stream)))
+        return info
+
+    def halo_export(self, dst_ptr: int = 0, capacity: int = 0, stream: int = 0):
+        """Pack the tail of the bound stream into dst_ptr (device; 0 = a context-owned buffer).  Returns (device pointer, HaloInfo)."""
+        ptr, info = C.c_void_p(), HaloInfo()
+        self._check(self.lib.mrp_fg_halo_export(self.ctx, C.c_void_p(dst_ptr), capacity, C.byref(ptr), C.byref(info), C.c_void_p(stream)))
+        return ptr.value, info
+
+    def halo_import(self, packed_ptr: int, info: "HaloInfo", stream: int = 0):
+        """Write a packed halo into the front (headroom) of the bound stream (mrp_fg_halo_import)."""
+        self._check(self.lib.mrp_fg_halo_import(self.ctx, C.c_void_p(packed_ptr), C.byref(info), C.c_void_p(stream)))
 
     def halo_rows(self) -> int:
         """Rows of history a time shard / host chunk needs in front of its own rows (mrp_fg_halo_rows)."""

@@ -144,6 +144,11 @@ struct mrp_fg_ctx {
     cudaEvent_t lane_done[2] = {nullptr, nullptr};
     uint32_t* lane_cursors[2] = {nullptr, nullptr};   // pinned: rebased tick / trade cursors of the chunk in flight
     size_t lane_cursor_cap[2] = {0, 0};
+    // time-shard halo (mrp_fg_halo_export): packed tail of the bound stream
+    DevBuf b_halo;
+    mrp_fg_halo_info halo_info{};
+    int64_t halo_t0 = 0, halo_j0 = 0;       // first tick / trade of the packed tail, in the bound stream's indices
+    uint64_t halo_gen = ~0ull;              // shape_gen the geometry was read for
     // the window and the book kernels write disjoint columns: the book pass may run on a second stream beside the window pass
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux[2] = {nullptr, nullptr};
@@ -489,7 +494,7 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
                       &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison,
                       &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win, &c->b_mom_part, &c->b_scaled,
-                      &c->b_mean_scale};
+                      &c->b_mean_scale, &c->b_halo};
     for (DevBuf* b : bufs) b->release();
     c->h_tables.release();
     if (c->tables_ready) cudaEventDestroy(c->tables_ready);
@@ -1018,6 +1023,160 @@ int mrp_fg_standardize(mrp_fg_ctx* c, const double* moments, double* out_host, c
     c->launches += 1;
     if (out_host) CU(cudaMemcpyAsync(out_host, c->b_scaled.p, (size_t)N * MRP_FG_NUM_FEATURES * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (out_device) *out_device = static_cast<const double*>(c->b_scaled.p);
+    return MRP_FG_OK;
+}
+
+}  // extern "C"
+
+namespace mrp {
+cudaError_t launch_rebase(const uint32_t* src, uint32_t* dst, int64_t n, uint32_t base, cudaStream_t st);
+}
+
+namespace {
+// byte offsets of the arrays inside a packed halo (every array starts on a 16-byte boundary)
+struct HaloLayout {
+    size_t ts, bpx, apx, bsz, asz, buy, sell, adds, kcur, jcur, mid, spread, tdir, total;
+};
+HaloLayout halo_layout(int64_t H, int64_t K, int64_t T, int L) {
+    HaloLayout o{};
+    size_t at = 0;
+    auto take = [&](size_t bytes) {
+        const size_t a = at;
+        at += (bytes + 15) & ~(size_t)15;
+        return a;
+    };
+    o.ts = take((size_t)H * 8);
+    o.bpx = take((size_t)H * L * 8);
+    o.apx = take((size_t)H * L * 8);
+    o.bsz = take((size_t)H * L * 4);
+    o.asz = take((size_t)H * L * 4);
+    o.buy = take((size_t)H * 8);
+    o.sell = take((size_t)H * 8);
+    o.adds = take((size_t)H * 4);
+    o.kcur = take((size_t)H * 4);
+    o.jcur = take((size_t)H * 4);
+    o.mid = take((size_t)K * 8);
+    o.spread = take((size_t)K * 8);
+    o.tdir = take((size_t)T);
+    o.total = at;
+    return o;
+}
+}  // namespace
+
+extern "C" {
+
+}  // extern "C"
+
+namespace {
+// where the tail of the bound stream starts on the tick / trade axes: read from the device once per bind
+int halo_geometry(mrp_fg_ctx* c, cudaStream_t st) {
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    if (c->n_streams != 1) return fail(MRP_FG_ERR_INVALID, "the halo calls need ONE bound stream (a time shard)");
+    const int64_t N = c->n_rows, H = mrp_fg_halo_rows(c);
+    if (N < H) return fail(MRP_FG_ERR_INVALID, "a time shard must hold at least mrp_fg_halo_rows() rows: the halo comes from ONE neighbour");
+    if (c->halo_gen == c->shape_gen) return MRP_FG_OK;
+    const int64_t a = N - H;
+    uint32_t kj[2];
+    CU(cudaMemcpyAsync(&kj[0], c->in.kcur + a, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&kj[1], c->in.jcur + a, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int64_t wmax = std::max(c->p.mid_window, c->p.dir_window + 1);
+    c->halo_t0 = std::max<int64_t>(0, (int64_t)kj[0] - wmax - 2);
+    c->halo_j0 = std::max<int64_t>(0, (int64_t)kj[1] - c->p.dir_window - 2);
+    if (c->halo_t0 > c->n_ticks || c->halo_j0 > c->n_trades) return fail(MRP_FG_ERR_INVALID, "a cursor points past the end of its stream's tick / trade arrays");
+    c->halo_info.n_rows = H;
+    c->halo_info.n_ticks = c->n_ticks - c->halo_t0;
+    c->halo_info.n_trades = c->n_trades - c->halo_j0;
+    c->halo_info.bytes = (int64_t)halo_layout(H, c->halo_info.n_ticks, c->halo_info.n_trades, c->p.depth_levels).total;
+    c->halo_gen = c->shape_gen;
+    return MRP_FG_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mrp_fg_halo_query(mrp_fg_ctx* c, mrp_fg_halo_info* info, void* stream) {
+    if (!c || !info) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    int rc = halo_geometry(c, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    *info = c->halo_info;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_halo_export(mrp_fg_ctx* c, void* dst_device, int64_t dst_capacity, const void** packed_device, mrp_fg_halo_info* info, void* stream) {
+    if (!c || !info) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = halo_geometry(c, st);
+    if (rc) return rc;
+    const int64_t N = c->n_rows, H = c->halo_info.n_rows, a = N - H;
+    const int L = c->p.depth_levels;
+    if (dst_device) {
+        if (dst_capacity < c->halo_info.bytes) return fail(MRP_FG_ERR_INVALID, "the destination buffer is smaller than mrp_fg_halo_query().bytes");
+    } else if ((rc = c->b_halo.ensure((size_t)c->halo_info.bytes))) {
+        return rc;
+    }
+    const int64_t K = c->halo_info.n_ticks, T = c->halo_info.n_trades;
+    const HaloLayout lo = halo_layout(H, K, T, L);
+    unsigned char* dst = static_cast<unsigned char*>(dst_device ? dst_device : c->b_halo.p);
+    const DevInputs& in = c->in;
+    auto d2d = [&](size_t off, const void* src, size_t bytes) { return bytes ? cudaMemcpyAsync(dst + off, src, bytes, cudaMemcpyDeviceToDevice, st) : cudaSuccess; };
+    auto d2d_levels = [&](size_t off, const void* src, size_t elem) {   // [L][N] rows a.. -> dense [L][H]
+        return cudaMemcpy2DAsync(dst + off, (size_t)H * elem, static_cast<const unsigned char*>(src) + (size_t)a * elem, (size_t)N * elem,
+                                 (size_t)H * elem, (size_t)L, cudaMemcpyDeviceToDevice, st);
+    };
+    CU(d2d(lo.ts, in.ts + a, (size_t)H * 8));
+    CU(d2d_levels(lo.bpx, in.bid_px, 8));
+    CU(d2d_levels(lo.apx, in.ask_px, 8));
+    CU(d2d_levels(lo.bsz, in.bid_sz, 4));
+    CU(d2d_levels(lo.asz, in.ask_sz, 4));
+    CU(d2d(lo.buy, in.buy + a, (size_t)H * 8));
+    CU(d2d(lo.sell, in.sell + a, (size_t)H * 8));
+    CU(d2d(lo.adds, in.adds + a, (size_t)H * 4));
+    CU(launch_rebase(in.kcur + a, reinterpret_cast<uint32_t*>(dst + lo.kcur), H, (uint32_t)c->halo_t0, st));
+    CU(launch_rebase(in.jcur + a, reinterpret_cast<uint32_t*>(dst + lo.jcur), H, (uint32_t)c->halo_j0, st));
+    CU(d2d(lo.mid, in.mid + c->halo_t0, (size_t)K * 8));
+    CU(d2d(lo.spread, in.spread + c->halo_t0, (size_t)K * 8));
+    CU(d2d(lo.tdir, in.tdir + c->halo_j0, (size_t)T));
+    c->launches += 2;
+    if (packed_device) *packed_device = dst;
+    *info = c->halo_info;
+    return MRP_FG_OK;
+}
+
+int mrp_fg_halo_import(mrp_fg_ctx* c, const void* packed_device, const mrp_fg_halo_info* info, void* stream) {
+    if (!c || !packed_device || !info) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    if (c->n_streams != 1) return fail(MRP_FG_ERR_INVALID, "mrp_fg_halo_import needs ONE bound stream (a time shard)");
+    const int64_t N = c->n_rows, H = info->n_rows, K = info->n_ticks, T = info->n_trades;
+    const int L = c->p.depth_levels;
+    if (H < 0 || K < 0 || T < 0 || H > N || K > c->n_ticks || T > c->n_trades) return fail(MRP_FG_ERR_INVALID, "the halo does not fit the headroom of the bound stream");
+    const HaloLayout lo = halo_layout(H, K, T, L);
+    if ((int64_t)lo.total != info->bytes) return fail(MRP_FG_ERR_INVALID, "halo info does not match this context's depth_levels / layout");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned char* src = static_cast<const unsigned char*>(packed_device);
+    const DevInputs& in = c->in;   // the bound arrays are the caller's; the headroom in front of them is overwritten
+    auto d2d = [&](const void* dstp, size_t off, size_t bytes) { return bytes ? cudaMemcpyAsync(const_cast<void*>(dstp), src + off, bytes, cudaMemcpyDeviceToDevice, st) : cudaSuccess; };
+    auto d2d_levels = [&](const void* dstp, size_t off, size_t elem) {   // dense [L][H] -> the first H rows of [L][N]
+        return cudaMemcpy2DAsync(const_cast<void*>(dstp), (size_t)N * elem, src + off, (size_t)H * elem, (size_t)H * elem, (size_t)L, cudaMemcpyDeviceToDevice, st);
+    };
+    if (H > 0) {
+        CU(d2d(in.ts, lo.ts, (size_t)H * 8));
+        CU(d2d_levels(in.bid_px, lo.bpx, 8));
+        CU(d2d_levels(in.ask_px, lo.apx, 8));
+        CU(d2d_levels(in.bid_sz, lo.bsz, 4));
+        CU(d2d_levels(in.ask_sz, lo.asz, 4));
+        CU(d2d(in.buy, lo.buy, (size_t)H * 8));
+        CU(d2d(in.sell, lo.sell, (size_t)H * 8));
+        CU(d2d(in.adds, lo.adds, (size_t)H * 4));
+        CU(d2d(in.kcur, lo.kcur, (size_t)H * 4));
+        CU(d2d(in.jcur, lo.jcur, (size_t)H * 4));
+    }
+    CU(d2d(in.mid, lo.mid, (size_t)K * 8));
+    CU(d2d(in.spread, lo.spread, (size_t)K * 8));
+    CU(d2d(in.tdir, lo.tdir, (size_t)T));
     return MRP_FG_OK;
 }
 

@@ -753,6 +753,16 @@ k_standardize(const double* __restrict__ x, double* __restrict__ out, const int6
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (int64_t)gridDim.x * blockDim.x) xo[r] = (xi[r] - mean) / scale;
 }
 
+// dst[i] = src[i] - base: the cursors of a packed halo count from its own first tick / trade
+__global__ void k_rebase(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, const int64_t n, const uint32_t base) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i] - base;
+}
+cudaError_t launch_rebase(const uint32_t* src, uint32_t* dst, int64_t n, uint32_t base, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_rebase<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, st>>>(src, dst, n, base);
+    return cudaGetLastError();
+}
+
 int col_moment_blocks(int64_t N) { return (int)((N + kMomRows - 1) / kMomRows); }
 
 // column c of the matrix starts at x + c * col_stride; N rows of it are summed

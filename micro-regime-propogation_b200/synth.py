@@ -164,6 +164,117 @@ def make_stream(spec: SynthSpec, device: str | torch.device = "cpu") -> Dict[str
     }
 
 
+def _blocked_sum(fn, n: int, dev, block: int = 1 << 24) -> int:
+    """sum_{i<n} fn(i) with i handed to fn in blocks (int64 tensors on dev); returns a Python int."""
+    total = 0
+    for a in range(0, n, block):
+        idx = torch.arange(a, min(a + block, n), dtype=torch.int64, device=dev)
+        total += int(fn(idx).sum().item())
+    return total
+
+
+def make_stream_range(spec: SynthSpec, r0: int, r1: int, device: str | torch.device = "cpu") -> Dict[str, object]:
+    """The rows [r0, r1) of make_stream(spec) and the ticks / trades that arrive during those rows (for r0 = 0: from the
+    stream's first tick / trade), bit-identical to slicing the whole stream — without materialising it: the generator is
+    counter-based, so only the running sums at the range start (the price walk, the trade count, the buy / sell volume
+    prefixes) are accumulated block by block.  Cursors stay GLOBAL (counts since the stream start).  Returns the arrays plus
+    'row0', 'tick0', 'trade0' = global index of the first row / tick / trade held.  Regular cursors only."""
+    if spec.variable_cursors:
+        raise ValueError("make_stream_range needs regular cursors (ticks_per_row fixed)")
+    dev = torch.device(device)
+    i64 = torch.int64
+    N, L, m, seed = spec.n_rows, spec.levels, spec.ticks_per_row, spec.seed
+    assert 0 <= r0 < r1 <= N
+    rows = torch.arange(r0, r1, dtype=i64, device=dev)
+    n = r1 - r0
+    kcur = spec.warm_ticks + m * rows
+    # ticks pushed before row r0's predecessor snapshot ... the shard holds the ticks [t0, t1) with t0 = cursor of row r0 - 1
+    t0 = 0 if r0 == 0 else spec.warm_ticks + m * (r0 - 1)
+    t1 = spec.warm_ticks + m * (r1 - 1) if r1 < N else max(spec.warm_ticks + m * (N - 1), 1)
+    per_tr = _h(seed, 2, rows) % (spec.max_trades_per_row + 1)
+    j_before = spec.warm_trades + _blocked_sum(lambda i: _h(seed, 2, i) % (spec.max_trades_per_row + 1), r0, dev)   # cursor of row r0 - 1 (r0 > 0)
+    jcur = j_before + torch.cumsum(per_tr, 0)
+    if r0 == 0:
+        j0 = 0
+    else:
+        j0 = j_before
+    T_total_here = int(jcur[-1].item())
+    j1 = T_total_here   # trades up to the last row's cursor (== the whole stream's trade count when r1 == N)
+
+    def step_of(k):
+        hk = _h(seed, 3, k)
+        thr = 100 + _tri(k, 150_000, 500)
+        move = (hk % 1024) < thr
+        sign = torch.where(((hk >> 20) & 1) == 1, 1, -1)
+        return torch.where(move, sign, torch.zeros_like(sign))
+
+    # the book at row r needs the tick before its cursor: ticks from min(t0, cursor(r0) - 1) on
+    ta = min(t0, max(int(kcur[0].item()) - 1, 0))
+    walk0 = _blocked_sum(step_of, ta, dev)                                  # the walk before tick ta
+    k = torch.arange(ta, t1, dtype=i64, device=dev)
+    walk = walk0 + torch.cumsum(step_of(k), 0)
+    B2 = 2 * spec.band
+    ph = (walk + spec.band) % (2 * B2)
+    best_bid_t = spec.base_ticks - spec.band + torch.where(ph < B2, ph, 2 * B2 - ph)
+    del walk, ph
+    hs = _h(seed, 4, k) % 8
+    spr_t = torch.where(hs < 6, torch.ones_like(hs), hs - 4)
+    del hs
+    mid = (2 * best_bid_t + spr_t).to(torch.float64) * 0.125
+    spread = spr_t.to(torch.float64) * 0.25
+    at = torch.clamp(kcur - 1, min=0) - ta
+    bb = best_bid_t[at]
+    sp = spr_t[at]
+    del best_bid_t, spr_t, k
+    mid, spread = mid[t0 - ta:], spread[t0 - ta:]
+    bid_px = torch.empty((L, n), dtype=torch.float64, device=dev)
+    ask_px = torch.empty((L, n), dtype=torch.float64, device=dev)
+    bid_sz = torch.empty((L, n), dtype=torch.int32, device=dev)
+    ask_sz = torch.empty((L, n), dtype=torch.int32, device=dev)
+    hz = _h(seed, 5, rows)
+    zb = torch.where(hz % 64 == 0, 1 + (hz >> 8) % 3, torch.zeros_like(hz))
+    za = torch.where((hz >> 16) % 64 == 0, 1 + (hz >> 24) % 3, torch.zeros_like(hz))
+    for i in range(L):
+        hold = 1 + (i % 3)
+        sb = 1 + _h(seed, 100 + i, rows // hold) % 200
+        sa = 1 + _h(seed, 300 + i, rows // hold) % 200
+        eb = (L - i) <= zb
+        ea = (L - i) <= za
+        bid_px[i] = torch.where(eb, 0.0, (bb - i).to(torch.float64) * 0.25)
+        ask_px[i] = torch.where(ea, 0.0, (bb + sp + i).to(torch.float64) * 0.25)
+        bid_sz[i] = torch.where(eb, 0, sb).to(torch.int32)
+        ask_sz[i] = torch.where(ea, 0, sa).to(torch.int32)
+    del hz, zb, za, bb, sp, at
+    ts = 1_746_453_700_000_000_000 + rows * 500_000_000 + _h(seed, 6, rows) % 20_000_000
+    adds = (_h(seed, 7, rows) % 300).to(torch.int32)
+
+    # trades: the volume windows reach dir_window trades back from the first cursor
+    def trade_of(j):
+        hj = _h(seed, 8, j)
+        pthr = 358 + _tri(j, 37_000, 308)
+        d = torch.where((hj % 1024) < pthr, 1, -1)
+        return d, (1 + (hj >> 12) % 50)
+
+    ja = max(0, min(j0, int(jcur[0].item()) - spec.dir_window))
+    j = torch.arange(ja, j1, dtype=i64, device=dev)
+    d, sz = trade_of(j)
+    zero = torch.zeros(1, dtype=i64, device=dev)
+    cb = torch.cat([zero, torch.cumsum(torch.where(d > 0, sz, torch.zeros_like(sz)), 0)])   # relative prefixes: only differences are used
+    cs = torch.cat([zero, torch.cumsum(torch.where(d < 0, sz, torch.zeros_like(sz)), 0)])
+    lo = torch.clamp(jcur - spec.dir_window, min=0)
+    buy = (cb[jcur - ja] - cb[lo - ja]).to(torch.float64)
+    sell = (cs[jcur - ja] - cs[lo - ja]).to(torch.float64)
+    tdir = d.to(torch.int8)[j0 - ja:]
+    tsize = sz.to(torch.float64)[j0 - ja:]
+    return {
+        "ts_ns": ts, "bid_px": bid_px, "ask_px": ask_px, "bid_sz": bid_sz, "ask_sz": ask_sz,
+        "buy_vol": buy, "sell_vol": sell, "adds": adds,
+        "tick_cursor": kcur, "trade_cursor": jcur,            # GLOBAL, int64 (a 400 M-row stream reaches 4e9 ticks)
+        "mid": mid, "spread": spread, "trade_dir": tdir, "trade_size": tsize,
+        "row0": r0, "tick0": t0, "trade0": j0, "n_rows_total": N,
+    }
+
+
 _ROW_KEYS_1D = ("ts_ns", "buy_vol", "sell_vol", "adds", "tick_cursor", "trade_cursor")
 _ROW_KEYS_2D = ("bid_px", "ask_px", "bid_sz", "ask_sz")
 _TICK_KEYS = ("mid", "spread")

@@ -113,6 +113,89 @@ def extend(shard: Dict[str, object], halo: Optional[Dict[str, object]]):
     return out, skip
 
 
+# ---- the same through the C ABI (mrp_fg_halo_query / _export / _import): the halo travels as ONE packed device buffer
+def layout_with_headroom(shard: Dict[str, object], lead) -> "tuple[Dict[str, object], int]":
+    """This rank's shard as ONE engine stream with room in front for the left neighbour's tail (`lead`: a HaloInfo, or None on
+    rank 0): own rows from row lead.n_rows on, own ticks / trades behind lead.n_ticks / lead.n_trades, own cursors counted
+    from the first HALO tick / trade.  Returns (batch of torch tensors for Engine.bind_device, rows to skip on output)."""
+    H, K, T = (int(lead.n_rows), int(lead.n_ticks), int(lead.n_trades)) if lead is not None else (0, 0, 0)
+    dev = shard["mid"].device
+    out: Dict[str, object] = {}
+
+    def front(t: torch.Tensor, lead_n: int) -> torch.Tensor:
+        if lead_n == 0:
+            return t.contiguous()
+        shape = list(t.shape)
+        shape[-1] += lead_n
+        o = torch.zeros(shape, dtype=t.dtype, device=dev)
+        o[..., lead_n:] = t
+        return o
+
+    for k in ("ts_ns", "buy_vol", "sell_vol", "adds") + ROW_KEYS_2D:
+        out[k] = front(shard[k], H)
+    out["tick_cursor"] = front((shard["tick_cursor"].to(torch.int64) - shard["tick0"] + K).to(torch.int32), H)
+    out["trade_cursor"] = front((shard["trade_cursor"].to(torch.int64) - shard["trade0"] + T).to(torch.int32), H)
+    for k in TICK_KEYS:
+        out[k] = front(shard[k], K)
+    for k in TRADE_KEYS:
+        out[k] = front(shard[k], T)
+    out["row_offsets"] = [0, int(out["ts_ns"].shape[0])]
+    out["tick_offsets"] = [0, int(out["mid"].shape[0])]
+    out["trade_offsets"] = [0, int(out["trade_dir"].shape[0])]
+    return out, H
+
+
+class TimeShard:
+    """One rank of a stream split by time, driven through the C ABI.  setup() binds the shard with headroom and agrees the halo
+    sizes with the neighbours (a chain of W - 1 tiny host messages, once); exchange() moves the packed tail to the right
+    neighbour (one NCCL / gloo message per step) and unpacks the left neighbour's into the headroom."""
+
+    def __init__(self, engine, shard: Dict[str, object], rank: int, world: int):
+        import torch.distributed as dist
+
+        from . import cabi
+
+        self.engine, self.rank, self.world = engine, rank, world
+        dev = shard["mid"].device
+        self.lead = None
+        if rank > 0:
+            meta = torch.empty(4, dtype=torch.int64, device=dev)
+            dist.recv(meta, rank - 1)
+            self.lead = cabi.HaloInfo(*[int(x) for x in meta.tolist()])
+        self.batch, self.skip = layout_with_headroom(shard, self.lead)
+        engine.bind_device(self.batch)
+        self.tail = None
+        self.send_buf = self.recv_buf = None
+        if rank + 1 < world:
+            self.tail = engine.halo_query(torch.cuda.current_stream().cuda_stream if dev.type == "cuda" else 0)
+            dist.send(torch.tensor([self.tail.n_rows, self.tail.n_ticks, self.tail.n_trades, self.tail.bytes], dtype=torch.int64, device=dev), rank + 1)
+            self.send_buf = torch.empty(int(self.tail.bytes), dtype=torch.uint8, device=dev)
+        if self.lead is not None:
+            self.recv_buf = torch.empty(int(self.lead.bytes), dtype=torch.uint8, device=dev)
+
+    def exchange(self) -> int:
+        """Pack, ship, unpack: returns the bytes this rank sent."""
+        import torch.distributed as dist
+
+        st = torch.cuda.current_stream().cuda_stream
+        ops = []
+        if self.tail is not None:
+            self.engine.halo_export(self.send_buf.data_ptr(), self.send_buf.numel(), st)
+            ops.append(dist.P2POp(dist.isend, self.send_buf, self.rank + 1))
+        if self.lead is not None:
+            ops.append(dist.P2POp(dist.irecv, self.recv_buf, self.rank - 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if self.lead is not None:
+            self.engine.halo_import(self.recv_buf.data_ptr(), self.lead, st)
+        return int(self.tail.bytes) if self.tail is not None else 0
+
+    @property
+    def own_rows(self):
+        return self.skip, int(self.batch["row_offsets"][1])
+
+
 _META = ("row0", "tick0", "trade0")
 _ALL = ROW_KEYS_1D + ROW_KEYS_2D + TICK_KEYS + TRADE_KEYS
 

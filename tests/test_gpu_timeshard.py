@@ -89,3 +89,48 @@ def test_boundary_rows_at_the_real_window(monkeypatch):
     rep = column_report(g_raw, g_norm, ref["raw"], ref["norm"], ref["raw_with_warm"], ref["norm_with_warm"], sk, W)
     parity_record("timeshard_boundary_W30000", checker=kind, rows=N, boundary=r0, compared_rows=[lo, hi], halo_rows=H,
                   shard_vs_whole_max_dz=float(np.nanmax(dz)), columns=rep)
+
+
+@pytest.mark.parametrize("variable", [False, True])
+def test_halo_through_the_c_abi(variable):
+    """mrp_fg_halo_query / _export / _import: shard 0's packed tail lands in shard 1's headroom; shard 1's own rows equal the
+    whole-stream run (what a C++ host with cudaMemcpyPeerAsync or ncclSend / ncclRecv between the two calls gets)."""
+    W, N, world = 2000, 9000, 2
+    p = mrp_b200.default_params(norm_window=W, emit_dirs=1, emit_counts=1)
+    full = synth.make_batch([synth.SynthSpec(n_rows=N, seed=93, variable_cursors=variable)])
+    full.pop("trade_size")
+    whole = _run_device(full, p)
+    shards = [timeshard.shard_of(full, *timeshard.shard_bounds(N, world, r)) for r in range(world)]
+    shards = [{k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in sh.items()} for sh in shards]
+    e0 = mrp_b200.Engine(p, device=0)
+    b0, skip0 = timeshard.layout_with_headroom(shards[0], None)
+    e0.bind_device(b0)
+    info = e0.halo_query()
+    assert info.n_rows == mrp_b200.halo_rows(p) == e0.halo_rows()
+    buf = torch.empty(int(info.bytes), dtype=torch.uint8, device="cuda")
+    e0.halo_export(buf.data_ptr(), buf.numel())
+    e1 = mrp_b200.Engine(p, device=0)
+    b1, skip1 = timeshard.layout_with_headroom(shards[1], info)
+    e1.bind_device(b1)
+    e1.halo_import(buf.data_ptr(), info)
+    e1.run()
+    got = e1.download()
+    r0, r1 = timeshard.shard_bounds(N, world, 1)
+    assert skip1 == info.n_rows and got["raw"].shape[1] - skip1 == r1 - r0
+    assert np.array_equal(got["bid_dir"][:, skip1:], whole["bid_dir"][:, r0:r1])
+    assert np.array_equal(got["counts"][:, skip1:], whole["counts"][:, r0:r1])
+    scale = np.nanmax(np.abs(whole["raw"]), axis=1, keepdims=True)
+    assert np.allclose(got["raw"][:, skip1:], whole["raw"][:, r0:r1], rtol=1e-10, atol=1e-13 * scale.max(), equal_nan=True)
+    dz = np.abs(got["norm"][:, skip1:] - whole["norm"][:, r0:r1]) / np.maximum(1.0, np.abs(whole["norm"][:, r0:r1]))
+    assert np.nanmax(dz) < 1e-9, np.nanmax(dz)
+    # own-row moments: the halo rows stay out (their features are recomputed by the left neighbour too)
+    m_own = e1.moments(rows=(skip1, got["raw"].shape[1]))
+    assert np.allclose(m_own[:, 0], np.isfinite(whole["raw"][:, r0:r1]).sum(1))
+    # the import must refuse a halo that does not fit
+    small = mrp_b200.Engine(p, device=0)
+    small.bind_device(b0)
+    bad = mrp_b200.HaloInfo(10 ** 9, info.n_ticks, info.n_trades, info.bytes)
+    with pytest.raises(mrp_b200.MrpError):
+        small.halo_import(buf.data_ptr(), bad)
+    for e in (e0, e1, small):
+        e.close()
