@@ -52,7 +52,7 @@ extern "C" {
 #define MRP_FG_ABI_VERSION 7   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
                                   5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize;
                                   6: + mrp_fg_halo_rows(_for), mrp_fg_moments_rows, mrp_fg_norm_moments_rows;
-                                  7: + mrp_fg_halo_query, mrp_fg_halo_export, mrp_fg_halo_import */
+                                  7: + mrp_fg_halo_query, mrp_fg_halo_export, mrp_fg_halo_import, mrp_fg_build_state */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -149,9 +149,9 @@ typedef struct mrp_fg_soa_view {
     const double* ask_px;         /* [L][n_rows]  ask_prices  (level 0 == best_ask_price)         */
     const int32_t* bid_sz;        /* [L][n_rows]  bid_sizes                                       */
     const int32_t* ask_sz;        /* [L][n_rows]  ask_sizes                                       */
-    const double* buy_vol;        /* [n_rows]     rolling_buy_volume                              */
-    const double* sell_vol;       /* [n_rows]     rolling_sell_volume                             */
-    const int32_t* adds;          /* [n_rows]     adds_since_last_snapshot                        */
+    const double* buy_vol;        /* [n_rows]     rolling_buy_volume       } NULL: derived on the device   */
+    const double* sell_vol;       /* [n_rows]     rolling_sell_volume      } by mrp_fg_build_state         */
+    const int32_t* adds;          /* [n_rows]     adds_since_last_snapshot }                               */
     const uint32_t* tick_cursor;  /* [n_rows]     ticks of this stream pushed before the snapshot */
     const uint32_t* trade_cursor; /* [n_rows]     trades of this stream pushed before the snapshot*/
     /* tick axis, n_ticks = tick_offsets[S] */
@@ -212,6 +212,19 @@ int mrp_fg_download(mrp_fg_ctx* ctx, double* raw, double* norm, int8_t* bid_dir,
 /* Copy the rows [row_begin, row_end) of the RAW and z-scored features to HOST buffers laid out [19][row_end - row_begin]
  * (what a time shard keeps after dropping its halo, or the newest row of a trailing window); NULL = skip. */
 int mrp_fg_download_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, double* raw, double* norm, void* stream);
+
+/* The rolling state FeatureEngine keeps between snapshots, derived on the device from per-event arrays instead of staged per row
+ * (ref: data_ingestion/src/core/feature_engine.cpp:87-150).  Call after bind / upload and before mrp_fg_run; the view may then
+ * leave buy_vol / sell_vol / adds NULL (28 bytes per row less on the wire).
+ *   trade_size  [n_trades] int32, aligned with trade_dir: the sizes FeatureEngine::update_trade received (order_engine.cpp:104).
+ *               rolling_buy_volume / rolling_sell_volume of a snapshot become the exact integer sums over the last dir_window
+ *               trades before its trade cursor, with the reference's eviction rule (feature_engine.cpp:95-110: a leaving trade is
+ *               subtracted from buy when its direction is > 0, from sell otherwise).  NULL = keep the bound arrays.
+ *   add_cursor  [n_rows] uint32: 'A' events of the stream before the snapshot; adds_since_last_snapshot = the difference of
+ *               consecutive cursors (feature_engine.cpp:74-75,119-122).  NULL = keep the bound array.
+ *   memory      MRP_MEM_DEVICE or MRP_MEM_HOST for the two pointers.
+ * (The tick directions of feature_engine.cpp:134-141 are always derived on the device from the midprice ticks.) */
+int mrp_fg_build_state(mrp_fg_ctx* ctx, const int32_t* trade_size, const uint32_t* add_cursor, int memory, void* stream);
 
 /* ONE STREAM SPLIT BY TIME ACROSS GPUs (BASELINE.json configs[4]).  Every state of the path has finite memory, so a shard that
  * is preceded by mrp_fg_halo_rows() rows of its stream (and one window of ticks / trades in front of those) reproduces the

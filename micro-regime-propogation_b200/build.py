@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(CSRC, "libmrp_fg.so")
-CU_SOURCES = ["kernels_window.cu", "kernels_row.cu", "kernels_norm.cu", "kernels_volvol.cu", "api.cu"]
+CU_SOURCES = ["kernels_window.cu", "kernels_row.cu", "kernels_norm.cu", "kernels_volvol.cu", "kernels_state.cu", "api.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3",

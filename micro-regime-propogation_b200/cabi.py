@@ -60,6 +60,7 @@ class SoaView(C.Structure):
 
 _ARRAY_FIELDS = ("ts_ns", "bid_px", "ask_px", "bid_sz", "ask_sz", "buy_vol", "sell_vol", "adds",
                  "tick_cursor", "trade_cursor", "mid", "spread", "trade_dir")
+_OPTIONAL_FIELDS = ("buy_vol", "sell_vol", "adds")   # mrp_fg_build_state can derive them
 _HOST_DTYPES = {
     "ts_ns": np.uint64, "bid_px": np.float64, "ask_px": np.float64, "bid_sz": np.int32, "ask_sz": np.int32,
     "buy_vol": np.float64, "sell_vol": np.float64, "adds": np.int32, "tick_cursor": np.uint32,
@@ -81,6 +82,8 @@ class HostView:
     def __init__(self, batch: Dict[str, object]):
         self.arrays = {}
         for k in _ARRAY_FIELDS:
+            if k in _OPTIONAL_FIELDS and batch.get(k) is None:
+                continue   # derived on the device (Engine.build_state)
             a = np.ascontiguousarray(np.asarray(batch[k]), dtype=_HOST_DTYPES[k])
             self.arrays[k] = a
         for k in ("row_offsets", "tick_offsets", "trade_offsets"):
@@ -108,7 +111,9 @@ def device_view(batch: Dict[str, object]) -> "tuple[SoaView, list]":
         setattr(v, k, a.ctypes.data)
     v.n_streams = len(keep[0]) - 1
     for k in _ARRAY_FIELDS:
-        t = batch[k]
+        t = batch.get(k) if k in _OPTIONAL_FIELDS else batch[k]
+        if t is None:
+            continue   # derived on the device (Engine.build_state)
         assert t.is_cuda and t.is_contiguous(), k
         keep.append(t)
         setattr(v, k, t.data_ptr())
@@ -149,6 +154,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_moments_rows.argtypes = [vp, i64, i64, vp, vp]
     lib.mrp_fg_norm_moments_rows.argtypes = [vp, i64, i64, vp, vp]
     lib.mrp_fg_halo_rows.argtypes = [vp]
+    lib.mrp_fg_build_state.argtypes = [vp, vp, vp, i32, vp]
     lib.mrp_fg_halo_query.argtypes = [vp, C.POINTER(HaloInfo), vp]
     lib.mrp_fg_halo_export.argtypes = [vp, vp, i64, C.POINTER(vp), C.POINTER(HaloInfo), vp]
     lib.mrp_fg_halo_import.argtypes = [vp, vp, C.POINTER(HaloInfo), vp]
@@ -224,6 +230,27 @@ class Engine:
             raw_ptr, norm_ptr = raw.ctypes.data, norm.ctypes.data
         self._check(self.lib.mrp_fg_process_host(self.ctx, C.byref(hv.view), C.c_void_p(raw_ptr), C.c_void_p(norm_ptr), chunk_rows))
         return raw, norm
+
+    # -- rolling state from per-event arrays (mrp_fg_build_state)
+    def build_state(self, trade_size=None, add_cursor=None, stream: int = 0):
+        """trade_size: int32 [n_trades], add_cursor: uint32 [n_rows]; numpy arrays (host) or CUDA torch tensors (device), or None."""
+        def ptr(a, dt):
+            if a is None:
+                return 0, None
+            if isinstance(a, np.ndarray):
+                a = np.ascontiguousarray(a, dtype=dt)
+                return a.ctypes.data, a
+            assert a.is_cuda and a.is_contiguous()
+            return a.data_ptr(), a
+        ps, ks = ptr(trade_size, np.int32)
+        pa, ka = ptr(add_cursor, np.uint32)
+        host = any(isinstance(x, np.ndarray) for x in (ks, ka))
+        dev = any(x is not None and not isinstance(x, np.ndarray) for x in (ks, ka))
+        assert not (host and dev), "trade_size and add_cursor must live in the same memory"
+        self._state_keep = (ks, ka)
+        self._check(self.lib.mrp_fg_build_state(self.ctx, C.c_void_p(ps), C.c_void_p(pa), MEM_HOST if host else MEM_DEVICE, C.c_void_p(stream)))
+        if host:
+            self.sync(stream)   # the staging copies read the numpy arrays
 
     # -- compute
     def run(self, stream: int = 0):

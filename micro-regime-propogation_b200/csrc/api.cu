@@ -22,6 +22,10 @@ cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*
 int col_moment_blocks(int64_t N);
 cudaError_t launch_col_moments(const double* x, int64_t col_stride, int64_t N, double* part, cudaStream_t st);
 cudaError_t launch_standardize(const double* x, double* out, int64_t N, const double* mean_scale_dev, cudaStream_t st);
+size_t state_prefix_bytes(int64_t T);
+size_t state_partial_bytes(int64_t T);
+cudaError_t launch_build_state(const int8_t* dir, const int32_t* size, int64_t T, const uint32_t* jcur, const uint32_t* add_cursor, int64_t n,
+                               int window, unsigned long long* part, unsigned long long* P, double* buy, double* sell, int32_t* adds, cudaStream_t st);
 cudaError_t launch_rolling(const double* x, int64_t x_stride, double* out, int64_t out_stride, const void* tiles, int ntiles, double* tot,
                            const int32_t* windows_dev, int njobs, int tile_rows, int mode, cudaStream_t st);
 bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, int* trade_ring, int* chunk_trades, size_t* smem);
@@ -144,6 +148,8 @@ struct mrp_fg_ctx {
     cudaEvent_t lane_done[2] = {nullptr, nullptr};
     uint32_t* lane_cursors[2] = {nullptr, nullptr};   // pinned: rebased tick / trade cursors of the chunk in flight
     size_t lane_cursor_cap[2] = {0, 0};
+    // rolling state derived on the device (mrp_fg_build_state)
+    DevBuf b_st_buy, b_st_sell, b_st_adds, b_st_size, b_st_addcur, b_st_part, b_st_prefix;
     // time-shard halo (mrp_fg_halo_export): packed tail of the bound stream
     DevBuf b_halo;
     mrp_fg_halo_info halo_info{};
@@ -304,9 +310,9 @@ int check_view(const mrp_fg_ctx* c, const mrp_fg_soa_view* v, int want_memory) {
             return fail(MRP_FG_ERR_INVALID, "a stream may hold at most 2^32-65536 ticks / trades (cursors are uint32); split longer streams by time (timeshard)");
     }
     const int64_t N = v->row_offsets[S];
-    if (N > 0 && (!v->ts_ns || !v->bid_px || !v->ask_px || !v->bid_sz || !v->ask_sz || !v->buy_vol || !v->sell_vol || !v->adds ||
-                  !v->tick_cursor || !v->trade_cursor))
+    if (N > 0 && (!v->ts_ns || !v->bid_px || !v->ask_px || !v->bid_sz || !v->ask_sz || !v->tick_cursor || !v->trade_cursor))
         return fail(MRP_FG_ERR_INVALID, "a snapshot-axis array is NULL");
+    // buy_vol / sell_vol / adds may be NULL: mrp_fg_build_state derives them from per-event arrays before mrp_fg_run
     if (v->tick_offsets[S] > 0 && (!v->mid || !v->spread)) return fail(MRP_FG_ERR_INVALID, "mid / spread are NULL");
     if (v->trade_offsets[S] > 0 && !v->trade_dir) return fail(MRP_FG_ERR_INVALID, "trade_dir is NULL");
     return MRP_FG_OK;
@@ -494,7 +500,8 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
                       &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison,
                       &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win, &c->b_mom_part, &c->b_scaled,
-                      &c->b_mean_scale, &c->b_halo};
+                      &c->b_mean_scale, &c->b_halo, &c->b_st_buy, &c->b_st_sell, &c->b_st_adds, &c->b_st_size, &c->b_st_addcur,
+                      &c->b_st_part, &c->b_st_prefix};
     for (DevBuf* b : bufs) b->release();
     c->h_tables.release();
     if (c->tables_ready) cudaEventDestroy(c->tables_ready);
@@ -586,6 +593,7 @@ int upload_impl(mrp_fg_ctx* c, const mrp_fg_soa_view* v, int64_t level_stride, c
     };
     for (const Copy& cp : copies) {
         const size_t bytes = (size_t)cp.count * cp.elem * (cp.levels ? (size_t)L : 1u);
+        if (!cp.src && bytes) continue;   // an omitted rolling-state array (mrp_fg_build_state supplies it)
         if ((rc = cp.b->ensure(bytes))) return rc;
         if (!bytes) continue;
         if (cp.levels && level_stride != N)
@@ -601,9 +609,9 @@ int upload_impl(mrp_fg_ctx* c, const mrp_fg_soa_view* v, int64_t level_stride, c
     in.ask_px = static_cast<const double*>(c->b_apx.p);
     in.bid_sz = static_cast<const int32_t*>(c->b_bsz.p);
     in.ask_sz = static_cast<const int32_t*>(c->b_asz.p);
-    in.buy = static_cast<const double*>(c->b_buy.p);
-    in.sell = static_cast<const double*>(c->b_sell.p);
-    in.adds = static_cast<const int32_t*>(c->b_adds.p);
+    in.buy = v->buy_vol ? static_cast<const double*>(c->b_buy.p) : nullptr;
+    in.sell = v->sell_vol ? static_cast<const double*>(c->b_sell.p) : nullptr;
+    in.adds = v->adds ? static_cast<const int32_t*>(c->b_adds.p) : nullptr;
     in.kcur = static_cast<const uint32_t*>(c->b_kcur.p);
     in.jcur = static_cast<const uint32_t*>(c->b_jcur.p);
     in.mid = static_cast<const double*>(c->b_mid.p);
@@ -637,6 +645,8 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
     const int S = v->n_streams, L = c->p.depth_levels;
     const int64_t NT = v->row_offsets[S];
     if (NT == 0) return MRP_FG_OK;
+    if (!v->buy_vol || !v->sell_vol || !v->adds)
+        return fail(MRP_FG_ERR_INVALID, "mrp_fg_process_host needs buy_vol / sell_vol / adds in the view (mrp_fg_build_state works on a bound batch)");
     const int64_t H = mrp_fg_halo_rows(c);
     if (chunk_rows <= 0) chunk_rows = 4 << 20;
     const int64_t wmax = std::max(c->p.mid_window, c->p.dir_window + 1);
@@ -739,6 +749,8 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
     if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
     if (!c->bound) return fail(MRP_FG_ERR_STATE, "mrp_fg_run before mrp_fg_bind_inputs / mrp_fg_upload");
     if (c->n_rows == 0) return MRP_FG_OK;
+    if (!c->in.buy || !c->in.sell || !c->in.adds)
+        return fail(MRP_FG_ERR_STATE, "rolling_buy_volume / rolling_sell_volume / adds are not bound: pass them in the view or call mrp_fg_build_state");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const DevSegment* segs = static_cast<const DevSegment*>(c->b_segs.p);
@@ -1094,6 +1106,55 @@ int halo_geometry(mrp_fg_ctx* c, cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+// the rolling state FeatureEngine keeps between snapshots, from per-event arrays (kernels_state.cu)
+int mrp_fg_build_state(mrp_fg_ctx* c, const int32_t* trade_size, const uint32_t* add_cursor, int memory, void* stream) {
+    if (!c) return fail(MRP_FG_ERR_INVALID, "ctx is NULL");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "mrp_fg_build_state after mrp_fg_bind_inputs / mrp_fg_upload");
+    if (memory != MRP_MEM_DEVICE && memory != MRP_MEM_HOST) return fail(MRP_FG_ERR_INVALID, "memory must be MRP_MEM_DEVICE or MRP_MEM_HOST");
+    if (!trade_size && !add_cursor) return MRP_FG_OK;
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t N = c->n_rows, T = c->n_trades;
+    int rc;
+    if (memory == MRP_MEM_HOST) {   // stage the per-event arrays
+        if (trade_size) {
+            if ((rc = c->b_st_size.ensure((size_t)T * 4))) return rc;
+            if (T) CU(cudaMemcpyAsync(c->b_st_size.p, trade_size, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+            trade_size = static_cast<const int32_t*>(c->b_st_size.p);
+        }
+        if (add_cursor) {
+            if ((rc = c->b_st_addcur.ensure((size_t)N * 4))) return rc;
+            if (N) CU(cudaMemcpyAsync(c->b_st_addcur.p, add_cursor, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+            add_cursor = static_cast<const uint32_t*>(c->b_st_addcur.p);
+        }
+    }
+    if (trade_size) {
+        if ((rc = c->b_st_buy.ensure((size_t)N * 8))) return rc;
+        if ((rc = c->b_st_sell.ensure((size_t)N * 8))) return rc;
+    }
+    if (add_cursor && (rc = c->b_st_adds.ensure((size_t)N * 4))) return rc;
+    int64_t tmax = 0;
+    for (int s = 0; s < c->n_streams; ++s) tmax = std::max(tmax, c->trade_off[s + 1] - c->trade_off[s]);
+    if (trade_size) {
+        if ((rc = c->b_st_part.ensure(state_partial_bytes(tmax)))) return rc;
+        if ((rc = c->b_st_prefix.ensure(state_prefix_bytes(tmax)))) return rc;
+    }
+    for (int s = 0; s < c->n_streams; ++s) {   // streams one after the other on `st`: they share the prefix scratch
+        const int64_t r0 = c->row_off[s], n = c->row_off[s + 1] - r0, j0 = c->trade_off[s], Ts = c->trade_off[s + 1] - j0;
+        CU(launch_build_state(c->in.tdir + j0, trade_size ? trade_size + j0 : nullptr, Ts, c->in.jcur + r0, add_cursor ? add_cursor + r0 : nullptr, n,
+                              c->p.dir_window, static_cast<unsigned long long*>(c->b_st_part.p), static_cast<unsigned long long*>(c->b_st_prefix.p),
+                              trade_size ? static_cast<double*>(c->b_st_buy.p) + r0 : nullptr, trade_size ? static_cast<double*>(c->b_st_sell.p) + r0 : nullptr,
+                              add_cursor ? static_cast<int32_t*>(c->b_st_adds.p) + r0 : nullptr, st));
+        c->launches += trade_size ? 4 : 1;
+    }
+    if (trade_size) {
+        c->in.buy = static_cast<const double*>(c->b_st_buy.p);
+        c->in.sell = static_cast<const double*>(c->b_st_sell.p);
+    }
+    if (add_cursor) c->in.adds = static_cast<const int32_t*>(c->b_st_adds.p);
+    return MRP_FG_OK;
+}
 
 int mrp_fg_halo_query(mrp_fg_ctx* c, mrp_fg_halo_info* info, void* stream) {
     if (!c || !info) return fail(MRP_FG_ERR_INVALID, "NULL argument");
