@@ -25,6 +25,7 @@ GpuFeatureProcessor::GpuFeatureProcessor(std::string symbol, int device, const m
 }
 
 GpuFeatureProcessor::~GpuFeatureProcessor() {
+    detach(this);
     if (ctx_) mrp_fg_destroy(ctx_);
 }
 
@@ -220,6 +221,37 @@ void GpuFeatureProcessor::flush_pair(GpuFeatureProcessor& base, GpuFeatureProces
     }
     base.clear();
     future.clear();
+}
+
+// ---- trade hook registry (a pipeline holds two engines; a flat list is enough)
+namespace {
+struct Attached {
+    const void* engine;
+    GpuFeatureProcessor* processor;
+};
+std::vector<Attached>& attached() {
+    static std::vector<Attached> v;
+    return v;
+}
+}  // namespace
+
+void GpuFeatureProcessor::attach(const void* feature_engine, GpuFeatureProcessor* processor) {
+    for (Attached& a : attached())
+        if (a.engine == feature_engine) {
+            a.processor = processor;
+            return;
+        }
+    attached().push_back({feature_engine, processor});
+}
+
+void GpuFeatureProcessor::detach(const GpuFeatureProcessor* processor) {
+    for (Attached& a : attached())
+        if (a.processor == processor) a.processor = nullptr;
+}
+
+void mrp_trade_hook(const void* feature_engine, std::int8_t direction) {
+    for (const Attached& a : attached())
+        if (a.engine == feature_engine && a.processor) a.processor->on_trade(direction);
 }
 
 }  // namespace microregime

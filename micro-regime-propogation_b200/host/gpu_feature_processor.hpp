@@ -66,6 +66,12 @@ public:
 
     const std::string& symbol() const { return symbol_; }
 
+    // The trade hook of INTEGRATION.md §3: OrderEngine::process_event only sees the FeatureEngine of the event's instrument
+    // (order_engine.cpp:34,107), so the pipeline registers which staging object belongs to which engine once, and the one
+    // line added next to `feature_engine->update_trade(price, size, direction)` forwards the direction.
+    static void attach(const void* feature_engine, GpuFeatureProcessor* processor);
+    static void detach(const GpuFeatureProcessor* processor);   // called by the destructor
+
 private:
     void run(std::vector<double>& raw, std::vector<double>& norm);
     void clear();
@@ -89,5 +95,8 @@ private:
     std::vector<double> mid_, spread_;
     std::vector<std::int8_t> tdir_;
 };
+
+// next to feature_engine->update_trade(...): forwards to the GpuFeatureProcessor attached to that engine (no-op when none is)
+void mrp_trade_hook(const void* feature_engine, std::int8_t direction);
 
 }  // namespace microregime
