@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 
+#include "binary_sink.hpp"
 #include "csv_writer.hpp"
 #include "gpu_feature_processor.hpp"
 
@@ -33,6 +34,33 @@ int mrp_host_write_csv(const char* project_root, const char* base_filename, uint
                 }
                 w.ingest_feature_set(instrument, grid_ts[r], a, b);
             }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// The same rows through BinarySink (NPY files in the reference's directory).  bulk = 0: one ingest_feature_set call per row.
+int mrp_host_write_binary(const char* project_root, const char* base_filename, uint64_t interval_ns, const char* date, const char* instrument,
+                          int64_t n, const uint64_t* grid_ts, const uint64_t* row_ts, const double* raw, const double* norm, int bulk) {
+    try {
+        microregime::BinarySink w(base_filename, interval_ns, date, project_root);
+        if (bulk) {
+            w.write_columns(instrument, grid_ts, raw, norm, n);
+        } else {
+            microregime::FeatureSet a, b;
+            for (int64_t r = 0; r < n; ++r) {
+                a.timestamp_ns = b.timestamp_ns = row_ts ? row_ts[r] : grid_ts[r];
+                a.instrument = b.instrument = instrument;
+                for (int c = 0; c < 19; ++c) {
+                    a.*(mrp_host::kFeatureMembers[c]) = raw[(size_t)c * n + r];
+                    b.*(mrp_host::kFeatureMembers[c]) = norm[(size_t)c * n + r];
+                }
+                w.ingest_feature_set(instrument, grid_ts[r], a, b);
+            }
+            w.close();
         }
         return 0;
     } catch (const std::exception& e) {

@@ -24,6 +24,7 @@ def load_host() -> C.CDLL:
         lib = C.CDLL(HOST_LIB_PATH)
         lib.mrp_host_last_error.restype = C.c_char_p
         lib.mrp_host_write_csv.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int]
+        lib.mrp_host_write_binary.argtypes = lib.mrp_host_write_csv.argtypes
         lib.mrp_host_features_to_csv.argtypes = [C.POINTER(SoaView), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64,
                                                  C.c_uint64, C.c_int, C.c_int]
         lib.mrp_host_rows_by_reference_calls.argtypes = [C.POINTER(SoaView), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
@@ -48,6 +49,35 @@ def write_csv(project_root: str, base_filename: str, interval_ns: int, date: str
     if rc != 0:
         raise RuntimeError(lib.mrp_host_last_error().decode())
     return csv_directory(project_root, interval_ns, date)
+
+
+def write_binary(project_root: str, base_filename: str, interval_ns: int, date: str, instrument: str, grid_ts: np.ndarray,
+                 raw: np.ndarray, norm: np.ndarray, row_ts: Optional[np.ndarray] = None, bulk: bool = True) -> str:
+    """The rows through microregime::BinarySink: NPY files in the reference's directory (np.load(..., mmap_mode="r"))."""
+    lib = load_host()
+    grid_ts = np.ascontiguousarray(grid_ts, dtype=np.uint64)
+    raw = np.ascontiguousarray(raw, dtype=np.float64)
+    norm = np.ascontiguousarray(norm, dtype=np.float64)
+    rts = np.ascontiguousarray(row_ts, dtype=np.uint64) if row_ts is not None else None
+    rc = lib.mrp_host_write_binary(project_root.encode(), base_filename.encode(), interval_ns, date.encode(), instrument.encode(),
+                                   raw.shape[1], grid_ts.ctypes.data, rts.ctypes.data if rts is not None else None,
+                                   raw.ctypes.data, norm.ctypes.data, int(bulk))
+    if rc != 0:
+        raise RuntimeError(lib.mrp_host_last_error().decode())
+    return csv_directory(project_root, interval_ns, date)
+
+
+def load_binary(directory: str, base_filename: str, mmap: bool = True):
+    """What the Python stage does instead of pandas.read_csv(<base>_norm.csv): (timestamps [n], raw [19, n], norm [19, n], column names),
+    memory-mapped.  `norm.T` is the (n, 19) matrix classifier.py:15-37 builds from the CSV."""
+    import json
+
+    mode = "r" if mmap else None
+    with open(os.path.join(directory, base_filename + "_columns.json")) as f:
+        meta = json.load(f)
+    return (np.load(os.path.join(directory, base_filename + "_timestamp_ns.npy"), mmap_mode=mode),
+            np.load(os.path.join(directory, base_filename + "_raw.npy"), mmap_mode=mode),
+            np.load(os.path.join(directory, base_filename + "_norm.npy"), mmap_mode=mode), meta)
 
 
 def features_to_csv(hv: HostView, project_root: str, base_filename: str, date: str, instrument: str, first_grid_ns: int,

@@ -104,3 +104,30 @@ def test_graft_entry_build_passes():
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build(); print('ok')"], cwd=ROOT, capture_output=True, text=True,
                        timeout=900)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_cmake_sm_100a_target_builds(tmp_path):
+    """The CMake target the north star names: configure + build both libraries, sm_100a code only, every ABI symbol exported."""
+    import shutil
+    import subprocess
+
+    cmake, ninja, nvcc = shutil.which("cmake"), shutil.which("ninja"), shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not (cmake and ninja and os.path.exists(nvcc)):
+        pytest.skip("cmake / ninja / nvcc not available")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    gxx = shutil.which("g++")
+    cfg = [cmake, "-S", ROOT, "-B", str(tmp_path), "-G", "Ninja", f"-DCMAKE_CUDA_COMPILER={nvcc}", f"-DCMAKE_CXX_COMPILER={gxx}",
+           f"-DCMAKE_CUDA_HOST_COMPILER={gxx}"]
+    if os.path.isdir("/root/reference/feature_generation/include"):
+        cfg.append("-DMRP_REFERENCE_ROOT=/root/reference")     # the adaptor against the reference's own headers
+    subprocess.run(cfg, check=True, env=env, capture_output=True)
+    subprocess.run([cmake, "--build", str(tmp_path)], check=True, env=env, capture_output=True)
+    lib = C.CDLL(os.path.join(str(tmp_path), "libmrp_fg.so"))
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    dump = subprocess.run([os.path.join(os.path.dirname(nvcc), "cuobjdump"), "--list-elf", os.path.join(str(tmp_path), "libmrp_fg.so")],
+                          capture_output=True, text=True).stdout
+    archs = {l.split(".")[-2] for l in dump.splitlines() if ".cubin" in l}
+    assert archs == {"sm_100a"}, archs

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+import mrp_b200
 from mrp_b200 import hostlib
 from oracle import binding as ob
 
@@ -66,3 +67,31 @@ def test_adaptor_refuses_to_run_without_a_gpu(tmp_path):
     hv = mrp_b200.HostView(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=16, seed=1)])))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         hostlib.features_to_csv(hv, str(tmp_path), "base_SYN", "20250505", "SYN", 0, 500_000_000)
+
+
+def test_binary_sink_is_mappable_and_equals_the_csv(tmp_path):
+    """microregime::BinarySink (SURVEY.md §8 f4): NPY files in the reference's directory, np.load(mmap_mode="r")-able, holding
+    the doubles themselves (the CSV's 16 significant digits lose the last bit or two of most of them)."""
+    import pandas as pd
+
+    from mrp_b200 import hostlib
+
+    rng = np.random.default_rng(3)
+    n = 1234
+    raw = rng.standard_normal((19, n)) * 10.0 ** rng.integers(-12, 6, (19, 1))
+    norm = rng.standard_normal((19, n))
+    raw[3, 5] = np.nan
+    norm[7, 9] = np.inf
+    grid = (1_746_453_700_000_000_000 + np.arange(n) * 500_000_000).astype(np.uint64)
+    d1 = hostlib.write_binary(str(tmp_path), "base_SYN", 500_000_000, "20250505", "SYN", grid, raw, norm, bulk=True)
+    ts, r1, z1, meta = hostlib.load_binary(d1, "base_SYN")
+    assert isinstance(r1, np.memmap) and r1.shape == (19, n) and meta["columns"] == list(mrp_b200.FEATURES) and meta["rows"] == n
+    assert np.array_equal(ts, grid) and np.array_equal(r1, raw, equal_nan=True) and np.array_equal(z1, norm, equal_nan=True)
+    # the per-row DataReciever path writes the same files
+    d2 = hostlib.write_binary(str(tmp_path / "rows"), "base_SYN", 500_000_000, "20250505", "SYN", grid, raw, norm, bulk=False)
+    _, r2, z2, _ = hostlib.load_binary(d2, "base_SYN", mmap=False)
+    assert np.array_equal(r2, raw, equal_nan=True) and np.array_equal(z2, norm, equal_nan=True)
+    # and the CSV of the same rows parses to the same matrix (what classifier.py would have read)
+    d3 = hostlib.write_csv(str(tmp_path / "csv"), "base_SYN", 500_000_000, "20250505", "SYN", grid, raw, norm, bulk=True)
+    df = pd.read_csv(os.path.join(d3, "base_SYN_norm.csv"))
+    assert np.allclose(df[list(mrp_b200.FEATURES)].to_numpy().T, np.asarray(z1), rtol=2e-15, atol=0, equal_nan=True)
