@@ -208,6 +208,7 @@ def timeshard_leg(args, rank: int, world: int, dev, rows_per_gpu: int, steps: in
     for _ in range(warmup):
         ts.exchange()
         eng.run(stream)
+        ts.carry_poison()
     barrier()
     launches0 = eng.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
@@ -217,6 +218,7 @@ def timeshard_leg(args, rank: int, world: int, dev, rows_per_gpu: int, steps: in
         sent = ts.exchange()
         ev[2 * i + 1].record()
         eng.run(stream)
+        ts.carry_poison()   # the normaliser's "poisoned for ever" state crosses shard boundaries too: one all-gather of 57 integers per rank
         ev[2 * i + 2].record()
     barrier()
     ms = ev[0].elapsed_time(ev[-1]) / steps

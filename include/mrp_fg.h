@@ -52,7 +52,8 @@ extern "C" {
 #define MRP_FG_ABI_VERSION 7   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
                                   5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize;
                                   6: + mrp_fg_halo_rows(_for), mrp_fg_moments_rows, mrp_fg_norm_moments_rows;
-                                  7: + mrp_fg_halo_query, mrp_fg_halo_export, mrp_fg_halo_import, mrp_fg_build_state */
+                                  7: + mrp_fg_halo_query, mrp_fg_halo_export, mrp_fg_halo_import, mrp_fg_build_state,
+                                     mrp_fg_poison_state, mrp_fg_poison_apply */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -188,7 +189,7 @@ int mrp_fg_upload(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, void* stream);
  * computed and downloaded on two alternating device buffer sets / CUDA streams, so PCIe runs in both directions while
  * the SMs compute.  A chunk is preceded by a halo (norm_window + EMA warm-up rows, one window of ticks / trades)
  * re-read from the host; results equal the single-shot upload / run / download sequence to within the EMA warm-up
- * (< 1e-17 of the column scale).  raw, norm: HOST double [19][n_rows] (pinned memory recommended).  Synchronous.
+ * (< 1e-17 of the column scale), including the normaliser's "poisoned for ever" columns, whose state is carried across chunks.  raw, norm: HOST double [19][n_rows] (pinned memory recommended).  Synchronous.
  * Replaces, for every row: FeatureProcessor::GetRawFeatureSet + GetProcessedFeatureSet (feature_processor.cpp:11-29). */
 int mrp_fg_process_host(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, double* raw, double* norm, int64_t chunk_rows);
 
@@ -254,6 +255,16 @@ typedef struct mrp_fg_halo_info {
 int mrp_fg_halo_query(mrp_fg_ctx* ctx, mrp_fg_halo_info* info, void* stream);
 int mrp_fg_halo_export(mrp_fg_ctx* ctx, void* dst_device, int64_t dst_capacity, const void** packed_device, mrp_fg_halo_info* info, void* stream);
 int mrp_fg_halo_import(mrp_fg_ctx* ctx, const void* packed_device, const mrp_fg_halo_info* info, void* stream);
+
+/* A NaN (or an infinity, once evicted) poisons the reference's running sums FOR EVER (feature_normalizer.cpp:37-51): every later
+ * z-score of that column is NaN.  Within one bound stream mrp_fg_run reproduces this; across time shards the state must travel:
+ *   mrp_fg_poison_state  after mrp_fg_run: state[s*57 + c*3 + {0,1,2}] = first NaN / +inf / -inf row of column c of stream s in
+ *                        ABSOLUTE stream rows (row_base[s] = absolute row of the bound stream's first row, NULL = 0), INT64_MAX = none.
+ *   mrp_fg_poison_apply  rewrites the bound rows' z-scores for what happened BEFORE the shard: state_before = the element-wise
+ *                        minimum of the states of all earlier shards (an all-gather of 57 integers per rank).  Synchronises.
+ * (mrp_fg_process_host carries the state from chunk to chunk by itself.) */
+int mrp_fg_poison_state(mrp_fg_ctx* ctx, const int64_t* row_base, int64_t* state, void* stream);
+int mrp_fg_poison_apply(mrp_fg_ctx* ctx, const int64_t* state_before, const int64_t* row_base, void* stream);
 
 /* EXTENSION WITHOUT A REFERENCE COUNTERPART (BASELINE.json configs[3]: "vol-of-vol over 3 horizons"; the reference has no
  * such feature, SURVEY.md 0.1 D2 — PARITY UNPINNED: its only checker is the restatement of this definition in oracle/).

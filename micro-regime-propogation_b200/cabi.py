@@ -154,6 +154,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.mrp_fg_moments_rows.argtypes = [vp, i64, i64, vp, vp]
     lib.mrp_fg_norm_moments_rows.argtypes = [vp, i64, i64, vp, vp]
     lib.mrp_fg_halo_rows.argtypes = [vp]
+    lib.mrp_fg_poison_state.argtypes = [vp, vp, vp, vp]
+    lib.mrp_fg_poison_apply.argtypes = [vp, vp, vp, vp]
     lib.mrp_fg_build_state.argtypes = [vp, vp, vp, i32, vp]
     lib.mrp_fg_halo_query.argtypes = [vp, C.POINTER(HaloInfo), vp]
     lib.mrp_fg_halo_export.argtypes = [vp, vp, i64, C.POINTER(vp), C.POINTER(HaloInfo), vp]
@@ -327,6 +329,22 @@ class Engine:
     def halo_import(self, packed_ptr: int, info: "HaloInfo", stream: int = 0):
         """Write a packed halo into the front (headroom) of the bound stream (mrp_fg_halo_import)."""
         self._check(self.lib.mrp_fg_halo_import(self.ctx, C.c_void_p(packed_ptr), C.byref(info), C.c_void_p(stream)))
+
+    # -- the normaliser's "poisoned for ever" state across time shards
+    def poison_state(self, row_base=None, stream: int = 0) -> np.ndarray:
+        """[n_streams, 19, 3] first NaN / +inf / -inf row per column in absolute stream rows (int64 max = none)."""
+        n_streams = len(np.atleast_1d(row_base)) if row_base is not None else 1
+        st = np.empty((n_streams, NUM_FEATURES, 3), np.int64)
+        rb = np.ascontiguousarray(np.atleast_1d(row_base), dtype=np.int64) if row_base is not None else None
+        self._check(self.lib.mrp_fg_poison_state(self.ctx, C.c_void_p(rb.ctypes.data) if rb is not None else C.c_void_p(),
+                                                 C.c_void_p(st.ctypes.data), C.c_void_p(stream)))
+        return st
+
+    def poison_apply(self, state_before: np.ndarray, row_base=None, stream: int = 0):
+        sb = np.ascontiguousarray(state_before, dtype=np.int64)
+        rb = np.ascontiguousarray(np.atleast_1d(row_base), dtype=np.int64) if row_base is not None else None
+        self._check(self.lib.mrp_fg_poison_apply(self.ctx, C.c_void_p(sb.ctypes.data), C.c_void_p(rb.ctypes.data) if rb is not None else C.c_void_p(),
+                                                 C.c_void_p(stream)))
 
     def halo_rows(self) -> int:
         """Rows of history a time shard / host chunk needs in front of its own rows (mrp_fg_halo_rows)."""

@@ -3,7 +3,9 @@
 // Host-side plumbing only: argument checking, device buffers, the segment / tile tables, launch order
 // and timing.  No feature arithmetic lives here and there is no CPU fallback: every entry point that
 // needs the GPU fails with MRP_FG_ERR_CUDA when the device or a kernel is unavailable.
+#include <climits>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,7 +18,9 @@
 namespace mrp {
 cudaError_t launch_windows(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
 cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
-cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, void*, const int64_t*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, void*, const int64_t*, int, long long*, const long long*,
+                             const DevParams&, cudaStream_t);
+cudaError_t launch_norm_poison(const DevOutputs&, int64_t, void*, const int64_t*, int, long long*, const long long*, const DevParams&, cudaStream_t);
 size_t norm_poison_bytes(int);
 cudaError_t launch_normalize_faithful(const DevOutputs&, int64_t, const int64_t*, int, const DevParams&, cudaStream_t);
 int col_moment_blocks(int64_t N);
@@ -148,6 +152,13 @@ struct mrp_fg_ctx {
     cudaEvent_t lane_done[2] = {nullptr, nullptr};
     uint32_t* lane_cursors[2] = {nullptr, nullptr};   // pinned: rebased tick / trade cursors of the chunk in flight
     size_t lane_cursor_cap[2] = {0, 0};
+    long long* pin_carry = nullptr;        // pinned: [57] "none" (resets the carry at a stream's start) + [2] the lanes' slice_row0
+    cudaEvent_t run_chain = nullptr;       // the chunks' kernels run in stream order across the two lanes (the carry is a chain)
+    // non-finite state of the normaliser carried across time chunks / shards (k_norm_poison): [n_streams][19][3] absolute rows + the
+    // absolute row of each bound stream's first row; null = the bound streams start at their stream's first row
+    DevBuf b_carry, b_slice_row0;
+    long long* carry = nullptr;              // device; may point into another context's buffer (mrp_fg_process_host lanes)
+    const long long* slice_row0 = nullptr;   // device
     // rolling state derived on the device (mrp_fg_build_state)
     DevBuf b_st_buy, b_st_sell, b_st_adds, b_st_size, b_st_addcur, b_st_part, b_st_prefix;
     // time-shard halo (mrp_fg_halo_export): packed tail of the bound stream
@@ -322,6 +333,8 @@ int check_view(const mrp_fg_ctx* c, const mrp_fg_soa_view* v, int want_memory) {
 int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     const int S = v->n_streams;
     c->n_streams = S;
+    c->carry = nullptr;          // a new binding starts at its streams' first rows unless the caller says otherwise
+    c->slice_row0 = nullptr;
     c->row_off.assign(v->row_offsets, v->row_offsets + S + 1);
     c->tick_off.assign(v->tick_offsets, v->tick_offsets + S + 1);
     c->trade_off.assign(v->trade_offsets, v->trade_offsets + S + 1);
@@ -496,12 +509,14 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
         if (c->lane_done[i]) cudaEventDestroy(c->lane_done[i]);
         if (c->lane_cursors[i]) cudaFreeHost(c->lane_cursors[i]);
     }
+    if (c->pin_carry) cudaFreeHost(c->pin_carry);
+    if (c->run_chain) cudaEventDestroy(c->run_chain);
     DevBuf* bufs[] = {&c->b_ts, &c->b_bpx, &c->b_apx, &c->b_bsz, &c->b_asz, &c->b_buy, &c->b_sell, &c->b_adds, &c->b_kcur,
                       &c->b_jcur, &c->b_mid, &c->b_spread, &c->b_tdir, &c->b_raw, &c->b_norm, &c->b_bdir, &c->b_adir,
                       &c->b_counts, &c->b_segs, &c->b_tiles, &c->b_tile_tot, &c->b_flags, &c->b_tables, &c->b_row_off, &c->b_poison,
                       &c->b_vov_raw, &c->b_vov_norm, &c->b_vov_tiles, &c->b_vov_tot, &c->b_vov_win, &c->b_mom_part, &c->b_scaled,
                       &c->b_mean_scale, &c->b_halo, &c->b_st_buy, &c->b_st_sell, &c->b_st_adds, &c->b_st_size, &c->b_st_addcur,
-                      &c->b_st_part, &c->b_st_prefix};
+                      &c->b_st_part, &c->b_st_prefix, &c->b_carry, &c->b_slice_row0};
     for (DevBuf* b : bufs) b->release();
     c->h_tables.release();
     if (c->tables_ready) cudaEventDestroy(c->tables_ready);
@@ -660,6 +675,18 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
             CU(cudaEventCreateWithFlags(&c->lane_done[i], cudaEventDisableTiming));
         }
     }
+    // a NaN (or an evicted infinity) poisons the reference's running sums FOR EVER (feature_normalizer.cpp:37-51): the state
+    // travels from chunk to chunk in a device table; the chunks' kernels are chained across the two lanes by one event
+    constexpr int kCarry = MRP_FG_NUM_FEATURES * 3;
+    if (!c->pin_carry) {
+        CU(cudaMallocHost(reinterpret_cast<void**>(&c->pin_carry), sizeof(long long) * (kCarry + 2)));
+        for (int i = 0; i < kCarry; ++i) c->pin_carry[i] = 0x7fffffffffffffffll;
+        CU(cudaEventCreateWithFlags(&c->run_chain, cudaEventDisableTiming));
+    }
+    if ((rc = c->b_carry.ensure(sizeof(long long) * kCarry))) return rc;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = c->lane[i]->b_slice_row0.ensure(sizeof(long long)))) return rc;
+    bool chained = false;
     bool busy[2] = {false, false};
     int li = 0;
     // whatever way this function is left, nothing may still be reading the caller's inputs or writing the caller's outputs
@@ -727,7 +754,15 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
             mrp_fg_ctx* ln = c->lane[li];
             cudaStream_t st = c->lane_stream[li];
             if ((rc = upload_impl(ln, &sub, NT, st, false))) return rc;
+            if (chained) CU(cudaStreamWaitEvent(st, c->run_chain, 0));
+            if (a == r0) CU(cudaMemcpyAsync(c->b_carry.p, c->pin_carry, sizeof(long long) * kCarry, cudaMemcpyHostToDevice, st));   // a new stream: nothing poisoned yet
+            c->pin_carry[kCarry + li] = e0 - r0;            // the slice's first row, in stream rows (the lane's previous chunk has completed: busy[] above)
+            CU(cudaMemcpyAsync(ln->b_slice_row0.p, c->pin_carry + kCarry + li, sizeof(long long), cudaMemcpyHostToDevice, st));
+            ln->carry = static_cast<long long*>(c->b_carry.p);
+            ln->slice_row0 = static_cast<const long long*>(ln->b_slice_row0.p);
             if ((rc = mrp_fg_run(ln, st))) return rc;
+            CU(cudaEventRecord(c->run_chain, st));
+            chained = true;
             const int64_t skip = a - e0, own = b - a;
             CU(copy_pitched(raw + a, (size_t)NT * 8, ln->out.raw + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
                             cudaMemcpyDeviceToHost, st));
@@ -790,7 +825,7 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
     if (tm) CU(cudaEventRecord(c->ev[2], st));
     CU(launch_normalize(c->out, c->n_rows, static_cast<const DevTile*>(c->b_tiles.p), c->ntiles,
                         static_cast<double*>(c->b_tile_tot.p), static_cast<int*>(c->b_flags.p), c->b_poison.p,
-                        static_cast<const int64_t*>(c->b_row_off.p), c->n_streams, c->dp, st));
+                        static_cast<const int64_t*>(c->b_row_off.p), c->n_streams, c->carry, c->slice_row0, c->dp, st));
     c->launches += kNumKernels + 1;  // + the (normally empty) non-finite fix-up pass
     if (c->p.norm_mode == MRP_NORM_FAITHFUL) {
         CU(launch_normalize_faithful(c->out, c->n_rows, static_cast<const int64_t*>(c->b_row_off.p), c->n_streams, c->dp, st));
@@ -1153,6 +1188,47 @@ int mrp_fg_build_state(mrp_fg_ctx* c, const int32_t* trade_size, const uint32_t*
         c->in.sell = static_cast<const double*>(c->b_st_sell.p);
     }
     if (add_cursor) c->in.adds = static_cast<const int32_t*>(c->b_st_adds.p);
+    return MRP_FG_OK;
+}
+
+// The normaliser's non-finite state across time shards (see k_norm_poison): [n_streams][19][3] first NaN / +inf / -inf in ABSOLUTE stream rows
+int mrp_fg_poison_state(mrp_fg_ctx* c, const int64_t* row_base, int64_t* state, void* stream) {
+    if (!c || !state) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = c->n_streams;
+    std::vector<uint32_t> loc((size_t)S * MRP_FG_NUM_FEATURES * 3);
+    CU(cudaMemcpyAsync(loc.data(), c->b_poison.p, loc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int s = 0; s < S; ++s)
+        for (int k = 0; k < MRP_FG_NUM_FEATURES * 3; ++k) {
+            const uint32_t v = loc[(size_t)s * MRP_FG_NUM_FEATURES * 3 + k];
+            state[(size_t)s * MRP_FG_NUM_FEATURES * 3 + k] = v == 0xffffffffu ? INT64_MAX : (int64_t)v + (row_base ? row_base[s] : 0);
+        }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_poison_apply(mrp_fg_ctx* c, const int64_t* state_before, const int64_t* row_base, void* stream) {
+    if (!c || !state_before) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c->bound) return fail(MRP_FG_ERR_STATE, "no inputs bound");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int S = c->n_streams;
+    const size_t nst = (size_t)S * MRP_FG_NUM_FEATURES * 3;
+    int rc;
+    if ((rc = c->b_carry.ensure(nst * sizeof(long long)))) return rc;
+    if ((rc = c->b_slice_row0.ensure((size_t)S * sizeof(long long)))) return rc;
+    std::vector<long long> base((size_t)S, 0);
+    if (row_base)
+        for (int s = 0; s < S; ++s) base[s] = row_base[s];
+    // (pageable sources: staged by the runtime before the calls return)
+    CU(cudaMemcpyAsync(c->b_carry.p, state_before, nst * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->b_slice_row0.p, base.data(), (size_t)S * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CU(launch_norm_poison(c->out, c->n_rows, c->b_poison.p, static_cast<const int64_t*>(c->b_row_off.p), S, static_cast<long long*>(c->b_carry.p),
+                          static_cast<const long long*>(c->b_slice_row0.p), c->dp, st));
+    c->launches += 1;
+    CU(cudaStreamSynchronize(st));   // `base` leaves scope
     return MRP_FG_OK;
 }
 

@@ -604,20 +604,46 @@ k_normalize_runs(const DevOutputs out, const int64_t N, const DevTile* __restric
 // (feature_normalizer.cpp:37-51,61-69):  a NaN makes sum / sum2 NaN for ever; an infinity makes sum = +-inf and
 // sum2 = +inf (variance NaN -> std 1 -> z = x - (+-inf)) until a NaN, an infinity of the other sign or its own
 // eviction W rows later turns the sums into NaN for ever.  One CTA per (stream, column); exits at once when clean.
+//
+// "For ever" reaches beyond a time chunk / time shard: `carry` ([n_streams][19][3] first NaN / +inf / -inf in ABSOLUTE stream
+// rows, LLONG_MAX = none; may be null) brings in what happened before the bound slice, whose first row is absolute row
+// slice_row0[stream]; the merged state is written back for the slice that follows.
+constexpr long long kNoRow = 0x7fffffffffffffffll;
 __global__ void k_norm_poison(const DevOutputs out, const int64_t N, const int64_t* __restrict__ row_off, const NormPoison* __restrict__ poison,
-                              const int* __restrict__ any_poison, const DevParams P) {
-    if (*any_poison == 0) return;
+                              const int* __restrict__ any_poison, long long* __restrict__ carry, const long long* __restrict__ slice_row0,
+                              const DevParams P) {
     const int sidx = blockIdx.x / kNF, c = blockIdx.x % kNF;
+    long long cN = kNoRow, cP = kNoRow, cM = kNoRow;
+    long long base = 0;
+    if (carry) {
+        const long long* cr = carry + ((int64_t)sidx * kNF + c) * 3;
+        cN = cr[0]; cP = cr[1]; cM = cr[2];
+        base = slice_row0[sidx];
+    }
+    if (*any_poison == 0 && cN == kNoRow && cP == kNoRow && cM == kNoRow) return;
     const NormPoison q = poison[(int64_t)sidx * kNF + c];
     const unsigned int none = 0xffffffffu;
-    if ((q.first_nan & q.first_pinf & q.first_ninf) == none) return;
+    // slice-local rows (negative = before the slice)
+    long long tNl = q.first_nan == none ? kNoRow : (long long)q.first_nan;
+    long long tPl = q.first_pinf == none ? kNoRow : (long long)q.first_pinf, tMl = q.first_ninf == none ? kNoRow : (long long)q.first_ninf;
+    if (cN != kNoRow && cN - base < tNl) tNl = cN - base;
+    if (cP != kNoRow && cP - base < tPl) tPl = cP - base;
+    if (cM != kNoRow && cM - base < tMl) tMl = cM - base;
+    __syncthreads();   // every thread has read the carry before it is updated
+    if (carry && threadIdx.x == 0) {
+        long long* cr = carry + ((int64_t)sidx * kNF + c) * 3;
+        cr[0] = tNl == kNoRow ? kNoRow : tNl + base;
+        cr[1] = tPl == kNoRow ? kNoRow : tPl + base;
+        cr[2] = tMl == kNoRow ? kNoRow : tMl + base;
+    }
+    if (tNl == kNoRow && tPl == kNoRow && tMl == kNoRow) return;
     const int64_t r0 = row_off[sidx], r1 = row_off[sidx + 1];
-    const int64_t n = r1 - r0;
-    const int64_t tN = q.first_nan == none ? n : q.first_nan;
-    const int64_t tP = q.first_pinf == none ? n : q.first_pinf, tM = q.first_ninf == none ? n : q.first_ninf;
-    const int64_t tI = tP < tM ? tP : tM;                 // first infinity
-    const int64_t tO = tP < tM ? tM : tP;                 // first infinity of the other sign (n if none)
-    int64_t tZ = tN;                                      // sums are NaN from here on
+    const long long n = r1 - r0;
+    const long long tN = tNl < n ? tNl : n;
+    const long long tP = tPl < n ? tPl : n, tM = tMl < n ? tMl : n;
+    const long long tI = tP < tM ? tP : tM;                 // first infinity
+    const long long tO = tP < tM ? tM : tP;                 // first infinity of the other sign (n if none)
+    long long tZ = tN;                                      // sums are NaN from here on
     if (tI < n) {
         if (tO < tZ) tZ = tO;
         if (tI + P.norm_window < tZ) tZ = tI + P.norm_window;
@@ -625,8 +651,9 @@ __global__ void k_norm_poison(const DevOutputs out, const int64_t N, const int64
     const double sig_inf = tP < tM ? __longlong_as_double(0x7ff0000000000000ll) : __longlong_as_double(0xfff0000000000000ll);
     const double* __restrict__ x = out.raw + (int64_t)c * N + r0;
     double* __restrict__ z = out.norm + (int64_t)c * N + r0;
-    const int64_t start = tI < tZ ? tI : tZ;
-    for (int64_t t = start + threadIdx.x; t < n; t += blockDim.x) {
+    long long start = tI < tZ ? tI : tZ;
+    if (start < 0) start = 0;
+    for (long long t = start + threadIdx.x; t < n; t += blockDim.x) {
         if (t >= tZ) z[t] = __longlong_as_double(0x7ff8000000000000ll);
         else z[t] = x[t] - sig_inf;                       // mean = +-inf, std = 1
     }
@@ -664,7 +691,8 @@ __global__ void k_normalize_faithful(const DevOutputs out, const int64_t N, cons
 size_t norm_poison_bytes(int n_streams) { return (size_t)n_streams * kNF * sizeof(NormPoison) + 16; }
 
 cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* tiles, int ntiles, double* tile_tot, int* flags,
-                             void* poison, const int64_t* row_off, int n_streams, const DevParams& P, cudaStream_t st) {
+                             void* poison, const int64_t* row_off, int n_streams, long long* carry, const long long* slice_row0,
+                             const DevParams& P, cudaStream_t st) {
     // the ticket counter at flags[ntiles]; tile totals preset to "unpublished"; poison table preset to "none" + the any-flag
     cudaError_t e = cudaMemsetAsync(flags + ntiles, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
@@ -699,7 +727,17 @@ cudaError_t launch_normalize(const DevOutputs& out, int64_t N, const DevTile* ti
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_norm_poison<<<n_streams * kNF, 256, 0, st>>>(out, N, row_off, static_cast<const NormPoison*>(poison), any, P);
+    k_norm_poison<<<n_streams * kNF, 256, 0, st>>>(out, N, row_off, static_cast<const NormPoison*>(poison), any, carry, slice_row0, P);
+    return cudaGetLastError();
+}
+
+// the fix-up pass on its own: applies a carry to z-scores that are already there (a time shard that learns later what its
+// predecessors saw); also the way to read the merged state back
+cudaError_t launch_norm_poison(const DevOutputs& out, int64_t N, void* poison, const int64_t* row_off, int n_streams, long long* carry,
+                               const long long* slice_row0, const DevParams& P, cudaStream_t st) {
+    const size_t pb = (size_t)n_streams * kNF * sizeof(NormPoison);
+    const int* any = reinterpret_cast<const int*>(static_cast<unsigned char*>(poison) + pb);
+    k_norm_poison<<<n_streams * kNF, 256, 0, st>>>(out, N, row_off, static_cast<const NormPoison*>(poison), any, carry, slice_row0, P);
     return cudaGetLastError();
 }
 

@@ -163,6 +163,7 @@ class TimeShard:
             dist.recv(meta, rank - 1)
             self.lead = cabi.HaloInfo(*[int(x) for x in meta.tolist()])
         self.batch, self.skip = layout_with_headroom(shard, self.lead)
+        self.row_base = int(shard["row0"]) - self.skip      # absolute stream row of the bound stream's first row
         engine.bind_device(self.batch)
         self.tail = None
         self.send_buf = self.recv_buf = None
@@ -190,6 +191,25 @@ class TimeShard:
         if self.lead is not None:
             self.engine.halo_import(self.recv_buf.data_ptr(), self.lead, st)
         return int(self.tail.bytes) if self.tail is not None else 0
+
+    def carry_poison(self) -> bool:
+        """After Engine.run: a NaN (or an evicted infinity) poisons the reference's running sums for ever, also across shard
+        boundaries (feature_normalizer.cpp:37-51).  All-gathers every shard's first non-finite rows (57 integers per rank) and
+        rewrites this shard's z-scores for what its predecessors saw.  Returns whether anything had to be rewritten."""
+        import numpy as np
+        import torch.distributed as dist
+
+        dev = self.batch["mid"].device
+        mine = torch.from_numpy(self.engine.poison_state([self.row_base])).to(dev)
+        allst = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allst, mine)
+        if self.rank == 0:
+            return False
+        before = torch.stack(allst[:self.rank]).amin(dim=0).cpu().numpy()
+        if (before == np.iinfo(np.int64).max).all():
+            return False
+        self.engine.poison_apply(before, [self.row_base])
+        return True
 
     @property
     def own_rows(self):

@@ -58,3 +58,27 @@ def test_default_window_and_chunk():
         assert np.allclose(raw[c], one["raw"][c], rtol=1e-10, atol=1e-13 * np.abs(one["raw"][c]).max(), equal_nan=True), c
     worst, frac = z_consistency(norm, one["norm"], one["raw"], hv.arrays["row_offsets"], 30000, raw_rel=1e-10)
     assert worst <= 1.0 and frac > 0.9, (worst, frac)
+
+
+def test_poisoned_columns_stay_poisoned_across_chunks():
+    """feature_normalizer.cpp:37-51: a NaN raw value turns the running sums NaN FOR EVER — also for rows thousands of chunks later.
+    An empty bid side at row 700 (price 0 -> log(0) = -inf in log_spread, lob_slope via the book) must poison every later chunk's
+    z-scores exactly as the single-shot run (and the oracle) have it."""
+    p = mrp_b200.default_params(norm_window=1000)
+    batch = synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=12000, seed=160)]))
+    batch["bid_px"] = batch["bid_px"].copy()
+    batch["bid_px"][:, 700] = np.nan          # a NaN book row: midprice, log_spread, lob_slope, price_gap ... go NaN at row 700
+    batch["ask_px"] = batch["ask_px"].copy()
+    batch["ask_px"][0, 2500] = np.inf          # an infinity: +-inf sums, NaN once it is evicted 1000 rows later
+    hv, one = run_gpu(batch, p)
+    ref = ob.run_oracle(hv, p)
+    assert np.array_equal(np.isnan(one["norm"]), np.isnan(ref["norm"]))
+    eng = mrp_b200.Engine(p, device=0)
+    raw, norm = eng.process_host(hv, chunk_rows=1500)     # halo = 1000 + 384 + 32 rows: chunks from row ~3000 on never see row 700
+    eng.close()
+    assert np.array_equal(np.isnan(norm), np.isnan(ref["norm"])), (np.isnan(norm).sum(), np.isnan(ref["norm"]).sum())
+    assert np.array_equal(np.isinf(norm), np.isinf(ref["norm"]))
+    poisoned = np.isnan(ref["norm"][:, -1])
+    assert poisoned.sum() >= 3                             # several columns are NaN to the end of the stream
+    fin = np.isfinite(ref["norm"])
+    assert np.allclose(norm[fin], one["norm"][fin], rtol=0, atol=1e-6)

@@ -134,3 +134,39 @@ def test_halo_through_the_c_abi(variable):
         small.halo_import(buf.data_ptr(), bad)
     for e in (e0, e1, small):
         e.close()
+
+
+def test_poison_travels_between_shards():
+    """mrp_fg_poison_state / mrp_fg_poison_apply: a NaN in shard 0 poisons shard 1's z-scores as in the whole-stream run."""
+    W, N, world = 2000, 12000, 2
+    p = mrp_b200.default_params(norm_window=W)
+    full = synth.make_batch([synth.SynthSpec(n_rows=N, seed=94)])
+    full.pop("trade_size")
+    full["ask_px"][0, 300] = float("nan")
+    whole = _run_device(full, p)
+    assert np.isnan(whole["norm"][:, -1]).sum() >= 2
+    shards = [timeshard.shard_of(full, *timeshard.shard_bounds(N, world, r)) for r in range(world)]
+    shards = [{k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in sh.items()} for sh in shards]
+    e0 = mrp_b200.Engine(p, device=0)
+    b0, _ = timeshard.layout_with_headroom(shards[0], None)
+    e0.bind_device(b0)
+    e0.run()
+    info = e0.halo_query()
+    buf = torch.empty(int(info.bytes), dtype=torch.uint8, device="cuda")
+    e0.halo_export(buf.data_ptr(), buf.numel())
+    state0 = e0.poison_state([0])
+    e1 = mrp_b200.Engine(p, device=0)
+    b1, skip = timeshard.layout_with_headroom(shards[1], info)
+    e1.bind_device(b1)
+    e1.halo_import(buf.data_ptr(), info)
+    e1.run()
+    r0, r1 = timeshard.shard_bounds(N, world, 1)
+    before = e1.download()
+    assert not np.array_equal(np.isnan(before["norm"][:, skip:]), np.isnan(whole["norm"][:, r0:r1]))   # the halo starts after row 300
+    e1.poison_apply(state0[0], [r0 - skip])
+    got = e1.download()
+    assert np.array_equal(np.isnan(got["norm"][:, skip:]), np.isnan(whole["norm"][:, r0:r1]))
+    fin = np.isfinite(whole["norm"][:, r0:r1])
+    assert np.allclose(got["norm"][:, skip:][fin], whole["norm"][:, r0:r1][fin], rtol=0, atol=1e-7)
+    e0.close()
+    e1.close()
