@@ -178,6 +178,31 @@ def cpu_baseline(levels: int, budget_rows: int):
             "sample": f"{threads} streams x {budget_rows} rows, one host thread per stream, {sec:.1f} s"}
 
 
+def config0_leg(events: int = 600_000):
+    """BASELINE.json configs[0]: the reference's own features_to_csv pipeline on a seeded synthetic MBO day, unmodified
+    (oracle/_ref/libmrp_refpipe.so) and with the INTEGRATION.md §3 patch (libmrp_gpupipe.so: GpuFeatureProcessor -> C ABI -> CUDA).
+    Wall times of both, whole program (event decode, book, features, CSV).  Returns None when the two builds are not here."""
+    import tempfile
+
+    libs = {k: os.path.join(ROOT, "oracle", "_ref", f"libmrp_{k}pipe.so") for k in ("ref", "gpu")}
+    if not all(os.path.exists(p) for p in libs.values()):
+        return None
+    out = {"events_per_instrument": events, "what": "features_to_csv end to end: synthetic MBO events -> order book -> features -> four CSV files"}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, lib in libs.items():
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_pipe.py"), lib, os.path.join(tmp, k), "--events", str(events)],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                return None
+            info = json.loads(r.stdout.strip().splitlines()[-1])
+            if info["rc"] != 0:
+                return None
+            out["seconds_reference" if k == "ref" else "seconds_patched_gpu"] = info["seconds"]
+    out["note"] = ("the event loop (decode, order book, FeatureEngine deques) is the reference's own host code in both; only the feature stage differs, "
+                   "and at this size the GPU context creation is a visible part of the patched run")
+    return out
+
+
 def timeshard_leg(args, rank: int, world: int, dev, rows_per_gpu: int, steps: int, warmup: int):
     """BASELINE.json configs[4]: ONE stream of rows_per_gpu * world snapshots split by time.  Every rank generates only its own
     rows (range-restartable generator), binds them with headroom for the left neighbour's tail, and per step: packs its tail
@@ -500,6 +525,7 @@ def main():
         if _ALL_CPUS:   # the CPU baseline gets every host core the launcher gave this process, not just the GPU's neighbours
             os.sched_setaffinity(0, _ALL_CPUS)
         cpu = cpu_baseline(args.levels, args.ref_rows)
+    config0 = config0_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
     tshard = None
     if world > 1 and not args.no_timeshard and args.days == 1 and args.levels == LEVELS:
@@ -528,7 +554,7 @@ def main():
                        "sharding": "instrument-day per GPU, no data-path collective (the `timeshard` sub-record is the one stream split by time)",
                        "l2": "inputs (>= 20 GB at 50 M rows) far exceed the 126 MB L2; no explicit flush"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "host_affinity": numa, "global_standardisation": scaler,
-            "global_moments_midprice": [float(x) for x in mom[0]], "timeshard": tshard,
+            "global_moments_midprice": [float(x) for x in mom[0]], "timeshard": tshard, "config0": config0,
         }
         _emit(line)
     if world > 1:

@@ -52,7 +52,8 @@ constexpr int kCons = kConsWarps * 32;             // consumer threads == most r
 constexpr int kWinThreads = kProd + kCons + 32;    // + the trade warp
 constexpr int kRun = MRP_WIN_RUN;                  // consecutive ticks per producer thread (odd: conflict-free 64-bit shared accesses); long
                                                    // runs keep the per-thread scan overhead (~300 instructions) small next to the tick arithmetic
-constexpr int kTradeRun = 8;                       // consecutive trades per lane of the trade warp
+constexpr int kTradeRun = 10;                      // consecutive trades per lane and pass of the trade warp: a chunk of 128 rows brings
+                                                   // ~260 trades, one pass of 320
 constexpr int kTradeStage = 1024 + 32;             // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
 // the log1p series covers relative moves below 2^-10 per tick (high word 0x3f500000)
 
@@ -78,6 +79,16 @@ __device__ __forceinline__ double log1p_small(double u) {
 }
 
 __device__ __forceinline__ uint32_t sub_floor0(uint32_t a, uint32_t w) { return a > w ? a - w : 0u; }
+
+// sqrt(v) for v >= 0: the reciprocal-root seed, one coupled Newton step, one correction of the root (the remainder v - s^2 is
+// exact in an fma) — within an ulp of the correctly rounded root for a third of the library routine's instructions; inputs
+// outside the fast range (zero, denormal, huge, NaN) take the library root
+__device__ __forceinline__ double sqrt_fast(double v) {
+    if (!rsqrt_pos_ok(v)) return sqrt(v);
+    const double r = rsqrt_pos(v);
+    const double s = v * r;
+    return fma(fma(-s, s, v), 0.5 * r, s);
+}
 __device__ __forceinline__ bool small_mag(double v, uint32_t hi_limit) {  // |v| < the double whose high word is hi_limit; NaN -> false
     return ((uint32_t)__double2hiint(v) & 0x7fffffffu) < hi_limit;
 }
@@ -228,14 +239,14 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
                 w = fma(pw, g.xf - g.Gs1, g.Ge);
                 if (!(w > 0.0)) w = 0.0;
             }
-            ewm = sqrt(w);
+            ewm = sqrt_fast(w);
             double sumU = 0.5 * (g.SA + g.SS), sumD = 0.5 * (g.SA - g.SS);
             if (!(sumU > 0.0) || !moved) sumU = 0.0;
             if (!(sumD > 0.0) || !moved) sumD = 0.0;
             const double au = nUp > 0 ? sumU * rcp_pos((double)nUp) : 0.0;          // :95-98 (an empty side counts 0)
             const double ad = cnt > nUp ? sumD * rcp_pos((double)(cnt - nUp)) : 0.0;
             const double diff = au - ad;
-            dv = sqrt(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
+            dv = sqrt_fast(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
         }
         {   // :101-107 with s_k = pivot + d_k: mean = (sum s)/1500, var = sum (s_k - mean)^2 / 1500
             const double n = (double)(e - s);
@@ -243,7 +254,7 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
             const double delta = mean - pivot;
             double ss = g.D2 - 2.0 * delta * g.D1 + n * delta * delta;
             if (!(ss > 0.0)) ss = 0.0;
-            sv = sqrt(ss * P.inv_spread_divisor);
+            sv = sqrt_fast(ss * P.inv_spread_divisor);
         }
         const uint32_t d0 = sub_floor0(e, (uint32_t)P.dir_window);
         t_tot = (int)(e - d0);
