@@ -51,7 +51,7 @@ def test_default_window_and_chunk():
     eng.upload(hv)
     eng.run()
     one = eng.download()
-    raw, norm = eng.process_host(hv, chunk_rows=40_000)      # halo of 30 544 rows in front of every chunk
+    raw, norm = eng.process_host(hv, chunk_rows=40_000)      # halo of mrp_fg_halo_rows() = 30 416 rows in front of every chunk
     eng.close()
     assert np.array_equal(raw[0], one["raw"][0])
     for c in range(19):
