@@ -22,14 +22,15 @@
 //
 // One CTA streams through one row segment in time order; the prefixes restart at the segment's first window (a halo
 // of 1802 ticks / 1502 trades — no halo ROWS), so their magnitude stays within ~100 window sums and a difference
-// keeps ~14 digits.  Work is split by warp role, two CTA barriers per chunk of <= 128 rows / 1280 ticks:
-//   warps 0-7  producers: the chunk's new ticks, 5 consecutive ticks per thread out of a staging buffer the copy engine
+// keeps ~14 digits.  Work is split by warp role (288 threads, one CTA per SM: the rings take 222 KB), ONE CTA barrier per chunk of
+// <= 128 rows / 1408 ticks plus named barriers inside the roles:
+//   warps 0-3  producers: the chunk's new ticks, 11 consecutive ticks per thread out of a staging buffer the copy engine
 //              filled (cp.async.bulk + mbarrier, requested one chunk ahead; no thread issues a global load for a tick):
 //              one reciprocal per two ticks and a 6-term log1p series instead of two logs, thread-local prefixes in
 //              registers, one warp scan + one cross-warp pass per quantity, results into the rings;
-//   warps 8-11 consumers: plan the next chunk (cursors, how many rows fit, request its ticks), finalise the previous
-//              chunk's rows from registers, then — between the two barriers — gather this chunk's prefix values;
-//   warp 12    the trade prefixes (8 trades per lane and pass).
+//   warps 4-7  consumers: plan the next chunk (cursors, how many rows fit, request its ticks), gather the PREVIOUS chunk's
+//              prefix values while the producers work on this one, finalise those rows from registers;
+//   warp 8     the trade prefixes (10 trades per lane and pass; a chunk's ~256 trades are one pass).
 // A snapshot that brings more new ticks / trades than a chunk holds simply advances the rings in several steps.
 //
 // Ticks the fast formulation cannot represent — a non-positive / non-finite midprice, a 50 ms move of 2^-10 relative or
