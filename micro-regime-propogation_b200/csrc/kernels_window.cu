@@ -30,8 +30,12 @@
 //              registers, one warp scan + one cross-warp pass per quantity, results into the rings;
 //   warps 4-7  consumers: plan the next chunk (cursors, how many rows fit, request its ticks), gather the PREVIOUS chunk's
 //              prefix values while the producers work on this one, finalise those rows from registers;
-//   warp 8     the trade prefixes (10 trades per lane and pass; a chunk's ~256 trades are one pass).
+//   warp 8     the trade prefixes (10 trades per lane and pass; a chunk's ~256 trades are one pass): everything but the ring
+//              stores happens before the "previous chunk has been gathered" barrier.
 // A snapshot that brings more new ticks / trades than a chunk holds simply advances the rings in several steps.
+// Code size matters here: three roles execute three instruction streams at once through one 32 KB instruction cache, so
+// the trade warp runs rolled loops, the ring-store loop exists once (wrap handled per element), and everything cold
+// (library square root, count columns, the quotient helper, direct_tick_row) is out of line.
 //
 // Ticks the fast formulation cannot represent — a non-positive / non-finite midprice, a 50 ms move of 2^-10 relative or
 // more (series range), a non-finite spread — contribute nothing to the prefixes and are flagged; every snapshot whose
@@ -47,6 +51,9 @@ namespace mrp {
 #ifndef MRP_WIN_RUN
 #define MRP_WIN_RUN 11
 #endif
+#ifndef MRP_WIN_WHATIF
+#define MRP_WIN_WHATIF 0   // timing experiments only (bit 0: no tick math, 1: no finalisation, 2: no warp scan, 3: no ring stores) — results are WRONG when set
+#endif
 constexpr int kProdWarps = MRP_WIN_PROD_WARPS, kConsWarps = 4;
 constexpr int kProd = kProdWarps * 32;             // producer threads
 constexpr int kCons = kConsWarps * 32;             // consumer threads == most rows of one chunk
@@ -55,7 +62,42 @@ constexpr int kRun = MRP_WIN_RUN;                  // consecutive ticks per prod
                                                    // runs keep the per-thread scan overhead (~300 instructions) small next to the tick arithmetic
 constexpr int kTradeRun = 10;                      // consecutive trades per lane and pass of the trade warp: a chunk of 128 rows brings
                                                    // ~260 trades, one pass of 320
-constexpr int kTradeStage = 1024 + 32;             // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
+#ifndef MRP_WIN_DEPTH
+#define MRP_WIN_DEPTH 1
+#endif
+#ifndef MRP_WIN_PROD_REGS
+#define MRP_WIN_PROD_REGS 1      // producers: 1 = the thread's run in registers, fully unrolled; 0 = short rolled loops over the staging buffer
+#endif
+#ifndef MRP_WIN_ORDER
+#define MRP_WIN_ORDER 1          // consumers: 0 = gather, finalise, plan; 1 = plan, gather, finalise
+#endif
+#ifndef MRP_WIN_MATH_UNROLL
+#define MRP_WIN_MATH_UNROLL 2    // tick pairs per trip of the producers' arithmetic loop
+#endif
+#ifndef MRP_WIN_STORE_UNROLL
+#define MRP_WIN_STORE_UNROLL 1   // ticks per trip of the producers' ring loop
+#endif
+#ifndef MRP_WIN_SLOG_SMEM
+#define MRP_WIN_SLOG_SMEM 1          // the c*log2(c) table in shared memory (from global memory through the L1: +0.35 ms at 50 M rows)
+#endif
+// Build-time switches of the organisation, all measured at 50 M rows (profiles/r2b_windows_experiments.md).
+// The defaults are the fastest combination; none of the others is faster, which is the finding: the kernel is neither
+// copy-latency-bound (kDepth 1 -> 2 -> 3: 6.16 / 6.17 / 6.8 ms) nor instruction-cache-bound (the hot loops were cut from 44 KB to
+// 25-31 KB, the SM's instruction-cache hit rate went from 68 % to 97.7-99.9 % and the GPC-level cache from 91 % to 2-24 % of its request
+// peak: same time).  It runs at the issue rate of ONE warp per scheduler walking ~1000 dependent instructions per chunk.
+//   MRP_WIN_DEPTH        chunks planned (and requested from the copy engine) ahead of the producers
+//   MRP_WIN_PROD_REGS    1: a producer thread keeps its 11-tick run in registers, everything unrolled; 0: short rolled loops
+//                        that overwrite the staged midprices with x in place (7 KB less code, but +20 % instructions: 8.2 ms
+//                        rolled, 6.7 ms with the arithmetic loop unrolled)
+//   MRP_WIN_ORDER        consumers: 1 = plan, gather, finalise; 0 = gather, finalise, plan (rings released 800 cycles earlier: slower)
+//   MRP_WIN_PROD_WARPS / MRP_WIN_RUN   4 x 11 (default) 6.16 ms; 5 x 9 6.70; 6 x 7 6.48; 7 x 7 6.38; 8 x 5 6.45
+constexpr int kMathUnroll = MRP_WIN_MATH_UNROLL, kStoreUnroll = MRP_WIN_STORE_UNROLL;
+constexpr int kDepth = MRP_WIN_DEPTH;              // chunks in flight ahead of the one being produced
+constexpr int kStages = kDepth + 1;                // staging buffers
+constexpr int kPlans = 8;                          // plan slots: chunk q lives in slot q & 7 (planned in iteration q - kDepth, gathered in q + 1)
+static_assert(kDepth >= 1 && kDepth + 3 <= kPlans, "plan slots");
+constexpr int kChunkTrades = 512;                  // most new trades of one chunk (a chunk of 128 rows brings ~260)
+constexpr int kTradeStage = kChunkTrades + 32;     // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
 // the log1p series covers relative moves below 2^-10 per tick (high word 0x3f500000)
 
 // 1/a for a normal, positive a (callers flag other inputs themselves): seed + two Newton steps
@@ -84,8 +126,9 @@ __device__ __forceinline__ uint32_t sub_floor0(uint32_t a, uint32_t w) { return 
 // sqrt(v) for v >= 0: the reciprocal-root seed, one coupled Newton step, one correction of the root (the remainder v - s^2 is
 // exact in an fma) — within an ulp of the correctly rounded root for a third of the library routine's instructions; inputs
 // outside the fast range (zero, denormal, huge, NaN) take the library root
+__device__ __noinline__ double sqrt_library(double v) { return sqrt(v); }   // out of line: the hot loops stay small
 __device__ __forceinline__ double sqrt_fast(double v) {
-    if (!rsqrt_pos_ok(v)) return sqrt(v);
+    if (!rsqrt_pos_ok(v)) return sqrt_library(v);
     const double r = rsqrt_pos(v);
     const double s = v * r;
     return fma(fma(-s, s, v), 0.5 * r, s);
@@ -103,6 +146,22 @@ struct DirectParams {
     double ewm_alpha, ewm_decay;
 };
 
+// the optional integer count columns are written out of line: the hot loops of the three roles share a 32 KB instruction cache
+__device__ __noinline__ void write_tick_counts(int32_t* __restrict__ counts, int64_t N, int64_t r, int n_valid, int n_up, int t_up, int t_dn,
+                                               int t_tot) {
+    counts[(int64_t)MRP_C_RET_VALID * N + r] = n_valid;
+    counts[(int64_t)MRP_C_RET_UP * N + r] = n_up;
+    counts[(int64_t)MRP_C_TICK_UP * N + r] = t_up;
+    counts[(int64_t)MRP_C_TICK_DOWN * N + r] = t_dn;
+    counts[(int64_t)MRP_C_TICK_TOTAL * N + r] = t_tot;
+}
+__device__ __noinline__ void write_trade_counts(int32_t* __restrict__ counts, int64_t N, int64_t r, int pos, int neg, int rev, int nd, int isum) {
+    counts[(int64_t)MRP_C_TRADE_POS * N + r] = pos;
+    counts[(int64_t)MRP_C_TRADE_NEG * N + r] = neg;
+    counts[(int64_t)MRP_C_TRADE_REVERSALS * N + r] = rev;
+    counts[(int64_t)MRP_C_TRADE_TOTAL * N + r] = nd;
+    counts[(int64_t)MRP_C_TRADE_DIR_SUM * N + r] = isum;
+}
 __device__ __forceinline__ void write_tick_row(const DevOutputs& out, int64_t N, int64_t r, double ewm, double rv, double dv, double sv,
                                                double tent, int n_valid, int n_up, int t_up, int t_dn, int t_tot) {
     out.raw[(int64_t)MRP_F_EWM_VOLATILITY * N + r] = ewm;
@@ -110,13 +169,7 @@ __device__ __forceinline__ void write_tick_row(const DevOutputs& out, int64_t N,
     out.raw[(int64_t)MRP_F_DIRECTIONAL_VOLATILITY * N + r] = dv;
     out.raw[(int64_t)MRP_F_SPREAD_VOLATILITY * N + r] = sv;
     out.raw[(int64_t)MRP_F_TICK_DIRECTION_ENTROPY * N + r] = tent;
-    if (out.counts) {
-        out.counts[(int64_t)MRP_C_RET_VALID * N + r] = n_valid;
-        out.counts[(int64_t)MRP_C_RET_UP * N + r] = n_up;
-        out.counts[(int64_t)MRP_C_TICK_UP * N + r] = t_up;
-        out.counts[(int64_t)MRP_C_TICK_DOWN * N + r] = t_dn;
-        out.counts[(int64_t)MRP_C_TICK_TOTAL * N + r] = t_tot;
-    }
+    if (out.counts) write_tick_counts(out.counts, N, r, n_valid, n_up, t_up, t_dn, t_tot);
 }
 
 __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, const double* __restrict__ spread, uint32_t e,
@@ -175,7 +228,7 @@ __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, con
 
 // a / n for a positive count n: reciprocal, product, ONE correction step (the quotient's remainder is exact in an fma) — the
 // correctly rounded quotient for the small integers that meet here, without a division and without a table
-__device__ __forceinline__ double div_by_count(double a, int n) {
+__device__ __noinline__ double div_by_count(double a, int n) {
     const double b = (double)n, r = rcp_pos(b);
     const double q = a * r;
     return fma(fma(-q, b, a), r, q);
@@ -193,13 +246,7 @@ __device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N
     out.raw[(int64_t)MRP_F_REVERSAL_RATE * N + r] = rr;
     out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * N + r] = ab;
     out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + r] = ent;
-    if (out.counts) {
-        out.counts[(int64_t)MRP_C_TRADE_POS * N + r] = pos;
-        out.counts[(int64_t)MRP_C_TRADE_NEG * N + r] = neg;
-        out.counts[(int64_t)MRP_C_TRADE_REVERSALS * N + r] = rev;
-        out.counts[(int64_t)MRP_C_TRADE_TOTAL * N + r] = nd;
-        out.counts[(int64_t)MRP_C_TRADE_DIR_SUM * N + r] = isum;
-    }
+    if (out.counts) write_trade_counts(out.counts, N, r, pos, neg, rev, nd, isum);
 }
 
 // What a consumer thread lifts out of the rings for its row between the two barriers of a chunk.
@@ -236,7 +283,8 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
             double w = 0.0;
             if (tot != 0.0) {
                 // :64-79: sum_{i>=1} alpha decay^(cnt-i) x_i + decay^cnt x_1  (the restart takes x_1 with weight decay^(cnt-1))
-                const double pw = full ? P.pow_ret_full : __ldg(P.ewm_pow + cnt);
+                double pw = P.pow_ret_full;
+                if (!full) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(pw) : "l"(P.ewm_pow + cnt));   // the first window of a stream only: no load in flight otherwise
                 w = fma(pw, g.xf - g.Gs1, g.Ge);
                 if (!(w > 0.0)) w = 0.0;
             }
@@ -277,6 +325,23 @@ __device__ __forceinline__ unsigned long long add4x16(unsigned long long a, unsi
     return ((a & ~H) + (b & ~H)) ^ ((a ^ b) & H);
 }
 
+#ifdef MRP_WIN_TIMERS
+// experiment builds only: per-role phase timers, summed over all CTAs (read with mrp_fg_debug_win_timers)
+__device__ unsigned long long g_win_tm[3][12];
+#define TM_DECL long long tm_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tm_last = clock64(); long long tm_iters = 0
+#define TM(i) do { const long long tm_now = clock64(); tm_acc[i] += tm_now - tm_last; tm_last = tm_now; } while (0)
+#define TM_FLUSH(role) do { if (lane == 0) { for (int i_ = 0; i_ < 10; ++i_) atomicAdd(&g_win_tm[role][i_], (unsigned long long)tm_acc[i_]); atomicAdd(&g_win_tm[role][10], (unsigned long long)tm_iters); } } while (0)
+extern "C" int mrp_fg_debug_win_timers(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, g_win_tm, sizeof(g_win_tm)) != cudaSuccess) return -1;
+    unsigned long long z[36] = {0};
+    return cudaMemcpyToSymbol(g_win_tm, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define TM_DECL
+#define TM(i)
+#define TM_FLUSH(role)
+#endif
 enum { PLAN_RUN = 0, PLAN_END = 1 };
 struct __align__(16) WinPlan {
     long long c0;              // first row of the chunk
@@ -288,10 +353,10 @@ struct __align__(16) WinPlan {
     int nr, mode;              // rows finalised by this chunk (0: the rings only advance)
 };
 struct __align__(16) WinStatic {
-    WinPlan plan[4];                   // chunk q lives in slot q & 3: planned in iteration q - 1, produced in q, gathered in q + 1
-    uint64_t full[2];                  // mbarriers of the two staging buffers
+    WinPlan plan[kPlans];              // chunk q lives in slot q & 7: planned in iteration q - kDepth, produced in q, gathered in q + 1
+    uint64_t full[kStages];            // mbarriers of the staging buffers
     double wt[kProdWarps][6];          // per-warp totals: x, +-x, d, d^2, EMA, counts (bit pattern)
-    __align__(16) unsigned char stgT[2][kTradeStage];   // staged trade directions of the chunk (position JFprev - 1 onwards)
+    __align__(16) unsigned char stgT[kStages][kTradeStage];   // staged trade directions of the chunk (position JFprev - 1 onwards)
     double carryG;                     // the EMA after the chunk's last tick
     uint32_t excP1;                    // 1 + position of the last flagged tick (0 = none)
     int cnt[kConsWarps];
@@ -310,11 +375,16 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
     double* __restrict__ QD1 = QS + R;
     double* __restrict__ QD2 = QD1 + R;
     double* __restrict__ QG = QD2 + R;
-    double* __restrict__ stgM = QG + R;            // [2][CTS]
-    double* __restrict__ stgS = stgM + 2 * CTS;    // [2][CTS]
-    unsigned long long* __restrict__ QT = reinterpret_cast<unsigned long long*>(stgS + 2 * CTS);   // [RJ]
+    double* __restrict__ stgM = QG + R;                  // [kStages][CTS]
+    double* __restrict__ stgS = stgM + kStages * CTS;    // [kStages][CTS]
+    unsigned long long* __restrict__ QT = reinterpret_cast<unsigned long long*>(stgS + kStages * CTS);   // [RJ]
+#if MRP_WIN_SLOG_SMEM
     double* __restrict__ sLog = reinterpret_cast<double*>(QT + RJ);                                 // [dir_window + 2]  c*log2(c), from the host
     uint32_t* __restrict__ QC = reinterpret_cast<uint32_t*>(sLog + P.dir_window + 2);                // [R]
+#else
+    const double* __restrict__ sLog = P.clog2c;          // seven look-ups per row in a 12 KB table: the L1 serves them
+    uint32_t* __restrict__ QC = reinterpret_cast<uint32_t*>(QT + RJ);                                // [R]
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevSegment sg = segs[blockIdx.x];
@@ -337,15 +407,17 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         const double s0 = __ldg(spread + baseK);
         if (fabs(s0) <= 1e150) pivot = s0;
     }
+#if MRP_WIN_SLOG_SMEM
     for (int i = tid; i < P.dir_window + 2; i += kWinThreads) sLog[i] = __ldg(P.clog2c + i);   // window counts never exceed dir_window
+#endif
     if (tid == 0) {
         sh.excP1 = 0u;
         sh.carryG = 0.0;
         QA[0] = QS[0] = QD1[0] = QD2[0] = QG[0] = 0.0;
         QC[0] = 0u;
         QT[0] = 0ull;
-        mbar_init(&sh.full[0], 1);
-        mbar_init(&sh.full[1], 1);
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) mbar_init(&sh.full[i], 1);
         mbar_init_fence();
     }
     __syncthreads();
@@ -359,23 +431,29 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 #pragma unroll
         for (int k = 0; k < 5; ++k) pw2[k] = __ldg(P.ewm_pow + (kRun << k));
         const double plane = __ldg(P.ewm_pow + kRun * lane), pwarp = __ldg(P.ewm_pow + kRun * 32);
-        __syncthreads();   // plan 0 is visible
+        __syncthreads();   // the first plans are visible
+        int stage = 0;
+        uint32_t phase = 0u;   // staging buffer of chunk q and the parity of its mbarrier phase
+        TM_DECL;
         for (int q = 0;; ++q) {
-            const WinPlan& pl = sh.plan[q & 3];
+            const WinPlan& pl = sh.plan[q & (kPlans - 1)];
             if (pl.mode != PLAN_RUN) break;
             const uint32_t TFp = pl.TFprev, TF = pl.TF;
             cG = sh.carryG;   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
-            mbar_wait(&sh.full[q & 1], (uint32_t)((q >> 1) & 1));
+            TM(0);
+            mbar_wait(&sh.full[stage], phase);
+            TM(1);
+            const int stage_q = stage;
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
             if (TF > TFp) {
-                const double* __restrict__ sm = stgM + (q & 1) * CTS + pl.shM;
-                const double* __restrict__ ss = stgS + (q & 1) * CTS + pl.shS;
+                const double* __restrict__ sm = stgM + stage_q * CTS + pl.shM;
+                const double* __restrict__ ss = stgS + stage_q * CTS + pl.shS;
                 const uint32_t k0 = TFp + (uint32_t)(kRun * tid);
                 const int i0 = (int)(k0 - pl.stg0);
                 const int nv = k0 < TF ? (int)min(TF - k0, (uint32_t)kRun) : 0;   // valid ticks of this thread
+#if MRP_WIN_PROD_REGS
+                // the run lives in registers, everything unrolled (more instruction-level parallelism, three times the code)
                 const bool has_prev = k0 > pl.stg0;
-                // mids m[0] = M_{k0-1}, m[1..11] = M_{k0..k0+10}; d = spread - pivot.  One path for whole and partial runs: every
-                // element is loaded — the staging rows are CT + 4 long, a stale element is never used — then ticks past the frontier
-                // repeat their predecessor (flat, no contribution) with d = 0.
                 double m[kRun + 1], d[kRun];
                 {
                     const int ib = nv > 0 ? i0 : 1;          // threads without a run read the buffer's head
@@ -391,8 +469,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     for (int i = 0; i < kRun; ++i)
                         if (i >= nv) { m[i + 1] = m[i]; d[i] = 0.0; }
                 }
-                // one reciprocal per two returns: log(M_k / M_{k-1}) = -log1p((M_{k-1} - M_k) / M_k) = log1p((M_k - M_{k-1}) / M_{k-1});
-                // x = +-r^2, the sign set unless the midprice rose (-0.0 for a flat tick)
                 double x[kRun];
                 uint32_t umax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
 #pragma unroll
@@ -408,7 +484,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                             const double xx = r * r;
                             const uint32_t uh = (uint32_t)__double2hiint(u), um = uh & 0x7fffffffu;
                             umax = max(umax, um);
-                            // a real move is a normal number: its high word alone tells it from zero
                             const uint32_t mv = um != 0u ? 1u : 0u;
                             const uint32_t up = h == 0 ? (uh >> 31) : (mv & ~(uh >> 31));
                             nneg += 1u - up;
@@ -418,7 +493,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     }
                 }
                 nneg -= (uint32_t)(kRun - nv);   // the padding ticks of a partial run are flat: they counted as "did not rise"
-                // thread totals
                 double va = 0.0, vs = 0.0, v1 = 0.0, v2 = 0.0, vg = 0.0;
 #pragma unroll
                 for (int i = 0; i < kRun; ++i) {
@@ -429,19 +503,80 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     v2 = fma(d[i], d[i], v2);
                     vg = fma(decay, vg, alpha * ax);
                 }
-                // flagged: a midprice that is not a positive normal number (its reciprocal is negative, or the returns round it are huge / NaN),
-                // a move beyond the series range, a spread that is not finite or absurd (its square leaves the range)
-                if (!(umax < 0x3f500000u && (rsign >> 31) == 0u && v2 < 1e300)) {
+                TM(2);
+                const bool bad = !(umax < 0x3f500000u && (rsign >> 31) == 0u && v2 < 1e300);
+                if (bad) {
                     if (nv > 0) atomicMax(&sh.excP1, k0 + (uint32_t)nv);
 #pragma unroll
                     for (int i = 0; i < kRun; ++i) { x[i] = 0.0; d[i] = 0.0; }
                     nneg = nmov = 0u;
                     va = vs = v1 = v2 = vg = 0.0;
                 }
+#else
+                // This thread's ticks M_{k0..k0+nv-1} sit at xm[0..nv-1]; the tick before them belongs to the neighbour (or to the
+                // previous chunk).  The arithmetic runs as a SHORT ROLLED loop that overwrites each midprice with its
+                // x = +-log(M_k / M_{k-1})^2 in place (the ring pass after the scan reads it back): the smallest code of the
+                // variants measured (the three roles' hot loops fit the SM's instruction cache with room to spare), not the fastest.
+                double* __restrict__ xm = const_cast<double*>(sm) + (nv > 0 ? i0 : 1);
+                const double* __restrict__ sp = ss + (nv > 0 ? i0 : 1);
+                double mprev = xm[-1];
+                if (!(k0 > pl.stg0)) mprev = xm[0];        // the tick at the base has no predecessor: flat
+                bar_sync_n(1, kProd);                      // every predecessor has been read before anybody overwrites a midprice
+                double va = 0.0, vs = 0.0, v1 = 0.0, v2 = 0.0, vg = 0.0;
+                uint32_t umax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
+#if MRP_WIN_WHATIF & 1
+#pragma unroll 1
+                for (int i = 0; i < nv; ++i) { const double u = xm[i] - mprev; mprev = xm[i]; xm[i] = u * u; va += u * u; }
+#else
+                // one reciprocal per two returns (that of the tick between them): log(M_k / M_{k-1}) = -log1p((M_{k-1} - M_k) / M_k),
+                // log(M_{k+1} / M_k) = log1p((M_{k+1} - M_k) / M_k); x = +-r^2, the sign set unless the midprice rose (-0.0 for a flat tick)
+#pragma unroll kMathUnroll
+                for (int i = 0; i < kRun + 1; i += 2) {
+                    const bool one = i < nv, two = i + 1 < nv;
+                    const double ma = one ? xm[i] : 1.0;
+                    const double mb = two ? xm[i + 1] : ma;
+                    const double rc = rcp_pos(ma);
+                    rsign |= (uint32_t)__double2hiint(rc);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double u = h == 0 ? ((one ? mprev : ma) - ma) * rc : (mb - ma) * rc;   // h == 0: rose <=> u < 0
+                        const double r = log1p_small(u);
+                        const double xx = r * r;
+                        const uint32_t uh = (uint32_t)__double2hiint(u), um = uh & 0x7fffffffu;
+                        umax = max(umax, um);
+                        const uint32_t mv = um != 0u ? 1u : 0u;   // a real move is a normal number: its high word alone tells it from zero
+                        const uint32_t up = h == 0 ? (uh >> 31) : (mv & ~(uh >> 31));
+                        const bool live = h == 0 ? one : two;
+                        const double x = __hiloint2double((int)((uint32_t)__double2hiint(xx) | ((1u - up) << 31)), __double2loint(xx));
+                        if (live) {
+                            const double dd = sp[i + h] - pivot;
+                            xm[i + h] = x;
+                            nneg += 1u - up;
+                            nmov += mv;
+                            va += xx;
+                            vs += x;
+                            v1 += dd;
+                            v2 = fma(dd, dd, v2);
+                            vg = fma(decay, vg, alpha * xx);
+                        }
+                    }
+                    mprev = mb;
+                }
+#endif
+                TM(2);
+                // flagged: a midprice that is not a positive normal number (its reciprocal is negative, or the returns round it are huge / NaN),
+                // a move beyond the series range, a spread that is not finite or absurd (its square leaves the range)
+                const bool bad = !(umax < 0x3f500000u && (rsign >> 31) == 0u && v2 < 1e300);
+                if (bad) {
+                    if (nv > 0) atomicMax(&sh.excP1, k0 + (uint32_t)nv);
+                    nneg = nmov = 0u;
+                    va = vs = v1 = v2 = vg = 0.0;
+                }
+#endif
                 uint32_t vc = nneg | (nmov << 16);
                 // warp scans of the thread totals (inclusive), the EMA as a scan of y -> decay^11 y + b
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
+                for (int k = 0; k < ((MRP_WIN_WHATIF & 4) ? 0 : 5); ++k) {
                     const int dd = 1 << k;
                     const double ua = shfl_up_d(va, dd), us = shfl_up_d(vs, dd), u1 = shfl_up_d(v1, dd), u2 = shfl_up_d(v2, dd),
                                  ug = shfl_up_d(vg, dd);
@@ -460,7 +595,9 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 double xa = shfl_up_d(va, 1), xs = shfl_up_d(vs, 1), x1 = shfl_up_d(v1, 1), x2 = shfl_up_d(v2, 1), xg = shfl_up_d(vg, 1);
                 uint32_t xc = __shfl_up_sync(0xffffffffu, vc, 1);
                 if (lane == 0) { xa = xs = x1 = x2 = xg = 0.0; xc = 0u; }
+                TM(3);
                 bar_sync_n(1, kProd);
+                TM(4);
                 // across the warps: lane l (< 6) walks quantity l over the warp totals; the four sums and the EMA share one
                 // fused multiply-add (factor 1 or decay^352), the counters an integer add
                 double mine_d = 0.0, acc_d;
@@ -488,57 +625,50 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 cD2 = __shfl_sync(0xffffffffu, acc_d, 3);
                 cC = (unsigned long long)__shfl_sync(0xffffffffu, acc_i, 5);
                 // the consumers have lifted the previous chunk's values out of the rings: its far-end entries may be overwritten
+                TM(5);
                 bar_sync_n(3, kWinThreads);
+                TM(6);
                 // into the rings: the prefix AFTER tick k lives at position k + 1.  The running sums continue from the offsets.
                 uint32_t slot = pl.slotT + (uint32_t)(kRun * tid) + 1u;
                 if (slot >= (uint32_t)R) slot -= (uint32_t)R;
-                if (slot + (uint32_t)kRun <= (uint32_t)R) {   // no wrap inside the run (all but one thread in ~300): immediate offsets
-                    double* __restrict__ pA = QA + slot;
-                    double* __restrict__ pS = QS + slot;
-                    double* __restrict__ p1 = QD1 + slot;
-                    double* __restrict__ p2 = QD2 + slot;
-                    double* __restrict__ pG = QG + slot;
-                    uint32_t* __restrict__ pC = QC + slot;
+                // into the rings (a rolled loop again: the x and the spreads come back from the staging buffer)
+#if MRP_WIN_PROD_REGS
 #pragma unroll
-                    for (int i = 0; i < kRun; ++i) {
-                        const double ax = fabs(x[i]);
+#else
+#pragma unroll kStoreUnroll
+#endif
+                for (int i = 0; i < ((MRP_WIN_WHATIF & 8) ? 1 : kRun); ++i) {
+                    if (i < nv) {
+#if MRP_WIN_PROD_REGS
+                        const double xv = x[i], dv = d[i];
+#else
+                        const double xv = bad ? 0.0 : xm[i], dv = bad ? 0.0 : sp[i] - pivot;
+#endif
+                        const double ax = fabs(xv);
                         gA += ax;
-                        gS += x[i];
-                        g1 += d[i];
-                        g2 = fma(d[i], d[i], g2);
+                        gS += xv;
+                        g1 += dv;
+                        g2 = fma(dv, dv, g2);
                         gG = fma(decay, gG, alpha * ax);
-                        gNeg += (uint32_t)__double2hiint(x[i]) >> 31;
+                        gNeg += (uint32_t)__double2hiint(xv) >> 31;
                         gMov += ax != 0.0 ? 1u : 0u;
-                        if (i < nv) {
-                            pA[i] = gA; pS[i] = gS; p1[i] = g1; p2[i] = g2; pG[i] = gG;
-                            pC[i] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
-                            if (k0 + (uint32_t)i + 1u == TF) sh.carryG = gG;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < kRun; ++i) {
-                        if (i < nv) {
-                            const double ax = fabs(x[i]);
-                            gA += ax;
-                            gS += x[i];
-                            g1 += d[i];
-                            g2 = fma(d[i], d[i], g2);
-                            gG = fma(decay, gG, alpha * ax);
-                            gNeg += (uint32_t)__double2hiint(x[i]) >> 31;
-                            gMov += ax != 0.0 ? 1u : 0u;
-                            QA[slot] = gA; QS[slot] = gS; QD1[slot] = g1; QD2[slot] = g2; QG[slot] = gG;
-                            QC[slot] = (gNeg & 0xffffu) | (gMov << 16);
-                            if (k0 + (uint32_t)i + 1u == TF) sh.carryG = gG;
-                            if (++slot == (uint32_t)R) slot = 0u;
-                        }
+                        QA[slot] = gA; QS[slot] = gS; QD1[slot] = g1; QD2[slot] = g2; QG[slot] = gG;
+                        QC[slot] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
+                        if (++slot == (uint32_t)R) slot = 0u;
                     }
                 }
+                if (nv > 0 && k0 + (uint32_t)nv == TF) sh.carryG = gG;   // the EMA after the chunk's last tick
             } else {
                 bar_sync_n(3, kWinThreads);
             }
+            TM(7);
             __syncthreads();   // the rings hold chunk q; plan q + 1 is visible
+            TM(8);
+#ifdef MRP_WIN_TIMERS
+            ++tm_iters;
+#endif
         }
+        if (warp == 0) TM_FLUSH(0);
     } else if (warp < kProdWarps + kConsWarps) {
         // ================================================================================ consumers: plan, gather, finalise
         const int ci = tid - kProd, cw = warp - kProdWarps;
@@ -550,6 +680,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         dpm.ewm_decay = P.ewm_decay;
         uint32_t cur_e = 0, cur_j = 0;   // this thread's candidate row of the chunk just planned
         int plan_nr = 0;
+        int pstage = 0;                  // staging buffer of the next chunk to plan
         // plan the chunk that follows (TFq, JFq) and starts at row c0n, from this thread's candidate cursors; request its ticks / trades
         auto make_plan = [&](const int q_new, const long long c0n, const uint32_t TFq, const uint32_t JFq, const uint32_t slotT,
                              const uint32_t slotJ, const uint32_t pe, const uint32_t pj) {
@@ -563,8 +694,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             const int nr = sh.cnt[0] + sh.cnt[1] + sh.cnt[2] + sh.cnt[3];
             plan_nr = nr;
             if (ci == (nr > 0 ? nr - 1 : 0)) {
-                WinPlan& np = sh.plan[q_new & 3];
-                const int sbuf = q_new & 1;
+                WinPlan& np = sh.plan[q_new & (kPlans - 1)];
+                const int sbuf = pstage;
                 const bool end = c0n >= rb;
                 uint32_t TFn = TFq, JFn = JFq;
                 if (!end) {
@@ -619,6 +750,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             }
             cur_e = ce;
             cur_j = cj;
+            if (++pstage == kStages) pstage = 0;
             // pull the ticks of the chunk after that one towards the L2
             const uint32_t pf = TFq + (uint32_t)CT + (uint32_t)ci * 16u;
             if (ci * 16 < CT && pf < nTicks) {
@@ -627,12 +759,11 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             }
         };
         // gather the rows of a produced chunk out of the rings and finalise them
-        auto gather_finish = [&](const WinPlan& pg, const uint32_t e, const uint32_t je, const bool arrive) {
+        auto gather = [&](const WinPlan& pg, const uint32_t e, const uint32_t je, RowGather& gat) {
             const uint32_t TF = pg.TF, JF = pg.JF;
             uint32_t slotTe = pg.slotT + (TF - pg.TFprev), slotJe = pg.slotJ + (JF - pg.JFprev);   // slots of the chunk's frontiers
             if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
             if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
-            RowGather gat;
             gat.row = -1;
             if (ci < pg.nr) {
                 auto slot_of = [&](uint32_t p) {   // ring slot of tick position p <= TF
@@ -687,7 +818,14 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 const uint32_t exc = sh.excP1;
                 gat.flagged = exc != 0u && e <= exc + Wmax + 1u;   // the window (or the entry just before it) may hold a flagged tick
             }
-            if (arrive) bar_arrive_n(3, kWinThreads);   // the values are in registers: the rings may move on
+        };
+        auto finish = [&](const RowGather& gat) {
+            if ((MRP_WIN_WHATIF & 2) && gat.row >= 0) {
+                write_tick_row(out, N, gat.row, gat.Ge + gat.Gs1 + gat.xf, gat.SA, gat.SS, gat.D1 + gat.D2, (double)(gat.negs + gat.movm + gat.negd + gat.movd), 0, 0, 0, 0, 0);
+                out.raw[(int64_t)MRP_F_REVERSAL_RATE * N + gat.row] = (double)(gat.rev + gat.isum);
+                out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * N + gat.row] = (double)gat.pos;
+                out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + gat.row] = (double)gat.neg;
+            } else
             if (gat.row >= 0) {
                 if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
                 else finish_tick_row(out, N, P, sLog, pivot, gat);
@@ -700,9 +838,29 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             pre_e = __ldg(kcur + ra + ci);
             pre_j = __ldg(jcur + ra + ci);
         }
+        // this thread's row cursors of the chunks in flight: eq[i] belongs to chunk q - 1 + i in iteration q (planned kDepth
+        // iterations before it is produced, gathered one iteration after)
+        uint32_t eq[kDepth + 2], jq[kDepth + 2];
+#pragma unroll
+        for (int i = 0; i < kDepth + 2; ++i) eq[i] = jq[i] = 0u;
+        // the plan that follows plan `pl` (frontiers, ring slots, first row), then this thread's candidate cursors for the one after
+        auto plan_after = [&](const int q_new, const WinPlan& pl) {
+            const uint32_t TF = pl.TF, JF = pl.JF;
+            uint32_t slotTe = pl.slotT + (TF - pl.TFprev), slotJe = pl.slotJ + (JF - pl.JFprev);
+            if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
+            if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
+            const long long c0n = pl.c0 + pl.nr;
+            make_plan(q_new, c0n, TF, JF, slotTe, slotJe, pre_e, pre_j);
+            const long long c2 = c0n + plan_nr;
+            pre_e = pre_j = 0;
+            if (c2 + ci < rb) {
+                pre_e = __ldg(kcur + c2 + ci);
+                pre_j = __ldg(jcur + c2 + ci);
+            }
+        };
         make_plan(0, ra, baseK, baseJ, 0u, 0u, pre_e, pre_j);
-        uint32_t e_next = cur_e, j_next = cur_j;   // this thread's row of chunk 0 (to be produced in iteration 0, gathered in iteration 1)
-        uint32_t e_gat = 0, j_gat = 0;             // ... of the chunk to be gathered in the current iteration
+        eq[1] = cur_e;
+        jq[1] = cur_j;
         {   // candidates of chunk 1
             const long long c1 = ra + plan_nr;
             pre_e = pre_j = 0;
@@ -711,65 +869,98 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 pre_j = __ldg(jcur + c1 + ci);
             }
         }
-        __syncthreads();   // plan 0 is visible to everybody
-        int q = 0;
-        for (;; ++q) {
-            const WinPlan& pl = sh.plan[q & 3];
-            if (pl.mode != PLAN_RUN) break;
-            const uint32_t TF = pl.TF, JF = pl.JF;
-            uint32_t slotTe = pl.slotT + (TF - pl.TFprev), slotJe = pl.slotJ + (JF - pl.JFprev);
-            if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
-            if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
-            const long long c0n = pl.c0 + pl.nr;
-            // the plan of chunk q + 1 first: its ticks then have the whole iteration to arrive
-            make_plan(q + 1, c0n, TF, JF, slotTe, slotJe, pre_e, pre_j);
-            {   // candidates of chunk q + 2: in flight during the gather
-                const long long c2 = c0n + plan_nr;
-                pre_e = pre_j = 0;
-                if (c2 + ci < rb) {
-                    pre_e = __ldg(kcur + c2 + ci);
-                    pre_j = __ldg(jcur + c2 + ci);
-                }
-            }
-            // chunk q - 1 is in the rings (the producers are busy with chunk q's arithmetic and will not store before barrier 3)
-            if (q > 0) gather_finish(sh.plan[(q - 1) & 3], e_gat, j_gat, true);
-            else bar_arrive_n(3, kWinThreads);
-            e_gat = e_next;
-            j_gat = j_next;
-            e_next = cur_e;
-            j_next = cur_j;
-            __syncthreads();   // the rings hold chunk q; plan q + 1 is visible
+#pragma unroll
+        for (int p2 = 1; p2 < kDepth; ++p2) {   // plans 1 .. kDepth - 1: each needs its predecessor (written by one thread) to be visible
+            bar_sync_n(2, kCons);
+            plan_after(p2, sh.plan[p2 - 1]);
+            eq[p2 + 1] = cur_e;
+            jq[p2 + 1] = cur_j;
         }
-        if (q > 0) gather_finish(sh.plan[(q - 1) & 3], e_gat, j_gat, false);   // the last chunk
+        __syncthreads();   // the first kDepth plans are visible to everybody
+        int q = 0;
+        TM_DECL;
+        for (;; ++q) {
+            const WinPlan& pl = sh.plan[q & (kPlans - 1)];
+            if (pl.mode != PLAN_RUN) break;
+            TM(0);
+            // chunk q - 1 is in the rings (the producers are busy with chunk q's arithmetic and will not store before barrier 3): lift
+            // its window values into registers FIRST and release the rings — everything the other roles do after barrier 3 (ring
+            // stores) then overlaps the plan and the finalisation
+            RowGather gat;
+            gat.row = -1;
+#if MRP_WIN_ORDER == 1
+            plan_after(q + kDepth, sh.plan[(q + kDepth - 1) & (kPlans - 1)]);
+            eq[kDepth + 1] = cur_e;
+            jq[kDepth + 1] = cur_j;
+            TM(5);
+#endif
+            if (q > 0) gather(sh.plan[(q - 1) & (kPlans - 1)], eq[0], jq[0], gat);
+            TM(1);
+            bar_arrive_n(3, kWinThreads);
+            finish(gat);
+            TM(2);
+#if MRP_WIN_ORDER == 0
+            // the plan of chunk q + kDepth LAST: its ticks still have more than kDepth - 1 iterations to arrive, and the cursor loads
+            // it ends with (candidates of the plan after it, out of HBM) have the chunk barrier and the next gather to land — no
+            // arithmetic of this role waits behind them on a scoreboard
+            plan_after(q + kDepth, sh.plan[(q + kDepth - 1) & (kPlans - 1)]);
+            eq[kDepth + 1] = cur_e;
+            jq[kDepth + 1] = cur_j;
+#endif
+#pragma unroll
+            for (int i = 0; i < kDepth + 1; ++i) { eq[i] = eq[i + 1]; jq[i] = jq[i + 1]; }
+            TM(3);
+            __syncthreads();   // the rings hold chunk q; plan q + kDepth is visible
+            TM(4);
+#ifdef MRP_WIN_TIMERS
+            ++tm_iters;
+#endif
+        }
+        if (cw == 0) TM_FLUSH(1);
+        if (q > 0) {   // the last chunk
+            RowGather gat;
+            gather(sh.plan[(q - 1) & (kPlans - 1)], eq[0], jq[0], gat);
+            finish(gat);
+        }
     } else {
         // ================================================================================ the trade warp: trades -> QT
         unsigned long long cJ = 0ull;    // the counters at the trade frontier
-        __syncthreads();   // plan 0 is visible
+        __syncthreads();   // the first plans are visible
+        int stage = 0;
+        uint32_t phase = 0u;
+        TM_DECL;
         for (int q = 0;; ++q) {
-            const WinPlan& pl = sh.plan[q & 3];
+            const WinPlan& pl = sh.plan[q & (kPlans - 1)];
             if (pl.mode != PLAN_RUN) break;
+            TM(0);
             const uint32_t JFp = pl.JFprev, JF = pl.JF;
             uint32_t slot0 = pl.slotJ;
-            if (JF > JFp) mbar_wait(&sh.full[q & 1], (uint32_t)((q >> 1) & 1));   // the chunk's trade directions have landed
+            if (JF > JFp) mbar_wait(&sh.full[stage], phase);   // the chunk's trade directions have landed
             const uint32_t t0 = JFp > baseJ ? JFp - 1u : baseJ;
-            const signed char* __restrict__ sb = reinterpret_cast<const signed char*>(sh.stgT[q & 1]) + pl.shT;   // sb[j - t0] = direction of trade j
-            bar_sync_n(3, kWinThreads);   // the previous chunk has been gathered
+            const signed char* __restrict__ sb = reinterpret_cast<const signed char*>(sh.stgT[stage]) + pl.shT;   // sb[j - t0] = direction of trade j
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            bool released = false;   // barrier 3 (the previous chunk has been gathered) is due before the first store into the ring
             for (uint32_t jp = JFp; jp < JF; jp += 32u * kTradeRun) {
                 const uint32_t j0 = jp + (uint32_t)(lane * kTradeRun);
-                int dprev = (j0 > baseJ && j0 < JF) ? (int)sb[j0 - 1u - t0] : 0;   // the trade at the base (trade 0) closes no pair
-                int dv[kTradeRun];
-#pragma unroll
-                for (int i = 0; i < kTradeRun; ++i) dv[i] = j0 + (uint32_t)i < JF ? (int)sb[j0 + (uint32_t)i - t0] : 0;
-                unsigned long long c[kTradeRun], t = 0ull;
-#pragma unroll
-                for (int i = 0; i < kTradeRun; ++i) {
-                    const int d = dv[i];
-                    // fields: pos | neg << 16 | reversal << 32 | dir << 48 (feature_processor.cpp:235, :242-245, :255-259); within a pass
-                    // no field but the top one can carry
-                    t += (unsigned long long)(d > 0 ? 1 : 0) + ((unsigned long long)(d < 0 ? 1 : 0) << 16) +
-                         ((unsigned long long)((d != 0 && d == -dprev) ? 1 : 0) << 32) + ((unsigned long long)(long long)d << 48);
-                    dprev = d;
-                    c[i] = t;
+                const int nt = j0 < JF ? (int)min(JF - j0, (uint32_t)kTradeRun) : 0;   // this lane's trades of the pass
+                const signed char* __restrict__ mine = sb + (j0 - t0);                // mine[i] = direction of trade j0 + i
+                const int dfirst = (j0 > baseJ && nt > 0) ? (int)mine[-1] : 0;        // the trade at the base (trade 0) closes no pair
+                // fields: pos | neg << 16 | reversal << 32 | dir << 48 (feature_processor.cpp:235, :242-245, :255-259); within a pass
+                // no field but the top one can carry.  Two short rolled loops (lane total, then the prefixes) instead of three unrolled
+                // ones: this role's instructions share the SM's instruction cache with the other two
+                auto fields = [](const int d, const int dprev) {
+                    return (unsigned long long)(d > 0 ? 1 : 0) + ((unsigned long long)(d < 0 ? 1 : 0) << 16) +
+                           ((unsigned long long)((d != 0 && d == -dprev) ? 1 : 0) << 32) + ((unsigned long long)(long long)d << 48);
+                };
+                unsigned long long t = 0ull;
+                {
+                    int dprev = dfirst;
+#pragma unroll 1
+                    for (int i = 0; i < nt; ++i) {
+                        const int d = (int)mine[i];
+                        t += fields(d, dprev);
+                        dprev = d;
+                    }
                 }
                 unsigned long long v = t;
 #pragma unroll
@@ -780,12 +971,23 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 unsigned long long ex = shfl_up_u64(v, 1);
                 if (lane == 0) ex = 0ull;
                 const unsigned long long base = add4x16(cJ, ex);
+                if (!released) {
+                    TM(1);
+                    bar_sync_n(3, kWinThreads);
+                    released = true;
+                    TM(2);
+                }
                 uint32_t slot = slot0 + (uint32_t)(lane * kTradeRun) + 1u;
                 if (slot >= (uint32_t)RJ) slot -= (uint32_t)RJ;
-#pragma unroll
-                for (int i = 0; i < kTradeRun; ++i) {
-                    if (j0 + (uint32_t)i < JF) {
-                        QT[slot] = add4x16(base, c[i]);
+                {
+                    int dprev = dfirst;
+                    unsigned long long c = 0ull;
+#pragma unroll 1
+                    for (int i = 0; i < nt; ++i) {
+                        const int d = (int)mine[i];
+                        c += fields(d, dprev);
+                        dprev = d;
+                        QT[slot] = add4x16(base, c);
                         if (++slot == (uint32_t)RJ) slot = 0u;
                     }
                 }
@@ -793,20 +995,28 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 slot0 += 32u * kTradeRun;
                 if (slot0 >= (uint32_t)RJ) slot0 -= (uint32_t)RJ;
             }
+            if (!released) bar_sync_n(3, kWinThreads);
+            TM(3);
             __syncthreads();   // the rings hold chunk q
+            TM(4);
+#ifdef MRP_WIN_TIMERS
+            ++tm_iters;
+#endif
         }
+        TM_FLUSH(2);
     }
 }
 
 // Ring geometry for given windows: the tick ring holds one window + one chunk, likewise the trade ring; everything must fit the
 // 227 KB a CTA can opt into.  Returns false when the windows are too long for the on-chip rings.
 static size_t win_smem(int ring, int chunk_ticks, int trade_ring, int dir_window) {
-    return (size_t)ring * 44 + (size_t)4 * (chunk_ticks + 4) * 8 + (size_t)trade_ring * 8 + (size_t)(dir_window + 2) * 8;
+    return (size_t)ring * 44 + (size_t)2 * kStages * (chunk_ticks + 4) * 8 + (size_t)trade_ring * 8 +
+           (MRP_WIN_SLOG_SMEM ? (size_t)(dir_window + 2) * 8 : 0);
 }
 bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, int* trade_ring, int* chunk_trades, size_t* smem) {
     const int wmax = mid_window > dir_window + 1 ? mid_window : dir_window + 1;
     const size_t budget = 232448 - sizeof(WinStatic) - 1024;
-    const int cj = 1024;
+    const int cj = kChunkTrades;
     const int rj = ((dir_window + 2 + cj + 8 + 1) / 2) * 2;
     for (int ct = kProd * kRun; ct >= 4 * kRun; ct -= 2 * kRun) {   // even (16-byte staging rows), whole thread runs
         const int r = ((wmax + 2 + ct + 8 + 1) / 2) * 2;

@@ -38,7 +38,8 @@ def main():
     tot_i = sum(l[3] for l in lines) or 1
     tot_s = sum(l[4] for l in lines) or 1
     print(f"{kern}: total warp-instructions {tot_i:,}  samples {tot_s:,}")
-    for l in sorted(lines, key=lambda x: -x[3])[:top]:
+    key = 4 if "--by-samples" in sys.argv else 3
+    for l in sorted(lines, key=lambda x: -x[key])[:top]:
         print(f"{l[0]}:{l[1]:4d} inst {100*l[3]/tot_i:5.1f}%  samp {100*l[4]/tot_s:5.1f}%  | {l[2].strip()[:110]}")
 
 
