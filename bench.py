@@ -516,8 +516,61 @@ def main():
         d2h = raw_h.numel() * 8 * 2
         e2e = {"value": e2e_rows * world / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "rows_per_gpu": e2e_rows, "ms_per_step": e_ms,
+               "h2d_gbs": h2d / e_ms * 1e-6, "d2h_gbs": d2h / e_ms * 1e-6,
                "checksum": float(norm_h[0, :1000].sum().item())}
         eng2.close()
+        # the wire's own ceiling: the SAME pinned buffers and byte counts moved by plain copies, no kernels —
+        # both directions at once (what the pipeline does), then host-to-device alone
+        def copy_loop(both: bool) -> float:
+            piece = 256 << 20
+            d_in = torch.empty(piece, dtype=torch.uint8, device=dev)
+            d_out = torch.empty(piece, dtype=torch.uint8, device=dev)
+            s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            srcs = [v.view(torch.uint8).reshape(-1) for k, v in host.items() if isinstance(v, torch.Tensor) and v.numel()]
+            dsts = [raw_h.view(torch.uint8).reshape(-1), norm_h.view(torch.uint8).reshape(-1)]
+            torch.cuda.synchronize()
+            barrier()
+            c0 = time.perf_counter()
+            with torch.cuda.stream(s_in):
+                for v in srcs:
+                    for off in range(0, v.numel(), piece):
+                        k = min(piece, v.numel() - off)
+                        d_in[:k].copy_(v[off:off + k], non_blocking=True)
+            if both:
+                with torch.cuda.stream(s_out):
+                    for v in dsts:
+                        for off in range(0, v.numel(), piece):
+                            k = min(piece, v.numel() - off)
+                            v[off:off + k].copy_(d_out[:k], non_blocking=True)
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - c0) * 1e3
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        # a consumer of the z-scored half only (the reference's Python stage reads `_norm.csv`, classifier.py:15-18): the raw matrix
+        # stays on the device, half the device-to-host bytes
+        eng3 = mrp_b200.Engine(mrp_b200.default_params(), device=local_rank)
+        eng3.process_host(hv, norm_ptr=norm_h.data_ptr(), chunk_rows=args.e2e_chunk)
+        barrier()
+        n0 = time.perf_counter()
+        eng3.process_host(hv, norm_ptr=norm_h.data_ptr(), chunk_rows=args.e2e_chunk)
+        n_ms = (time.perf_counter() - n0) * 1e3
+        if world > 1:
+            t = torch.tensor([n_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            n_ms = float(t.item())
+        eng3.close()
+        e2e["norm_only"] = {"value": e2e_rows * world / (n_ms * 1e-3), "ms_per_step": n_ms, "d2h_bytes_per_step": d2h // 2,
+                            "what": "mrp_fg_process_host with raw = NULL (not the headline: the reference emits both matrices)"}
+        copy_loop(True)
+        both_ms, h2d_ms = copy_loop(True), copy_loop(False)
+        e2e["ceiling"] = {"both_directions_ms": both_ms, "h2d_only_ms": h2d_ms, "h2d_only_gbs": h2d / h2d_ms * 1e-6,
+                          "both_h2d_gbs": h2d / both_ms * 1e-6, "both_d2h_gbs": d2h / both_ms * 1e-6,
+                          "what": "the same pinned buffers and byte counts moved by plain cudaMemcpyAsync in 256 MB pieces on two streams, no kernels (max over ranks)"}
+        e2e["frac_of_copy_ceiling"] = both_ms / e_ms
         del host, hv, raw_h, norm_h   # 37 GB of pinned memory per rank: released before anything else is staged
 
     cpu = None

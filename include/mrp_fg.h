@@ -185,11 +185,12 @@ int mrp_fg_bind_inputs(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view);
 int mrp_fg_upload(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, void* stream);
 
 /* Host-resident data in, host-resident features out (what a pipeline holding pinned host arrays calls): every stream
- * of the HOST view is cut into time chunks of `chunk_rows` snapshots (0 = default, 4 Mi rows) that are uploaded,
+ * of the HOST view is cut into time chunks of at most `chunk_rows` snapshots (0 = default, 2 Mi rows; the first and last chunks of a call are shorter) that are uploaded,
  * computed and downloaded on two alternating device buffer sets / CUDA streams, so PCIe runs in both directions while
  * the SMs compute.  A chunk is preceded by a halo (norm_window + EMA warm-up rows, one window of ticks / trades)
  * re-read from the host; results equal the single-shot upload / run / download sequence to within the EMA warm-up
- * (< 1e-17 of the column scale), including the normaliser's "poisoned for ever" columns, whose state is carried across chunks.  raw, norm: HOST double [19][n_rows] (pinned memory recommended).  Synchronous.
+ * (< 1e-17 of the column scale), including the normaliser's "poisoned for ever" columns, whose state is carried across chunks.  raw, norm: HOST double [19][n_rows] (pinned memory recommended); ONE of them may be
+ * NULL — that matrix is not copied back (a consumer of the `_norm.csv` half only: half the device-to-host bytes).  Synchronous.
  * Replaces, for every row: FeatureProcessor::GetRawFeatureSet + GetProcessedFeatureSet (feature_processor.cpp:11-29). */
 int mrp_fg_process_host(mrp_fg_ctx* ctx, const mrp_fg_soa_view* view, double* raw, double* norm, int64_t chunk_rows);
 

@@ -226,11 +226,12 @@ class Engine:
                      raw_ptr: int = 0, norm_ptr: int = 0):
         """raw / norm: numpy [19, n] outputs (allocated when omitted), or raw_ptr / norm_ptr: addresses of pinned buffers."""
         n = hv.n_rows
-        if not raw_ptr:
+        if not raw_ptr and not norm_ptr:
             raw = raw if raw is not None else np.empty((NUM_FEATURES, n), np.float64)
             norm = norm if norm is not None else np.empty((NUM_FEATURES, n), np.float64)
             raw_ptr, norm_ptr = raw.ctypes.data, norm.ctypes.data
-        self._check(self.lib.mrp_fg_process_host(self.ctx, C.byref(hv.view), C.c_void_p(raw_ptr), C.c_void_p(norm_ptr), chunk_rows))
+        # with raw_ptr / norm_ptr, ONE of the two may be 0: that matrix is not copied back
+        self._check(self.lib.mrp_fg_process_host(self.ctx, C.byref(hv.view), C.c_void_p(raw_ptr or None), C.c_void_p(norm_ptr or None), chunk_rows))
         return raw, norm
 
     # -- rolling state from per-event arrays (mrp_fg_build_state)

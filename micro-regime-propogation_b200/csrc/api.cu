@@ -147,12 +147,16 @@ struct mrp_fg_ctx {
     bool ev_made = false;
     int64_t launches = 0;
     // mrp_fg_process_host: two child contexts (device buffer sets), each with its own non-blocking stream
-    mrp_fg_ctx* lane[2] = {nullptr, nullptr};
-    cudaStream_t lane_stream[2] = {nullptr, nullptr};
-    cudaEvent_t lane_done[2] = {nullptr, nullptr};
-    uint32_t* lane_cursors[2] = {nullptr, nullptr};   // pinned: rebased tick / trade cursors of the chunk in flight
-    size_t lane_cursor_cap[2] = {0, 0};
-    long long* pin_carry = nullptr;        // pinned: [57] "none" (resets the carry at a stream's start) + [2] the lanes' slice_row0
+    // mrp_fg_process_host: kLanes device buffer sets / streams.  Two are enough: three were measured (475.8 ms against 477.0 ms per
+    // 50 M rows — a lane's next upload waits for its previous download, but the host's per-chunk preparation is not what the
+    // upload engine waits for), so the third set of device buffers is not spent.
+    static constexpr int kLanes = 2;
+    mrp_fg_ctx* lane[kLanes] = {};
+    cudaStream_t lane_stream[kLanes] = {};
+    cudaEvent_t lane_done[kLanes] = {};
+    uint32_t* lane_cursors[kLanes] = {};   // pinned: rebased tick / trade cursors of the chunk in flight
+    size_t lane_cursor_cap[kLanes] = {};
+    long long* pin_carry = nullptr;        // pinned: [57] "none" (resets the carry at a stream's start) + [kLanes] the lanes' slice_row0
     cudaEvent_t run_chain = nullptr;       // the chunks' kernels run in stream order across the two lanes (the carry is a chain)
     // non-finite state of the normaliser carried across time chunks / shards (k_norm_poison): [n_streams][19][3] absolute rows + the
     // absolute row of each bound stream's first row; null = the bound streams start at their stream's first row
@@ -503,7 +507,7 @@ int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out) {
 int mrp_fg_destroy(mrp_fg_ctx* c) {
     if (!c) return MRP_FG_OK;
     cudaSetDevice(c->device);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < mrp_fg_ctx::kLanes; ++i) {
         if (c->lane[i]) mrp_fg_destroy(c->lane[i]);
         if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
         if (c->lane_done[i]) cudaEventDestroy(c->lane_done[i]);
@@ -653,7 +657,7 @@ int mrp_fg_upload(mrp_fg_ctx* c, const mrp_fg_soa_view* v, void* stream) {
 // one of two lanes (device buffer set + non-blocking stream) while chunk i+1 travels on the other.  Every state of the
 // path has finite memory, so a chunk's own rows are exact (EMAs agree to < 1e-17 of their scale).
 int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, double* norm, int64_t chunk_rows) {
-    if (!c || !raw || !norm) return fail(MRP_FG_ERR_INVALID, "NULL argument");
+    if (!c || (!raw && !norm)) return fail(MRP_FG_ERR_INVALID, "NULL argument (one of raw / norm may be NULL, not both)");
     int rc = check_view(c, v, MRP_MEM_HOST);
     if (rc) return rc;
     CU(cudaSetDevice(c->device));
@@ -663,9 +667,10 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
     if (!v->buy_vol || !v->sell_vol || !v->adds)
         return fail(MRP_FG_ERR_INVALID, "mrp_fg_process_host needs buy_vol / sell_vol / adds in the view (mrp_fg_build_state works on a bound batch)");
     const int64_t H = mrp_fg_halo_rows(c);
-    if (chunk_rows <= 0) chunk_rows = 4 << 20;
+    if (chunk_rows <= 0) chunk_rows = 2 << 20;   // measured at 50 M rows: 1 / 2 / 3 / 4 Mi rows -> 489 / 481 / 482 / 491 ms
     const int64_t wmax = std::max(c->p.mid_window, c->p.dir_window + 1);
-    for (int i = 0; i < 2; ++i) {
+    constexpr int kLanes = mrp_fg_ctx::kLanes;
+    for (int i = 0; i < kLanes; ++i) {
         if (!c->lane[i]) {
             mrp_fg_params p = c->p;
             p.emit_dirs = p.emit_counts = 0;
@@ -679,21 +684,21 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
     // travels from chunk to chunk in a device table; the chunks' kernels are chained across the two lanes by one event
     constexpr int kCarry = MRP_FG_NUM_FEATURES * 3;
     if (!c->pin_carry) {
-        CU(cudaMallocHost(reinterpret_cast<void**>(&c->pin_carry), sizeof(long long) * (kCarry + 2)));
+        CU(cudaMallocHost(reinterpret_cast<void**>(&c->pin_carry), sizeof(long long) * (kCarry + kLanes)));
         for (int i = 0; i < kCarry; ++i) c->pin_carry[i] = 0x7fffffffffffffffll;
         CU(cudaEventCreateWithFlags(&c->run_chain, cudaEventDisableTiming));
     }
     if ((rc = c->b_carry.ensure(sizeof(long long) * kCarry))) return rc;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kLanes; ++i)
         if ((rc = c->lane[i]->b_slice_row0.ensure(sizeof(long long)))) return rc;
     bool chained = false;
-    bool busy[2] = {false, false};
+    bool busy[kLanes] = {};
     int li = 0;
     // whatever way this function is left, nothing may still be reading the caller's inputs or writing the caller's outputs
     struct Drain {
         mrp_fg_ctx* c;
         ~Drain() {
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < mrp_fg_ctx::kLanes; ++i)
                 if (c->lane_stream[i]) cudaStreamSynchronize(c->lane_stream[i]);
         }
     } drain{c};
@@ -701,8 +706,18 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
         const int64_t r0 = v->row_offsets[s], r1 = v->row_offsets[s + 1];
         const int64_t k0 = v->tick_offsets[s], K = v->tick_offsets[s + 1] - k0;
         const int64_t j0 = v->trade_offsets[s], T = v->trade_offsets[s + 1] - j0;
-        for (int64_t a = r0; a < r1; a += chunk_rows, li ^= 1) {
-            const int64_t b = std::min(a + chunk_rows, r1);
+        // Chunk schedule: the first chunk's upload and the last chunk's download overlap nothing, so the call starts with
+        // chunk/8, chunk/4, chunk/2 and ends by halving what is left down to chunk/8 (measured at 50 M rows, 2 Mi-row chunks:
+        // the exposed head and tail shrink from ~40 ms to ~10 ms of a 480 ms call)
+        const int64_t min_chunk = std::max<int64_t>(1, chunk_rows >> 3);
+        int head = s == 0 ? 0 : 3;
+        int64_t b = r0;
+        for (int64_t a = r0; a < r1; a = b, li = (li + 1) % kLanes) {
+            const int64_t rem = r1 - a;
+            int64_t take = std::min(rem, chunk_rows);
+            if (head < 3 && rem > 2 * chunk_rows) take = std::max<int64_t>(1, chunk_rows >> (3 - head++));
+            else if (s == S - 1 && rem <= 2 * chunk_rows && rem > min_chunk) take = (rem + 1) / 2;
+            b = a + take;
             const int64_t e0 = std::max(r0, a - H);           // first halo row
             const int64_t n = b - e0;
             int64_t tb = 0, jb = 0;                            // tick / trade bases: the slice's "stream start"
@@ -764,16 +779,18 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
             CU(cudaEventRecord(c->run_chain, st));
             chained = true;
             const int64_t skip = a - e0, own = b - a;
-            CU(copy_pitched(raw + a, (size_t)NT * 8, ln->out.raw + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
-                            cudaMemcpyDeviceToHost, st));
-            CU(copy_pitched(norm + a, (size_t)NT * 8, ln->out.norm + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
-                            cudaMemcpyDeviceToHost, st));
+            if (raw)    // a matrix the caller does not want stays on the device: half the device-to-host bytes
+                CU(copy_pitched(raw + a, (size_t)NT * 8, ln->out.raw + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
+                                cudaMemcpyDeviceToHost, st));
+            if (norm)
+                CU(copy_pitched(norm + a, (size_t)NT * 8, ln->out.norm + skip, (size_t)n * 8, (size_t)own * 8, MRP_FG_NUM_FEATURES,
+                                cudaMemcpyDeviceToHost, st));
             CU(cudaEventRecord(c->lane_done[li], st));
             busy[li] = true;
             c->launches += kNumKernels + 1;
         }
     }
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < kLanes; ++i)
         if (busy[i]) CU(cudaEventSynchronize(c->lane_done[i]));
     CU(cudaGetLastError());
     (void)L;

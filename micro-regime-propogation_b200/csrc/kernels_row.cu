@@ -46,6 +46,12 @@ __device__ __noinline__ void lob_sums_direct(const double* __restrict__ bid_px, 
     *ask_lw = al;
 }
 
+// Library exponentials / logarithms sit on rare paths (a level that moved, a row outside the series range) but were inlined a
+// dozen times into the level loop: 1.2 k of its 2 k instructions, 350 of the tail's 1 k.  Out of line the chunk loop is 1.6 k
+// instructions instead of 3.1 k and fits the SM's 32 KB instruction cache (profiles/r2b_windows_experiments.md has the method).
+__device__ __noinline__ double exp_rare(double x) { return exp(x); }
+__device__ __noinline__ double log_diff_rare(double a, double b) { return log(a) - log(b); }
+
 // The EMA y_t = decay * y_{t-1} + b_t over a chunk, as a scan of affine maps.  pw2 = decay^(1,2,4,8,16,32)
 // (kernel-parameter constants: operands, not loads); pw[n] = decay^n per lane.  Two halves around ONE block barrier so
 // that several EMAs share it: ema_warp (in-warp scan, publishes the warp's total), then ema_block (carries across warps).
@@ -293,17 +299,17 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
                         const int j = (g >= 1 && g <= kStressCache) ? g - 1 : 0;
                         if ((ub && xb != cx[j]) || (ua && xa != cx[j])) {   // rare: something moved
                             if (ub) {
-                                if (xb != cx[j]) { cx[j] = xb; ce[j] = exp(xb); }
+                                if (xb != cx[j]) { cx[j] = xb; ce[j] = exp_rare(xb); }
                                 liq_b += ce[j] * fbs;
                             }
-                            if (ua) liq_a += ((xa == cx[j]) ? ce[j] : exp(xa)) * fas;
+                            if (ua) liq_a += ((xa == cx[j]) ? ce[j] : exp_rare(xa)) * fas;
                         } else {
                             liq_b += ub ? ce[j] * fbs : 0.0;
                             liq_a += ua ? ce[j] * fas : 0.0;
                         }
                     } else {
-                        if (ub) liq_b += exp(xb) * fbs;
-                        if (ua) liq_a += exp(xa) * fas;
+                        if (ub) liq_b += exp_rare(xb) * fbs;
+                        if (ua) liq_a += exp_rare(xa) * fas;
                     }
                 }
             }
@@ -353,14 +359,14 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
 
         if (full) {
             // log_spread = log(ask0) - log(bid0), :33
-            const double log_spread = (spread0_ok && !oor) ? spread0 : log(ba) - log(bb);
+            const double log_spread = (spread0_ok && !oor) ? spread0 : log_diff_rare(ba, bb);
             // log_return, :37-42: the normaliser deque holds min(t, W) earlier rows when row t asks for index `lag`
             const int64_t tl = t - sr0;
             const int64_t have = tl < P.norm_window ? tl : P.norm_window;
             double log_ret = 0.0;
             if ((int64_t)P.return_lag < have && old_mid > 0.0) {
                 const double u = (midp - old_mid) * old_inv;
-                log_ret = fabs(u) <= kSeriesMax ? log1p_series(u) : log(midp) - log(old_mid);
+                log_ret = fabs(u) <= kSeriesMax ? log1p_series(u) : log_diff_rare(midp, old_mid);
             }
             double rate = 0.0;  // :143-151
             if (pts > 0ull) {

@@ -91,7 +91,7 @@ constexpr int kTradeRun = 10;                      // consecutive trades per lan
 //                        rolled, 6.7 ms with the arithmetic loop unrolled)
 //   MRP_WIN_ORDER        consumers: 1 = plan, gather, finalise; 0 = gather, finalise, plan (rings released 800 cycles earlier: slower)
 //   MRP_WIN_PROD_WARPS / MRP_WIN_RUN   4 x 11 (default) 6.16 ms; 5 x 9 6.70; 6 x 7 6.48; 7 x 7 6.38; 8 x 5 6.45
-constexpr int kMathUnroll = MRP_WIN_MATH_UNROLL, kStoreUnroll = MRP_WIN_STORE_UNROLL;
+[[maybe_unused]] constexpr int kMathUnroll = MRP_WIN_MATH_UNROLL, kStoreUnroll = MRP_WIN_STORE_UNROLL;
 constexpr int kDepth = MRP_WIN_DEPTH;              // chunks in flight ahead of the one being produced
 constexpr int kStages = kDepth + 1;                // staging buffers
 constexpr int kPlans = 8;                          // plan slots: chunk q lives in slot q & 7 (planned in iteration q - kDepth, gathered in q + 1)

@@ -82,3 +82,21 @@ def test_poisoned_columns_stay_poisoned_across_chunks():
     assert poisoned.sum() >= 3                             # several columns are NaN to the end of the stream
     fin = np.isfinite(ref["norm"])
     assert np.allclose(norm[fin], one["norm"][fin], rtol=0, atol=1e-6)
+
+
+def test_one_output_may_be_left_on_the_device():
+    """raw == NULL or norm == NULL: that matrix is not copied back; the other one is byte-identical to the two-output call."""
+    hv = mrp_b200.HostView(synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=30_000, seed=171)])))
+    p = mrp_b200.default_params(norm_window=4000)
+    eng = mrp_b200.Engine(p, device=0)
+    raw, norm = eng.process_host(hv, chunk_rows=8000)
+    only = np.full_like(norm, -7.0)
+    eng.process_host(hv, chunk_rows=8000, norm_ptr=only.ctypes.data)
+    assert np.array_equal(only, norm, equal_nan=True)
+    only[:] = -7.0
+    eng.process_host(hv, chunk_rows=8000, raw_ptr=only.ctypes.data)
+    assert np.array_equal(only, raw, equal_nan=True)
+    with pytest.raises(mrp_b200.MrpError):
+        eng.lib.mrp_fg_process_host.restype = int
+        eng._check(eng.lib.mrp_fg_process_host(eng.ctx, None, None, None, 0))
+    eng.close()
