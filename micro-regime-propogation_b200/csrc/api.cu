@@ -112,6 +112,7 @@ struct PinBuf {
 struct mrp_fg_ctx {
     mrp_fg_params p{};
     int device = 0;
+    int sm_count = 148;   // multiprocessors of the device (segment lengths are chosen per batch against it)
     bool bound = false;
     int n_streams = 0;
     int64_t n_rows = 0, n_ticks = 0, n_trades = 0;
@@ -367,9 +368,22 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     }
 
     // row segments: enough CTAs to fill 148 SMs several times over, long enough to amortise the window halo
-    int64_t seg_rows = (N + 1183) / 1184;
-    seg_rows = std::min<int64_t>(std::max<int64_t>(seg_rows, 2048), 16384);
-    seg_rows = ((seg_rows + kThreads - 1) / kThreads) * kThreads;
+    // Both segment kernels run one CTA per SM, so a launch costs waves x (segment + halo): the halo (one EMA warm-up of the book pass,
+    // one window of ticks) is paid per segment, an unfilled last wave per launch.  Pick the whole-chunk length that minimises that
+    // product for THIS batch (streams are cut separately).  50 M rows: 16 128-16 384 rows as before; 32 x 46 600 rows: 5 376 rows,
+    // 288 segments = two waves, instead of 2 304 rows in five.
+    int64_t seg_rows = 16384;
+    {
+        const int sms = std::max(1, c->sm_count);
+        double best = 1e300;
+        for (int64_t cand = 4 * kThreads; cand <= 16384; cand += kThreads) {
+            int64_t nseg = 0;
+            for (int s2 = 0; s2 < S; ++s2) nseg += (c->row_off[s2 + 1] - c->row_off[s2] + cand - 1) / cand;
+            const int64_t waves = (nseg + sms - 1) / sms;
+            const double cost = (double)waves * (double)(cand + c->dp.ema_warm_rows);
+            if (cost <= best) { best = cost; seg_rows = cand; }   // ties: the longer segment (fewer halos)
+        }
+    }
     if (const char* e = std::getenv("MRP_FG_SEGMENT_ROWS")) {
         long v2 = std::atol(e);
         if (v2 >= 1) seg_rows = v2;
@@ -494,6 +508,7 @@ int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out) {
     mrp_fg_ctx* c = new mrp_fg_ctx();
     c->p = pp;
     c->device = device;
+    c->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("MRP_FG_TWO_STREAMS")) c->two_streams = std::atoi(e) != 0;
     rc = setup_params(c);
     if (rc) {

@@ -29,8 +29,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture
 def bench_shape(monkeypatch):
-    """The code path of the 50 M-row benchmark: 16 384-row segments, 2 000-row normaliser tiles."""
-    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "16384")
+    """The code path of the 50 M-row benchmark: 15 360-row segments (what the wave-aware choice in setup_shape picks for 50 M rows on
+    148 SMs), 2 000-row normaliser tiles."""
+    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "15360")
     monkeypatch.setenv("MRP_FG_NORM_TILE", "2000")
     yield
 

@@ -53,7 +53,7 @@ def test_boundary_rows_at_the_real_window(monkeypatch):
 
     from helpers import ORACLE_WARM_ROWS, column_report, nan_pattern_equal, norm_check, oracle_on_windows, parity_record
 
-    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "16384")
+    monkeypatch.setenv("MRP_FG_SEGMENT_ROWS", "15360")
     monkeypatch.setenv("MRP_FG_NORM_TILE", "2000")
     W, N, world = 30000, 140_000, 2
     p = mrp_b200.default_params(emit_dirs=1, emit_counts=1)
