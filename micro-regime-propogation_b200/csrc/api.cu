@@ -18,6 +18,8 @@
 namespace mrp {
 cudaError_t launch_windows(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
 cudaError_t launch_book(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, cudaStream_t);
+cudaError_t launch_book_direct(const DevInputs&, const DevOutputs&, const DevSegment*, int, const DevParams&, int, cudaStream_t);
+bool book_direct_supported(const DevParams&);
 cudaError_t launch_normalize(const DevOutputs&, int64_t, const DevTile*, int, double*, int*, void*, const int64_t*, int, long long*, const long long*,
                              const DevParams&, cudaStream_t);
 cudaError_t launch_norm_poison(const DevOutputs&, int64_t, void*, const int64_t*, int, long long*, const long long*, const DevParams&, cudaStream_t);
@@ -175,6 +177,13 @@ struct mrp_fg_ctx {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_aux[2] = {nullptr, nullptr};
     int two_streams = 0;
+    // Co-scheduling (mrp_fg_run): k_windows keeps one CTA per SM busy at ~40 % of the issue slots; a share of the book pass's
+    // segments is worked off beside it by the staging-free k_book form (one 160-thread CTA fits into what k_windows leaves of an
+    // SM).  k_windows runs on an internal high-priority stream so that its next CTA, not a second staging-free CTA, takes the
+    // slot a finished k_windows CTA frees.
+    double corun_frac = 0.0;              // share of the segments given to the staging-free form (0 = off)
+    cudaStream_t hi_stream = nullptr;     // k_windows when co-scheduling
+    cudaEvent_t ev_win = nullptr;
 };
 
 namespace {
@@ -216,14 +225,14 @@ int pick_tile_rows(int W, int64_t n_rows) {
 }
 
 // Rows after which both row-axis EMAs have forgotten their start (decay^rows < 1e-17 for the slower one; also covers the
-// return lag), rounded up to whole chunks of the book pass.  -1: the alphas are out of range.
+// return lag), rounded up to whole 128-row blocks.  -1: the alphas are out of range.
 int ema_warm_rows_for(const mrp_fg_params& p) {
     const double slow = std::max(1.0 - p.ofi_alpha, 1.0 - p.stress_alpha);
     int warm = 0;
     if (slow > 0.0 && slow < 1.0) warm = (int)std::ceil(std::log(1e-17) / std::log(slow));
     else if (slow >= 1.0) return -1;
     warm = std::max(warm, p.return_lag + 1);
-    return ((warm + kThreads - 1) / kThreads) * kThreads;
+    return ((warm + 127) / 128) * 128;   // whole 128-row blocks (384 rows for the reference's alphas), whatever the book kernel's chunk length
 }
 
 // Build device parameters, ring geometry and the host-computed constant tables.
@@ -510,6 +519,7 @@ int mrp_fg_create(const mrp_fg_params* p, int device, mrp_fg_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (const char* e = std::getenv("MRP_FG_TWO_STREAMS")) c->two_streams = std::atoi(e) != 0;
+    if (const char* e = std::getenv("MRP_FG_CORUN")) c->corun_frac = std::min(0.9, std::max(0.0, std::atof(e)));
     rc = setup_params(c);
     if (rc) {
         delete c;
@@ -542,6 +552,8 @@ int mrp_fg_destroy(mrp_fg_ctx* c) {
     if (c->ev_made)
         for (auto& ev : c->ev) cudaEventDestroy(ev);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->hi_stream) cudaStreamDestroy(c->hi_stream);
+    if (c->ev_win) cudaEventDestroy(c->ev_win);
     for (cudaEvent_t ev : {c->ev_fork, c->ev_join, c->ev_aux[0], c->ev_aux[1]})
         if (ev) cudaEventDestroy(ev);
     delete c;
@@ -830,6 +842,17 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
         for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
         c->ev_made = true;
     }
+    const int n_direct = (c->corun_frac > 0.0 && !c->two_streams && book_direct_supported(c->dp) && c->nseg >= 2)
+                             ? (int)(c->corun_frac * c->nseg) : 0;
+    if (n_direct > 0 && !c->hi_stream) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&c->hi_stream, cudaStreamNonBlocking, greatest));
+        CU(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, least));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_win, cudaEventDisableTiming));
+    }
     if (c->two_streams && !c->aux_stream) {
         CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -849,6 +872,19 @@ int mrp_fg_run(mrp_fg_ctx* c, void* stream) {
         CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, st));
         if (tm) CU(cudaEventRecord(c->ev[1], st));
         CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+    } else if (n_direct > 0) {
+        CU(cudaEventRecord(c->ev_fork, st));
+        CU(cudaStreamWaitEvent(c->hi_stream, c->ev_fork, 0));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, c->hi_stream));   // first: one CTA on every SM
+        CU(cudaEventRecord(c->ev_win, c->hi_stream));
+        CU(launch_book_direct(c->in, c->out, segs, n_direct, c->dp, 0, c->aux_stream));   // ... then what still fits beside them
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        CU(cudaStreamWaitEvent(st, c->ev_win, 0));
+        if (tm) CU(cudaEventRecord(c->ev[1], st));   // "windows" = until k_windows is done (part of the book pass ran beside it)
+        CU(launch_book(c->in, c->out, segs + n_direct, c->nseg - n_direct, c->dp, st));   // "book" = what is left of it after that
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
+        c->launches += 1;
     } else {
         CU(launch_windows(c->in, c->out, segs, c->nseg, c->dp, st));
         if (tm) CU(cudaEventRecord(c->ev[1], st));

@@ -105,13 +105,18 @@ struct __align__(16) BookStage {
 };
 
 // LG = levels per staged batch (it divides the depth L, so the level loop carries no bounds predicates), NS = stages.
-template <int LG, int NS>
-__global__ void __launch_bounds__(kThreads, MRP_BOOK_MINB)
+// T = threads (= rows per chunk).  DIRECT: no staging at all — every thread loads its own row's levels from global memory.  That
+// form is slower on its own (few warps, exposed load latency) but needs 6 KB of shared memory instead of 94 and a third of the
+// registers per CTA, so two of its 96-thread CTAs fit on an SM BESIDE k_windows' one CTA (which holds 215 KB of shared memory
+// but leaves 60 % of the issue slots idle): mrp_fg_run gives it a share of the segments to work off in k_windows' shadow.
+template <int LG, int NS, int T, bool DIRECT>
+__global__ void __launch_bounds__(T, DIRECT ? 1 : MRP_BOOK_MINB)
 k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ segs, const DevParams P) {
-    static_assert(4 * LG <= 32 * kWarps, "one lane per (array, level) run of a batch");
+    constexpr int kThreads = T, kWarps = T / 32;   // shadow the namespace constants: everything below is per instantiation
+    static_assert(DIRECT || 4 * LG <= 32 * kWarps, "one lane per (array, level) run of a batch");
     extern __shared__ __align__(16) unsigned char book_dyn[];
     BookStage<LG>* __restrict__ stg = reinterpret_cast<BookStage<LG>*>(book_dyn);
-    double* __restrict__ sOfiW = reinterpret_cast<double*>(book_dyn + sizeof(BookStage<LG>) * NS);  // [L] depth weights
+    double* __restrict__ sOfiW = reinterpret_cast<double*>(book_dyn + (DIRECT ? 0 : sizeof(BookStage<LG>) * NS));  // [L] depth weights
     __shared__ double sInv[2][kThreads], sMid[2][kThreads];
     __shared__ double sWarpLiq[kWarps], sCarLiq;
     __shared__ double sWOfi[kWarps], sWSt[kWarps];
@@ -136,13 +141,15 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     if (tid == 0) {
         sCarLiq = 0.0;
         sYOfi[0] = sYOfi[1] = sYSt[0] = sYSt[1] = 0.0;
+        if constexpr (!DIRECT) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&sFull[s], 4 * LG);     // one arrival (with its byte count) per requesting lane
-            mbar_init(&sEmpty[s], kWarps);    // one arrival per warp that has finished reading the stage
+            for (int s = 0; s < NS; ++s) {
+                mbar_init(&sFull[s], 4 * LG);     // one arrival (with its byte count) per requesting lane
+                mbar_init(&sEmpty[s], kWarps);    // one arrival per warp that has finished reading the stage
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         }
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     for (int i = tid; i < L; i += kThreads) sOfiW[i] = P.ofi_weight[i];
     int buf = 0;
@@ -171,6 +178,7 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
     const int64_t step_in = (int64_t)LG * N;                      // next level group, same chunk
     const int64_t step_out = kThreads - (int64_t)(nb - 1) * LG * N;   // first level group of the next chunk
     auto request = [&]() {
+        if constexpr (DIRECT) return;
         if (ic < rb) {
             const int s = nreq % NS;
             if (nreq >= NS) mbar_wait(&sEmpty[s], (uint32_t)((nreq / NS - 1) & 1));
@@ -224,28 +232,52 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
         int8_t* __restrict__ oad = out.adir + tc;
         for (int i0 = 0; i0 < L; i0 += LG) {
             request();   // keeps NS-1 batches in flight
-            const int sidx = nuse % NS;
-            mbar_wait(&sFull[sidx], (uint32_t)((nuse / NS) & 1));
+            const int sidx = DIRECT ? 0 : nuse % NS;
+            if constexpr (!DIRECT) mbar_wait(&sFull[sidx], (uint32_t)((nuse / NS) & 1));
             ++nuse;
             const BookStage<LG>& S = stg[sidx];
+            // DIRECT: this row's LG levels straight from global memory, all 6 * LG loads issued before the first use
+            double dbp[DIRECT ? LG : 1], dap[DIRECT ? LG : 1];
+            int dbs[DIRECT ? LG : 1], das[DIRECT ? LG : 1], dqb[DIRECT ? LG : 1], dqa[DIRECT ? LG : 1];
+            if constexpr (DIRECT) {
+                const int64_t e = (int64_t)i0 * N + tc;
+#pragma unroll
+                for (int g = 0; g < LG; ++g) {
+                    dbp[g] = __ldg(in.bid_px + e + (int64_t)g * N);
+                    dap[g] = __ldg(in.ask_px + e + (int64_t)g * N);
+                    dbs[g] = __ldg(in.bid_sz + e + (int64_t)g * N);
+                    das[g] = __ldg(in.ask_sz + e + (int64_t)g * N);
+                    dqb[g] = hasprev ? __ldg(in.bid_sz + e + (int64_t)g * N - 1) : 0;
+                    dqa[g] = hasprev ? __ldg(in.ask_sz + e + (int64_t)g * N - 1) : 0;
+                }
+            }
             if (i0 == 0) {
-                const int4 sh = S.shift[0];
-                bb = S.bp[0][sh.x + tid];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
-                ba = S.ap[0][sh.y + tid];
+                if constexpr (DIRECT) {
+                    bb = dbp[0];
+                    ba = dap[0];
+                } else {
+                    const int4 sh = S.shift[0];
+                    bb = S.bp[0][sh.x + tid];  // level 0 == best bid / ask (feature_engine.cpp:22-28)
+                    ba = S.ap[0][sh.y + tid];
+                }
                 midp = (ba + bb) / 2;  // feature_processor.cpp:34,161
                 inv_mid = 1.0 / midp;
             }
 #pragma unroll
             for (int g = 0; g < LG; ++g) {
                 const int i = i0 + g;
-                const int4 sh = S.shift[g];
-                const double bp = S.bp[g][sh.x + tid], ap = S.ap[g][sh.y + tid];
-                const int bs = S.bs[g][sh.z + tid], as = S.as[g][sh.w + tid];
-                // first snapshot compares with an empty book (order_book.cpp:115,168)
-                int qb = 0, qa = 0;
-                if (hasprev) {
-                    qb = S.bs[g][sh.z + tid - 1];
-                    qa = S.as[g][sh.w + tid - 1];
+                double bp, ap;
+                int bs, as, qb = 0, qa = 0;   // first snapshot compares with an empty book (order_book.cpp:115,168)
+                if constexpr (DIRECT) {
+                    bp = dbp[g]; ap = dap[g]; bs = dbs[g]; as = das[g]; qb = dqb[g]; qa = dqa[g];
+                } else {
+                    const int4 sh = S.shift[g];
+                    bp = S.bp[g][sh.x + tid]; ap = S.ap[g][sh.y + tid];
+                    bs = S.bs[g][sh.z + tid]; as = S.as[g][sh.w + tid];
+                    if (hasprev) {
+                        qb = S.bs[g][sh.z + tid - 1];
+                        qa = S.as[g][sh.w + tid - 1];
+                    }
                 }
                 const int bd = (bs > qb) - (bs < qb);  // order_book.cpp:208-239
                 const int ad = (as > qa) - (as < qa);
@@ -306,8 +338,10 @@ k_book(const DevInputs in, const DevOutputs out, const DevSegment* __restrict__ 
             }
             obd += (int64_t)LG * N;
             oad += (int64_t)LG * N;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sEmpty[sidx]);   // this warp is done with the stage
+            if constexpr (!DIRECT) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sEmpty[sidx]);   // this warp is done with the stage
+            }
         }
         if (oor && full) lob_sums_direct(in.bid_px, in.ask_px, in.bid_sz, in.ask_sz, N, tc, L, midp, &bid_lw, &ask_lw);
         const double liq = liq_b + liq_a;  // :301
@@ -400,16 +434,17 @@ static cudaError_t launch_book_t(const DevInputs& in, const DevOutputs& out, con
     if (e != cudaSuccess) return e;
     int& ready = ready_for[dev & 63];
     if (ready < bytes) {
-        e = cudaFuncSetAttribute(k_book<LG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        e = cudaFuncSetAttribute(k_book<LG, NS, kThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return e;
         ready = bytes;
     }
-    k_book<LG, NS><<<nseg, kThreads, bytes, st>>>(in, out, segs, P);
+    k_book<LG, NS, kThreads, false><<<nseg, kThreads, bytes, st>>>(in, out, segs, P);
     return cudaGetLastError();
 }
 
 cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg,
                         const DevParams& P, cudaStream_t st) {
+    if (nseg <= 0) return cudaSuccess;
     const int L = P.L;
 #if MRP_BOOK_LG10
     if (L % 10 == 0) return launch_book_t<10, 2>(in, out, segs, nseg, P, st);
@@ -418,6 +453,30 @@ cudaError_t launch_book(const DevInputs& in, const DevOutputs& out, const DevSeg
     if (L % 4 == 0) return launch_book_t<4, 2>(in, out, segs, nseg, P, st);
     if (L % 2 == 0) return launch_book_t<2, 3>(in, out, segs, nseg, P, st);
     return launch_book_t<1, 4>(in, out, segs, nseg, P, st);
+}
+
+// The staging-free form for the segments that are worked off beside k_windows (see the kernel's header).  Its dynamic shared
+// memory request is padded so that exactly kDirectPerSm of its CTAs fit into what k_windows leaves of an SM.
+#ifndef MRP_BOOK_DIRECT_THREADS
+#define MRP_BOOK_DIRECT_THREADS 96
+#endif
+constexpr int kDirectThreads = MRP_BOOK_DIRECT_THREADS;
+bool book_direct_supported(const DevParams& P) { return P.L % 5 == 0 && P.return_lag + 1 <= kDirectThreads; }
+cudaError_t launch_book_direct(const DevInputs& in, const DevOutputs& out, const DevSegment* segs, int nseg, const DevParams& P,
+                               int smem_pad, cudaStream_t st) {
+    if (nseg <= 0) return cudaSuccess;
+    const int bytes = P.L * (int)sizeof(double) + smem_pad;
+    static bool carve_set[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!carve_set[dev & 63]) {   // the same L1 / shared-memory split as k_windows, or the two could not share an SM
+        e = cudaFuncSetAttribute(k_book<5, 1, kDirectThreads, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+        carve_set[dev & 63] = true;
+    }
+    k_book<5, 1, kDirectThreads, true><<<nseg, kDirectThreads, bytes, st>>>(in, out, segs, P);
+    return cudaGetLastError();
 }
 
 }  // namespace mrp

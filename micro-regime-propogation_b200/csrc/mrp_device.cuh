@@ -88,7 +88,9 @@ struct DevParams {
 };
 
 #ifndef MRP_BOOK_THREADS
-#define MRP_BOOK_THREADS 384   // measured: 384 x 1 CTA/SM (up to 168 registers) 4.88 ms, 256 x 2 (128 registers) 4.99 ms at 50 M rows
+#define MRP_BOOK_THREADS 512   // measured at 50 M rows, one CTA per SM: 384 threads (146 registers) 4.79 ms, 416 5.04, 448 4.82, 512 (123 registers, no
+                               // spills) 4.38, 512 with three stages 4.45, 576 5.39, 640 5.08, 768 5.61.  (Round 1's kernel needed 168 registers: 384 x 1
+                               // 4.88 ms against 256 x 2 at 128 registers 4.99 ms; the leaner round-2 kernel fits sixteen warps.)
 #endif
 constexpr int kThreads = MRP_BOOK_THREADS;   // CTA size of the book pass (= rows per chunk)
 constexpr int kWarps = kThreads / 32;

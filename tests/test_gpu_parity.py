@@ -58,3 +58,25 @@ def test_multi_stream_device_pointers():
 def test_normaliser_window_eviction():
     # longer than WINDOW_SIZE = 30000 rows so the rolling z-score window evicts
     _check(make_host_batch([synth.SynthSpec(n_rows=33500, seed=13)]))
+
+
+def test_coscheduled_book_share_matches_the_default_run(monkeypatch):
+    """MRP_FG_CORUN (experiment switch, default off): a share of the book pass's segments runs as the staging-free k_book form on a
+    low-priority stream beside k_windows.  Same arithmetic per row: every column is byte-identical to the default run except the
+    two row-axis EMAs (ofi, liquidity_stress), whose block scans are cut into chunks of another length (last-bit differences)."""
+    batch = synth.to_numpy(synth.make_batch([synth.SynthSpec(n_rows=9000, seed=77), synth.SynthSpec(n_rows=4000, seed=78, variable_cursors=True)]))
+    p = mrp_b200.default_params(norm_window=2000, emit_dirs=1, emit_counts=1)
+    _, one = run_gpu(batch, p)
+    monkeypatch.setenv("MRP_FG_CORUN", "0.5")
+    _, two = run_gpu(batch, p)
+    for k in ("bid_dir", "ask_dir", "counts"):
+        assert np.array_equal(one[k], two[k]), k
+    emas = {mrp_b200.FEATURES.index("ofi"), mrp_b200.FEATURES.index("liquidity_stress")}
+    for c in range(mrp_b200.NUM_FEATURES):
+        if c in emas:
+            scale = np.nanmax(np.abs(one["raw"][c]))
+            assert np.allclose(one["raw"][c], two["raw"][c], rtol=1e-12, atol=1e-15 * scale, equal_nan=True), mrp_b200.FEATURES[c]
+            assert np.allclose(one["norm"][c], two["norm"][c], rtol=1e-7, atol=1e-9, equal_nan=True), mrp_b200.FEATURES[c]
+        else:
+            assert np.array_equal(one["raw"][c], two["raw"][c], equal_nan=True), mrp_b200.FEATURES[c]
+            assert np.array_equal(one["norm"][c], two["norm"][c], equal_nan=True), mrp_b200.FEATURES[c]
