@@ -201,7 +201,8 @@ int check_params(const mrp_fg_params& p) {
 // Normaliser tile: a divisor of the window W (so that a window is a whole number of tiles).  A warp sweeps 128 rows
 // per step, 4 per lane: multiples of 4 keep the 256-bit accesses, little waste in the last step.  Larger tiles
 // amortise the per-tile look-back (measured: 4.8 ms at 1000 rows, 4.4 ms at 2000-3000 on 50 M rows), but the batch must
-// still offer a few thousand tiles to fill 148 SMs x 3 CTAs, so the choice depends on the row count.
+// still offer a round of tiles for 148 SMs x 2 CTAs, so the choice depends on the row count (round 1 asked for 3000 tiles, which
+// picked 500-row tiles for 32 x 46 600 rows: 0.244 ms against 0.176 ms with 2000-row tiles; 200 k rows still prefer 500: 0.058 ms).
 int pick_tile_rows(int W, int64_t n_rows) {
     if (const char* e = std::getenv("MRP_FG_NORM_TILE")) {  // experiments
         const int t = std::atoi(e);
@@ -213,7 +214,8 @@ int pick_tile_rows(int W, int64_t n_rows) {
     for (int t = 128; t <= 3072 && t <= W; t += 4)
         if (W % t == 0) {
             const double eff = (double)t / (double)(((t + 127) / 128) * 128);   // last-step waste
-            const double fill = std::min(1.0, (double)(n_rows / t) / 3000.0);   // enough tiles for the machine
+            const double fill = std::min(1.0, (double)(n_rows / t) / 300.0);    // enough tiles for the machine: one round of 148 SMs x 2 CTAs
+                                                                                 // (measured at 32 x 46 600 rows: 500-row tiles 0.244 ms, 1000-2000 rows 0.176-0.181)
             const double size = std::min(1.0, 0.6 + 0.4 * (double)t / 2000.0);  // look-back amortisation
             const double s = eff * fill * size;
             if (s > best + 1e-12) { best = s; pick = t; }
