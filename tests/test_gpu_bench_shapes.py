@@ -1,7 +1,7 @@
 """GPU parity AT THE SHAPES THE BENCHMARK RUNS (SURVEY.md §8d "Parity runs").
 
 Segment length and normaliser tile are functions of the batch size (api.cu: setup_shape / pick_tile_rows), so the
-50 M-row benchmark runs 16 384-row segments and 2 000-row tiles.  These tests pin those two values and compare with
+50 M-row benchmark runs 15 360-row segments and 2 000-row tiles.  These tests pin those two values and compare with
 the compiled, unmodified reference (oracle/_ref, when it travelled with the repository; the C restatement otherwise):
 
   * one full instrument-day of 46 600 rows (BASELINE.json configs[0] / [2]);
