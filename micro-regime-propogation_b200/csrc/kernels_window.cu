@@ -54,10 +54,16 @@ namespace mrp {
 #ifndef MRP_WIN_WHATIF
 #define MRP_WIN_WHATIF 0   // timing experiments only (bit 0: no tick math, 1: no finalisation, 2: no warp scan, 3: no ring stores) — results are WRONG when set
 #endif
+#ifndef MRP_WIN_SPLIT_SPREAD
+#define MRP_WIN_SPLIT_SPREAD 0   // 1: the spread prefixes (QD1, QD2) are produced by warps of their own beside the midprice producers
+#endif
+constexpr bool kSplit = MRP_WIN_SPLIT_SPREAD != 0;
 constexpr int kProdWarps = MRP_WIN_PROD_WARPS, kConsWarps = 4;
-constexpr int kProd = kProdWarps * 32;             // producer threads
+constexpr int kProd = kProdWarps * 32;             // (midprice) producer threads
+constexpr int kSpread = kSplit ? kProd : 0;        // spread producer threads: the same ticks per thread as the midprice producers
+constexpr int kFirstCons = kProd + kSpread;        // first consumer thread
 constexpr int kCons = kConsWarps * 32;             // consumer threads == most rows of one chunk
-constexpr int kWinThreads = kProd + kCons + 32;    // + the trade warp
+constexpr int kWinThreads = kFirstCons + kCons + 32;    // + the trade warp
 constexpr int kRun = MRP_WIN_RUN;                  // consecutive ticks per producer thread (odd: conflict-free 64-bit shared accesses); long
                                                    // runs keep the per-thread scan overhead (~300 instructions) small next to the tick arithmetic
 constexpr int kTradeRun = 10;                      // consecutive trades per lane and pass of the trade warp: a chunk of 128 rows brings
@@ -91,6 +97,10 @@ constexpr int kTradeRun = 10;                      // consecutive trades per lan
 //                        rolled, 6.7 ms with the arithmetic loop unrolled)
 //   MRP_WIN_ORDER        consumers: 1 = plan, gather, finalise; 0 = gather, finalise, plan (rings released 800 cycles earlier: slower)
 //   MRP_WIN_PROD_WARPS / MRP_WIN_RUN   4 x 11 (default) 6.16 ms; 5 x 9 6.70; 6 x 7 6.48; 7 x 7 6.38; 8 x 5 6.45
+//   MRP_WIN_SPLIT_SPREAD 1: four more warps produce the spread prefixes (QD1, QD2), the midprice producers' loop shrinks from 1027
+//                        to 827 instructions — and the kernel goes from 6.02 to 6.22 ms (460 -> 501 M warp-instructions per 8 M rows at
+//                        41 -> 43 % issue-active): it is the TOTAL instruction count at ~0.45 instructions per scheduler-cycle that
+//                        sets the time, not the longest warp
 [[maybe_unused]] constexpr int kMathUnroll = MRP_WIN_MATH_UNROLL, kStoreUnroll = MRP_WIN_STORE_UNROLL;
 constexpr int kDepth = MRP_WIN_DEPTH;              // chunks in flight ahead of the one being produced
 constexpr int kStages = kDepth + 1;                // staging buffers
@@ -356,6 +366,7 @@ struct __align__(16) WinStatic {
     WinPlan plan[kPlans];              // chunk q lives in slot q & 7: planned in iteration q - kDepth, produced in q, gathered in q + 1
     uint64_t full[kStages];            // mbarriers of the staging buffers
     double wt[kProdWarps][6];          // per-warp totals: x, +-x, d, d^2, EMA, counts (bit pattern)
+    double wtS[kProdWarps][2];         // kSplit: the spread producers' per-warp totals d, d^2
     __align__(16) unsigned char stgT[kStages][kTradeStage];   // staged trade directions of the chunk (position JFprev - 1 onwards)
     double carryG;                     // the EMA after the chunk's last tick
     uint32_t excP1;                    // 1 + position of the last flagged tick (0 = none)
@@ -460,7 +471,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 #pragma unroll
                     for (int i = 0; i < kRun; ++i) {
                         m[i + 1] = sm[ib + i];
-                        d[i] = ss[ib + i] - pivot;
+                        d[i] = kSplit ? 0.0 : ss[ib + i] - pivot;
                     }
                     m[0] = sm[ib - 1];
                     if (nv == 0) m[1] = 1.0;
@@ -578,11 +589,12 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 #pragma unroll
                 for (int k = 0; k < ((MRP_WIN_WHATIF & 4) ? 0 : 5); ++k) {
                     const int dd = 1 << k;
-                    const double ua = shfl_up_d(va, dd), us = shfl_up_d(vs, dd), u1 = shfl_up_d(v1, dd), u2 = shfl_up_d(v2, dd),
-                                 ug = shfl_up_d(vg, dd);
+                    const double ua = shfl_up_d(va, dd), us = shfl_up_d(vs, dd), ug = shfl_up_d(vg, dd);
+                    const double u1 = kSplit ? 0.0 : shfl_up_d(v1, dd), u2 = kSplit ? 0.0 : shfl_up_d(v2, dd);
                     const uint32_t uc = __shfl_up_sync(0xffffffffu, vc, dd);
                     if (lane >= dd) {
-                        va += ua; vs += us; v1 += u1; v2 += u2;
+                        va += ua; vs += us;
+                        if (!kSplit) { v1 += u1; v2 += u2; }
                         vg = fma(pw2[k], ug, vg);
                         vc += uc;
                     }
@@ -592,7 +604,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     sh.wt[warp][5] = __longlong_as_double((long long)(((unsigned long long)(vc >> 16) << 32) | (vc & 0xffffu)));
                 }
                 // exclusive within the warp (by shuffle, not by subtraction)
-                double xa = shfl_up_d(va, 1), xs = shfl_up_d(vs, 1), x1 = shfl_up_d(v1, 1), x2 = shfl_up_d(v2, 1), xg = shfl_up_d(vg, 1);
+                double xa = shfl_up_d(va, 1), xs = shfl_up_d(vs, 1), xg = shfl_up_d(vg, 1);
+                double x1 = kSplit ? 0.0 : shfl_up_d(v1, 1), x2 = kSplit ? 0.0 : shfl_up_d(v2, 1);
                 uint32_t xc = __shfl_up_sync(0xffffffffu, vc, 1);
                 if (lane == 0) { xa = xs = x1 = x2 = xg = 0.0; xc = 0u; }
                 TM(3);
@@ -614,15 +627,17 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                         acc_i += __double_as_longlong(t);
                     }
                 }
-                double gA = __shfl_sync(0xffffffffu, mine_d, 0) + xa, gS = __shfl_sync(0xffffffffu, mine_d, 1) + xs,
-                       g1 = __shfl_sync(0xffffffffu, mine_d, 2) + x1, g2 = __shfl_sync(0xffffffffu, mine_d, 3) + x2;
+                double gA = __shfl_sync(0xffffffffu, mine_d, 0) + xa, gS = __shfl_sync(0xffffffffu, mine_d, 1) + xs;
+                double g1 = kSplit ? 0.0 : __shfl_sync(0xffffffffu, mine_d, 2) + x1, g2 = kSplit ? 0.0 : __shfl_sync(0xffffffffu, mine_d, 3) + x2;
                 double gG = fma(plane, __shfl_sync(0xffffffffu, mine_d, 4), xg);   // the EMA entering this thread's first tick
                 const unsigned long long mC = (unsigned long long)__shfl_sync(0xffffffffu, mine_i, 5);
                 uint32_t gNeg = (uint32_t)mC + (xc & 0xffffu), gMov = (uint32_t)(mC >> 32) + (xc >> 16);
                 cA = __shfl_sync(0xffffffffu, acc_d, 0);
                 cS = __shfl_sync(0xffffffffu, acc_d, 1);
-                cD1 = __shfl_sync(0xffffffffu, acc_d, 2);
-                cD2 = __shfl_sync(0xffffffffu, acc_d, 3);
+                if (!kSplit) {
+                    cD1 = __shfl_sync(0xffffffffu, acc_d, 2);
+                    cD2 = __shfl_sync(0xffffffffu, acc_d, 3);
+                }
                 cC = (unsigned long long)__shfl_sync(0xffffffffu, acc_i, 5);
                 // the consumers have lifted the previous chunk's values out of the rings: its far-end entries may be overwritten
                 TM(5);
@@ -647,12 +662,15 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                         const double ax = fabs(xv);
                         gA += ax;
                         gS += xv;
-                        g1 += dv;
-                        g2 = fma(dv, dv, g2);
+                        if (!kSplit) {
+                            g1 += dv;
+                            g2 = fma(dv, dv, g2);
+                        }
                         gG = fma(decay, gG, alpha * ax);
                         gNeg += (uint32_t)__double2hiint(xv) >> 31;
                         gMov += ax != 0.0 ? 1u : 0u;
-                        QA[slot] = gA; QS[slot] = gS; QD1[slot] = g1; QD2[slot] = g2; QG[slot] = gG;
+                        QA[slot] = gA; QS[slot] = gS; QG[slot] = gG;
+                        if (!kSplit) { QD1[slot] = g1; QD2[slot] = g2; }
                         QC[slot] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
                         if (++slot == (uint32_t)R) slot = 0u;
                     }
@@ -669,9 +687,88 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 #endif
         }
         if (warp == 0) TM_FLUSH(0);
-    } else if (warp < kProdWarps + kConsWarps) {
+    } else if (kSplit && tid < kFirstCons) {
+        // ================================================================================ spread producers: spreads -> QD1, QD2
+        // The same ticks per thread as the midprice producers, two quantities instead of six: the longest warp of a chunk walks
+        // ~800 instead of ~1040 instructions.  A thread that sees an absurd / non-finite spread flags its run like the midprice
+        // producers do (the two roles zero their own contributions independently: windows that contain the run are evaluated directly).
+        const int stid = tid - kProd, swarp = warp - kProdWarps;
+        double cD1 = 0.0, cD2 = 0.0;
+        __syncthreads();   // the first plans are visible
+        int stage = 0;
+        uint32_t phase = 0u;
+        for (int q = 0;; ++q) {
+            const WinPlan& pl = sh.plan[q & (kPlans - 1)];
+            if (pl.mode != PLAN_RUN) break;
+            const uint32_t TFp = pl.TFprev, TF = pl.TF;
+            mbar_wait(&sh.full[stage], phase);
+            const int stage_q = stage;
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (TF > TFp) {
+                const double* __restrict__ ss = stgS + stage_q * CTS + pl.shS;
+                const uint32_t k0 = TFp + (uint32_t)(kRun * stid);
+                const int i0 = (int)(k0 - pl.stg0);
+                const int nv = k0 < TF ? (int)min(TF - k0, (uint32_t)kRun) : 0;
+                const int ib = nv > 0 ? i0 : 1;
+                double d[kRun], v1 = 0.0, v2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < kRun; ++i) d[i] = ss[ib + i] - pivot;
+#pragma unroll
+                for (int i = 0; i < kRun; ++i) {
+                    if (i >= nv) d[i] = 0.0;
+                    v1 += d[i];
+                    v2 = fma(d[i], d[i], v2);
+                }
+                if (!(v2 < 1e300)) {
+                    if (nv > 0) atomicMax(&sh.excP1, k0 + (uint32_t)nv);
+#pragma unroll
+                    for (int i = 0; i < kRun; ++i) d[i] = 0.0;
+                    v1 = v2 = 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int dd = 1 << k;
+                    const double u1 = shfl_up_d(v1, dd), u2 = shfl_up_d(v2, dd);
+                    if (lane >= dd) { v1 += u1; v2 += u2; }
+                }
+                if (lane == 31) { sh.wtS[swarp][0] = v1; sh.wtS[swarp][1] = v2; }
+                double g1 = shfl_up_d(v1, 1), g2 = shfl_up_d(v2, 1);
+                if (lane == 0) g1 = g2 = 0.0;
+                bar_sync_n(4, kSpread);
+                {   // across the warps, in the midprice producers' order: carry, then warp 0, 1, ...
+                    double a1 = cD1, a2 = cD2, m1 = 0.0, m2 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kProdWarps; ++w) {
+                        if (w == swarp) { m1 = a1; m2 = a2; }
+                        a1 = fma(1.0, a1, sh.wtS[w][0]);
+                        a2 = fma(1.0, a2, sh.wtS[w][1]);
+                    }
+                    cD1 = a1;
+                    cD2 = a2;
+                    g1 += m1;
+                    g2 += m2;
+                }
+                bar_sync_n(3, kWinThreads);
+                uint32_t slot = pl.slotT + (uint32_t)(kRun * stid) + 1u;
+                if (slot >= (uint32_t)R) slot -= (uint32_t)R;
+#pragma unroll
+                for (int i = 0; i < kRun; ++i) {
+                    if (i < nv) {
+                        g1 += d[i];
+                        g2 = fma(d[i], d[i], g2);
+                        QD1[slot] = g1;
+                        QD2[slot] = g2;
+                        if (++slot == (uint32_t)R) slot = 0u;
+                    }
+                }
+            } else {
+                bar_sync_n(3, kWinThreads);
+            }
+            __syncthreads();   // the rings hold chunk q
+        }
+    } else if (tid < kFirstCons + kCons) {
         // ================================================================================ consumers: plan, gather, finalise
-        const int ci = tid - kProd, cw = warp - kProdWarps;
+        const int ci = tid - kFirstCons, cw = (tid - kFirstCons) >> 5;
         DirectParams dpm;
         dpm.mid_window = Wm;
         dpm.dir_window = Wd;
