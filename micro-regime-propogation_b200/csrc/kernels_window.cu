@@ -106,6 +106,7 @@ constexpr int kDepth = MRP_WIN_DEPTH;              // chunks in flight ahead of 
 constexpr int kStages = kDepth + 1;                // staging buffers
 constexpr int kPlans = 8;                          // plan slots: chunk q lives in slot q & 7 (planned in iteration q - kDepth, gathered in q + 1)
 static_assert(kDepth >= 1 && kDepth + 3 <= kPlans, "plan slots");
+constexpr int kRingPad = ((MRP_WIN_RUN + 1) / 2) * 2;   // entries past the end of each tick ring (a whole thread run; even: 16-byte alignment of what follows)
 constexpr int kChunkTrades = 512;                  // most new trades of one chunk (a chunk of 128 rows brings ~260)
 constexpr int kTradeStage = kChunkTrades + 32;     // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
 // the log1p series covers relative moves below 2^-10 per tick (high word 0x3f500000)
@@ -381,12 +382,15 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
     extern __shared__ __align__(16) unsigned char win_dyn[];
     __shared__ WinStatic sh;
     const int R = P.win_ring, RJ = P.win_trade_ring, CT = P.win_chunk_ticks, CJ = P.win_chunk_trades, CTS = CT + 4;
+    // every tick ring has kRingPad entries past its R: a thread stores its run linearly (no wrap test per element) and the one
+    // thread in ~300 whose run crosses the end copies the overhang to the ring's head afterwards
+    const int RP = R + kRingPad;
     double* __restrict__ QA = reinterpret_cast<double*>(win_dyn);
-    double* __restrict__ QS = QA + R;
-    double* __restrict__ QD1 = QS + R;
-    double* __restrict__ QD2 = QD1 + R;
-    double* __restrict__ QG = QD2 + R;
-    double* __restrict__ stgM = QG + R;                  // [kStages][CTS]
+    double* __restrict__ QS = QA + RP;
+    double* __restrict__ QD1 = QS + RP;
+    double* __restrict__ QD2 = QD1 + RP;
+    double* __restrict__ QG = QD2 + RP;
+    double* __restrict__ stgM = QG + RP;                 // [kStages][CTS]
     double* __restrict__ stgS = stgM + kStages * CTS;    // [kStages][CTS]
     unsigned long long* __restrict__ QT = reinterpret_cast<unsigned long long*>(stgS + kStages * CTS);   // [RJ]
 #if MRP_WIN_SLOG_SMEM
@@ -435,8 +439,10 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 
     if (warp < kProdWarps) {
         // ================================================================================ producers: ticks -> prefix rings
-        double cA = 0.0, cS = 0.0, cD1 = 0.0, cD2 = 0.0, cG = 0.0;   // the prefixes at the tick frontier
-        unsigned long long cC = 0ull;                               // ... of the two counters: did-not-rise | moved << 32
+        // the prefixes at the tick frontier, one quantity per lane: lane 0 sum x, 1 sum +-x, 2 sum d, 3 sum d^2, 4 the EMA (re-read
+        // from sh.carryG every chunk), 5 the two counters did-not-rise | moved << 32 (the other lanes shadow lane 0)
+        double car_d = 0.0;
+        long long car_i = 0;
         // decay^(11*2^k), decay^(11*lane), decay^352: the EMA composes over whole thread runs / warps
         double pw2[5];
 #pragma unroll
@@ -450,7 +456,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             const WinPlan& pl = sh.plan[q & (kPlans - 1)];
             if (pl.mode != PLAN_RUN) break;
             const uint32_t TFp = pl.TFprev, TF = pl.TF;
-            cG = sh.carryG;   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
+            if (lane == 4) car_d = sh.carryG;   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
             TM(0);
             mbar_wait(&sh.full[stage], phase);
             TM(1);
@@ -476,9 +482,11 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     m[0] = sm[ib - 1];
                     if (nv == 0) m[1] = 1.0;
                     if (!(nv > 0 && has_prev)) m[0] = m[1];   // the tick at the base has no predecessor: flat
+                    if (__any_sync(0xffffffffu, nv < kRun)) {   // only the warp that holds the frontier has partial or empty runs
 #pragma unroll
-                    for (int i = 0; i < kRun; ++i)
-                        if (i >= nv) { m[i + 1] = m[i]; d[i] = 0.0; }
+                        for (int i = 0; i < kRun; ++i)
+                            if (i >= nv) { m[i + 1] = m[i]; d[i] = 0.0; }
+                    }
                 }
                 double x[kRun];
                 uint32_t umax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
@@ -613,11 +621,10 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 TM(4);
                 // across the warps: lane l (< 6) walks quantity l over the warp totals; the four sums and the EMA share one
                 // fused multiply-add (factor 1 or decay^352), the counters an integer add
-                double mine_d = 0.0, acc_d;
-                long long mine_i = 0, acc_i = (long long)cC;
+                double mine_d = 0.0, acc_d = car_d;
+                long long mine_i = 0, acc_i = car_i;
                 {
                     const int ql = lane < 6 ? lane : 0;
-                    acc_d = ql == 0 ? cA : ql == 1 ? cS : ql == 2 ? cD1 : ql == 3 ? cD2 : cG;
                     const double mul = ql == 4 ? pwarp : 1.0;
 #pragma unroll
                     for (int w = 0; w < kProdWarps; ++w) {
@@ -632,13 +639,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 double gG = fma(plane, __shfl_sync(0xffffffffu, mine_d, 4), xg);   // the EMA entering this thread's first tick
                 const unsigned long long mC = (unsigned long long)__shfl_sync(0xffffffffu, mine_i, 5);
                 uint32_t gNeg = (uint32_t)mC + (xc & 0xffffu), gMov = (uint32_t)(mC >> 32) + (xc >> 16);
-                cA = __shfl_sync(0xffffffffu, acc_d, 0);
-                cS = __shfl_sync(0xffffffffu, acc_d, 1);
-                if (!kSplit) {
-                    cD1 = __shfl_sync(0xffffffffu, acc_d, 2);
-                    cD2 = __shfl_sync(0xffffffffu, acc_d, 3);
-                }
-                cC = (unsigned long long)__shfl_sync(0xffffffffu, acc_i, 5);
+                car_d = acc_d;   // each lane keeps its own quantity's prefix for the next chunk: no broadcast
+                car_i = acc_i;
                 // the consumers have lifted the previous chunk's values out of the rings: its far-end entries may be overwritten
                 TM(5);
                 bar_sync_n(3, kWinThreads);
@@ -646,7 +648,13 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 // into the rings: the prefix AFTER tick k lives at position k + 1.  The running sums continue from the offsets.
                 uint32_t slot = pl.slotT + (uint32_t)(kRun * tid) + 1u;
                 if (slot >= (uint32_t)R) slot -= (uint32_t)R;
-                // into the rings (a rolled loop again: the x and the spreads come back from the staging buffer)
+                // linear stores from the thread's first slot (the rings are padded by one run); the overhang is copied below
+                double* __restrict__ pA = QA + slot;
+                double* __restrict__ pS = QS + slot;
+                double* __restrict__ p1 = QD1 + slot;
+                double* __restrict__ p2 = QD2 + slot;
+                double* __restrict__ pG = QG + slot;
+                uint32_t* __restrict__ pC = QC + slot;
 #if MRP_WIN_PROD_REGS
 #pragma unroll
 #else
@@ -669,10 +677,17 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                         gG = fma(decay, gG, alpha * ax);
                         gNeg += (uint32_t)__double2hiint(xv) >> 31;
                         gMov += ax != 0.0 ? 1u : 0u;
-                        QA[slot] = gA; QS[slot] = gS; QG[slot] = gG;
-                        if (!kSplit) { QD1[slot] = g1; QD2[slot] = g2; }
-                        QC[slot] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
-                        if (++slot == (uint32_t)R) slot = 0u;
+                        pA[i] = gA; pS[i] = gS; pG[i] = gG;
+                        if (!kSplit) { p1[i] = g1; p2[i] = g2; }
+                        pC[i] = (gNeg & 0xffffu) | (gMov << 16);   // two wrapping 16-bit counters
+                    }
+                }
+                if (slot + (uint32_t)nv > (uint32_t)R) {   // one thread in ~300: the run crossed the end of the rings
+#pragma unroll 1
+                    for (uint32_t j = (uint32_t)R - slot; j < (uint32_t)nv; ++j) {
+                        const uint32_t w = slot + j - (uint32_t)R;
+                        QA[w] = pA[j]; QS[w] = pS[j]; QG[w] = pG[j]; QC[w] = pC[j];
+                        if (!kSplit) { QD1[w] = p1[j]; QD2[w] = p2[j]; }
                     }
                 }
                 if (nv > 0 && k0 + (uint32_t)nv == TF) sh.carryG = gG;   // the EMA after the chunk's last tick
@@ -751,14 +766,22 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 bar_sync_n(3, kWinThreads);
                 uint32_t slot = pl.slotT + (uint32_t)(kRun * stid) + 1u;
                 if (slot >= (uint32_t)R) slot -= (uint32_t)R;
+                double* __restrict__ p1 = QD1 + slot;
+                double* __restrict__ p2 = QD2 + slot;
 #pragma unroll
                 for (int i = 0; i < kRun; ++i) {
                     if (i < nv) {
                         g1 += d[i];
                         g2 = fma(d[i], d[i], g2);
-                        QD1[slot] = g1;
-                        QD2[slot] = g2;
-                        if (++slot == (uint32_t)R) slot = 0u;
+                        p1[i] = g1;
+                        p2[i] = g2;
+                    }
+                }
+                if (slot + (uint32_t)nv > (uint32_t)R) {
+#pragma unroll 1
+                    for (uint32_t j = (uint32_t)R - slot; j < (uint32_t)nv; ++j) {
+                        QD1[slot + j - (uint32_t)R] = p1[j];
+                        QD2[slot + j - (uint32_t)R] = p2[j];
                     }
                 }
             } else {
@@ -1107,7 +1130,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
 // Ring geometry for given windows: the tick ring holds one window + one chunk, likewise the trade ring; everything must fit the
 // 227 KB a CTA can opt into.  Returns false when the windows are too long for the on-chip rings.
 static size_t win_smem(int ring, int chunk_ticks, int trade_ring, int dir_window) {
-    return (size_t)ring * 44 + (size_t)2 * kStages * (chunk_ticks + 4) * 8 + (size_t)trade_ring * 8 +
+    return (size_t)(ring + kRingPad) * 44 + (size_t)2 * kStages * (chunk_ticks + 4) * 8 + (size_t)trade_ring * 8 +
            (MRP_WIN_SLOG_SMEM ? (size_t)(dir_window + 2) * 8 : 0);
 }
 bool win_geometry(int mid_window, int dir_window, int* ring, int* chunk_ticks, int* trade_ring, int* chunk_trades, size_t* smem) {
