@@ -339,8 +339,15 @@ __device__ __forceinline__ unsigned long long add4x16(unsigned long long a, unsi
 #ifdef MRP_WIN_TIMERS
 // experiment builds only: per-role phase timers, summed over all CTAs (read with mrp_fg_debug_win_timers)
 __device__ unsigned long long g_win_tm[3][12];
-#define TM_DECL long long tm_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tm_last = clock64(); long long tm_iters = 0
-#define TM(i) do { const long long tm_now = clock64(); tm_acc[i] += tm_now - tm_last; tm_last = tm_now; } while (0)
+// the clock is read through an asm statement with a memory clobber: a plain clock64() may be moved across the barrier next to it, which
+// books a barrier wait on the phase AFTER the barrier (the first timer runs of this session did exactly that)
+__device__ __forceinline__ long long tm_clock() {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+#define TM_DECL long long tm_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tm_last = tm_clock(); long long tm_iters = 0
+#define TM(i) do { const long long tm_now = tm_clock(); tm_acc[i] += tm_now - tm_last; tm_last = tm_now; } while (0)
 #define TM_FLUSH(role) do { if (lane == 0) { for (int i_ = 0; i_ < 10; ++i_) atomicAdd(&g_win_tm[role][i_], (unsigned long long)tm_acc[i_]); atomicAdd(&g_win_tm[role][10], (unsigned long long)tm_iters); } } while (0)
 extern "C" int mrp_fg_debug_win_timers(unsigned long long* out) {
     cudaDeviceSynchronize();
