@@ -144,6 +144,22 @@ __device__ __forceinline__ double sqrt_fast(double v) {
     const double s = v * r;
     return fma(fma(-s, s, v), 0.5 * r, s);
 }
+// The same root without a branch: zero gives zero, every other input outside the fast range raises `rare` (the caller recomputes
+// those with the library root in ONE out-of-line call after all its roots) — three roots, two reciprocals and three quotients of
+// a row then sit in one basic block and overlap, instead of running one after the other between branches and calls.
+__device__ __forceinline__ double sqrt_fast_nb(double v, bool& rare) {
+    const bool ok = rsqrt_pos_ok(v);
+    rare |= !ok && v != 0.0;
+    const double r = rsqrt_pos(ok ? v : 1.0);
+    const double s = v * r;
+    const double f = fma(fma(-s, s, v), 0.5 * r, s);
+    return v == 0.0 ? 0.0 : f;
+}
+__device__ __noinline__ void sqrt_rare3(double a, double b, double c, double* out) {
+    out[0] = sqrt(a);
+    out[1] = sqrt(b);
+    out[2] = sqrt(c);
+}
 __device__ __forceinline__ bool small_mag(double v, uint32_t hi_limit) {  // |v| < the double whose high word is hi_limit; NaN -> false
     return ((uint32_t)__double2hiint(v) & 0x7fffffffu) < hi_limit;
 }
@@ -239,7 +255,7 @@ __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, con
 
 // a / n for a positive count n: reciprocal, product, ONE correction step (the quotient's remainder is exact in an fma) — the
 // correctly rounded quotient for the small integers that meet here, without a division and without a table
-__device__ __noinline__ double div_by_count(double a, int n) {
+__device__ __forceinline__ double div_by_count(double a, int n) {
     const double b = (double)n, r = rcp_pos(b);
     const double q = a * r;
     return fma(fma(-q, b, a), r, q);
@@ -281,41 +297,50 @@ __device__ __forceinline__ void finish_tick_row(const DevOutputs& out, const int
     int cnt = 0, nUp = 0, t_up = 0, t_dn = 0, t_tot = 0;
     const uint32_t e = g.e;
     if (e > 0u) {
+        // One basic block: selects instead of branches, so that the independent chains (three roots, two reciprocals, the entropy's
+        // table look-ups) overlap.  Values computed for a case that does not apply are discarded by the selects.
         const uint32_t s = sub_floor0(e, (uint32_t)P.mid_window);
         cnt = (int)(e - s) - 1;
-        if (cnt > 0) {
-            nUp = cnt - g.negs;
-            // a window of flat ticks only is exactly zero in the reference; do not let rounding residue of the prefix
-            // differences through the square roots
-            const bool moved = g.movm > 0;
-            const double tot = (g.SA > 0.0 && moved) ? g.SA : 0.0;
-            const bool full = cnt == P.mid_window - 1;   // the steady state: the window's constants sit in the kernel parameters
-            rv = tot * (full ? P.inv_ret_full : rcp_pos((double)cnt));  // feature_processor.cpp:61
-            double w = 0.0;
-            if (tot != 0.0) {
-                // :64-79: sum_{i>=1} alpha decay^(cnt-i) x_i + decay^cnt x_1  (the restart takes x_1 with weight decay^(cnt-1))
-                double pw = P.pow_ret_full;
-                if (!full) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(pw) : "l"(P.ewm_pow + cnt));   // the first window of a stream only: no load in flight otherwise
-                w = fma(pw, g.xf - g.Gs1, g.Ge);
-                if (!(w > 0.0)) w = 0.0;
-            }
-            ewm = sqrt_fast(w);
-            double sumU = 0.5 * (g.SA + g.SS), sumD = 0.5 * (g.SA - g.SS);
-            if (!(sumU > 0.0) || !moved) sumU = 0.0;
-            if (!(sumD > 0.0) || !moved) sumD = 0.0;
-            const double au = nUp > 0 ? sumU * rcp_pos((double)nUp) : 0.0;          // :95-98 (an empty side counts 0)
-            const double ad = cnt > nUp ? sumD * rcp_pos((double)(cnt - nUp)) : 0.0;
-            const double diff = au - ad;
-            dv = sqrt_fast(fabs(diff)) * ((diff >= 0) ? 1.0 : -1.0);
+        const bool has = cnt > 0;
+        nUp = has ? cnt - g.negs : 0;
+        // a window of flat ticks only is exactly zero in the reference; do not let rounding residue of the prefix
+        // differences through the square roots
+        const bool moved = has && g.movm > 0;
+        const double tot = (g.SA > 0.0 && moved) ? g.SA : 0.0;
+        const bool full = cnt == P.mid_window - 1;   // the steady state: the window's constants sit in the kernel parameters
+        double pw = P.pow_ret_full, inv_cnt = P.inv_ret_full;
+        if (has && !full) {   // the first window of a stream only: no load in flight otherwise
+            asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(pw) : "l"(P.ewm_pow + cnt));
+            inv_cnt = rcp_pos((double)cnt);
         }
-        {   // :101-107 with s_k = pivot + d_k: mean = (sum s)/1500, var = sum (s_k - mean)^2 / 1500
-            const double n = (double)(e - s);
-            const double mean = (g.D1 + n * pivot) * P.inv_spread_divisor;
-            const double delta = mean - pivot;
-            double ss = g.D2 - 2.0 * delta * g.D1 + n * delta * delta;
-            if (!(ss > 0.0)) ss = 0.0;
-            sv = sqrt_fast(ss * P.inv_spread_divisor);
+        rv = tot * inv_cnt;  // feature_processor.cpp:61
+        // :64-79: sum_{i>=1} alpha decay^(cnt-i) x_i + decay^cnt x_1  (the restart takes x_1 with weight decay^(cnt-1))
+        double w = fma(pw, g.xf - g.Gs1, g.Ge);
+        if (!(tot != 0.0 && w > 0.0)) w = 0.0;
+        double sumU = 0.5 * (g.SA + g.SS), sumD = 0.5 * (g.SA - g.SS);
+        if (!(sumU > 0.0) || !moved) sumU = 0.0;
+        if (!(sumD > 0.0) || !moved) sumD = 0.0;
+        const int nDn = cnt - nUp;
+        const double au = nUp > 0 ? sumU * rcp_pos((double)(nUp > 0 ? nUp : 1)) : 0.0;          // :95-98 (an empty side counts 0)
+        const double ad = (has && nDn > 0) ? sumD * rcp_pos((double)(nDn > 0 ? nDn : 1)) : 0.0;
+        const double diff = au - ad;
+        // :101-107 with s_k = pivot + d_k: mean = (sum s)/1500, var = sum (s_k - mean)^2 / 1500
+        const double n = (double)(e - s);
+        const double mean = (g.D1 + n * pivot) * P.inv_spread_divisor;
+        const double delta = mean - pivot;
+        double ss = g.D2 - 2.0 * delta * g.D1 + n * delta * delta;
+        if (!(ss > 0.0)) ss = 0.0;
+        const double r0 = w, r1 = fabs(diff), r2 = ss * P.inv_spread_divisor;
+        bool rare = false;
+        double q0 = sqrt_fast_nb(r0, rare), q1 = sqrt_fast_nb(r1, rare), q2 = sqrt_fast_nb(r2, rare);
+        if (rare) {   // denormal, huge or NaN radicands: the library root for all three
+            double q[3];
+            sqrt_rare3(r0, r1, r2, q);
+            q0 = q[0]; q1 = q[1]; q2 = q[2];
         }
+        ewm = has ? q0 : 0.0;
+        dv = has ? q1 * ((diff >= 0) ? 1.0 : -1.0) : 0.0;
+        sv = q2;
         const uint32_t d0 = sub_floor0(e, (uint32_t)P.dir_window);
         t_tot = (int)(e - d0);
         t_up = t_tot - g.negd;            // sign clear <=> the midprice rose
