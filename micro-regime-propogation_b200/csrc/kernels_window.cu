@@ -75,7 +75,7 @@ constexpr int kTradeRun = 10;                      // consecutive trades per lan
 #define MRP_WIN_PROD_REGS 1      // producers: 1 = the thread's run in registers, fully unrolled; 0 = short rolled loops over the staging buffer
 #endif
 #ifndef MRP_WIN_ORDER
-#define MRP_WIN_ORDER 1          // consumers: 0 = gather, finalise, plan; 1 = plan, gather, finalise
+#define MRP_WIN_ORDER 1          // consumers: 0 = gather, finalise, plan; 1 = plan, gather, finalise; 2 = finalise (previous iteration's rows), plan, gather
 #endif
 #ifndef MRP_WIN_MATH_UNROLL
 #define MRP_WIN_MATH_UNROLL 2    // tick pairs per trip of the producers' arithmetic loop
@@ -95,7 +95,8 @@ constexpr int kTradeRun = 10;                      // consecutive trades per lan
 //   MRP_WIN_PROD_REGS    1: a producer thread keeps its 11-tick run in registers, everything unrolled; 0: short rolled loops
 //                        that overwrite the staged midprices with x in place (7 KB less code, but +20 % instructions: 8.2 ms
 //                        rolled, 6.7 ms with the arithmetic loop unrolled)
-//   MRP_WIN_ORDER        consumers: 1 = plan, gather, finalise; 0 = gather, finalise, plan (rings released 800 cycles earlier: slower)
+//   MRP_WIN_ORDER        consumers: 1 = plan, gather, finalise; 0 = gather, finalise, plan (rings released 800 cycles earlier: slower);
+//                        2 = finalise the previous iteration's rows first, then plan and gather (7.04 ms: the ring stores wait for the gather)
 //   MRP_WIN_PROD_WARPS / MRP_WIN_RUN   4 x 11 (default) 6.16 ms; 5 x 9 6.70; 6 x 7 6.48; 7 x 7 6.38; 8 x 5 6.45
 //   MRP_WIN_SPLIT_SPREAD 1: four more warps produce the spread prefixes (QD1, QD2), the midprice producers' loop shrinks from 1027
 //                        to 827 instructions — and the kernel goes from 6.02 to 6.22 ms (460 -> 501 M warp-instructions per 8 M rows at
@@ -1031,6 +1032,43 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         __syncthreads();   // the first kDepth plans are visible to everybody
         int q = 0;
         TM_DECL;
+#if MRP_WIN_ORDER == 2
+        // The iteration opens with the finalisation of the rows gathered in the PREVIOUS iteration — arithmetic and global stores out of
+        // registers — because the shared-memory pipe is still draining the producers' ring stores of the chunk before (every load
+        // issued right after the chunk barrier waits 700-1000 cycles behind them); the plan and the gather follow when the pipe is free.
+        RowGather held;
+        held.row = -1;
+        for (;; ++q) {
+            const WinPlan& pl = sh.plan[q & (kPlans - 1)];
+            if (pl.mode != PLAN_RUN) break;
+            TM(0);
+            finish(held);
+            TM(2);
+            plan_after(q + kDepth, sh.plan[(q + kDepth - 1) & (kPlans - 1)]);
+            eq[kDepth + 1] = cur_e;
+            jq[kDepth + 1] = cur_j;
+            TM(5);
+            held.row = -1;
+            if (q > 0) gather(sh.plan[(q - 1) & (kPlans - 1)], eq[0], jq[0], held);
+            TM(1);
+            bar_arrive_n(3, kWinThreads);
+#pragma unroll
+            for (int i = 0; i < kDepth + 1; ++i) { eq[i] = eq[i + 1]; jq[i] = jq[i + 1]; }
+            TM(3);
+            __syncthreads();   // the rings hold chunk q; plan q + kDepth is visible
+            TM(4);
+#ifdef MRP_WIN_TIMERS
+            ++tm_iters;
+#endif
+        }
+        if (cw == 0) TM_FLUSH(1);
+        finish(held);
+        if (q > 0) {   // the last chunk
+            RowGather gat;
+            gather(sh.plan[(q - 1) & (kPlans - 1)], eq[0], jq[0], gat);
+            finish(gat);
+        }
+#else
         for (;; ++q) {
             const WinPlan& pl = sh.plan[q & (kPlans - 1)];
             if (pl.mode != PLAN_RUN) break;
@@ -1074,6 +1112,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             gather(sh.plan[(q - 1) & (kPlans - 1)], eq[0], jq[0], gat);
             finish(gat);
         }
+#endif
     } else {
         // ================================================================================ the trade warp: trades -> QT
         unsigned long long cJ = 0ull;    // the counters at the trade frontier
