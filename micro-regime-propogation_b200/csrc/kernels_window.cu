@@ -63,12 +63,7 @@ constexpr int kProd = kProdWarps * 32;             // (midprice) producer thread
 constexpr int kSpread = kSplit ? kProd : 0;        // spread producer threads: the same ticks per thread as the midprice producers
 constexpr int kFirstCons = kProd + kSpread;        // first consumer thread
 constexpr int kCons = kConsWarps * 32;             // consumer threads == most rows of one chunk
-#ifndef MRP_WIN_CONS_SPLIT
-#define MRP_WIN_CONS_SPLIT 0     // 1: the consumers are two groups of four warps — plan + trade-axis rows, and tick-axis rows
-#endif
-constexpr bool kConsSplit = MRP_WIN_CONS_SPLIT != 0;
-constexpr int kFirstTickCons = kFirstCons + kCons;                       // kConsSplit: first thread of the tick-axis group
-constexpr int kWinThreads = kFirstCons + (kConsSplit ? 2 : 1) * kCons + 32;    // + the trade warp
+constexpr int kWinThreads = kFirstCons + kCons + 32;    // + the trade warp
 constexpr int kRun = MRP_WIN_RUN;                  // consecutive ticks per producer thread (odd: conflict-free 64-bit shared accesses); long
                                                    // runs keep the per-thread scan overhead (~300 instructions) small next to the tick arithmetic
 constexpr int kTradeRun = 10;                      // consecutive trades per lane and pass of the trade warp: a chunk of 128 rows brings
@@ -78,9 +73,6 @@ constexpr int kTradeRun = 10;                      // consecutive trades per lan
 #endif
 #ifndef MRP_WIN_PROD_REGS
 #define MRP_WIN_PROD_REGS 1      // producers: 1 = the thread's run in registers, fully unrolled; 0 = short rolled loops over the staging buffer
-#endif
-#ifndef MRP_WIN_PREFETCH
-#define MRP_WIN_PREFETCH 0       // 1: a producer thread fetches its NEXT run into registers before the ring stores of the current chunk (kDepth >= 2)
 #endif
 #ifndef MRP_WIN_ORDER
 #define MRP_WIN_ORDER 1          // consumers: 0 = gather, finalise, plan; 1 = plan, gather, finalise; 2 = finalise (previous iteration's rows), plan, gather
@@ -115,7 +107,6 @@ constexpr int kDepth = MRP_WIN_DEPTH;              // chunks in flight ahead of 
 constexpr int kStages = kDepth + 1;                // staging buffers
 constexpr int kPlans = 8;                          // plan slots: chunk q lives in slot q & 7 (planned in iteration q - kDepth, gathered in q + 1)
 static_assert(kDepth >= 1 && kDepth + 3 <= kPlans, "plan slots");
-static_assert(!kConsSplit || kDepth <= 2, "sE holds four chunks");
 constexpr int kRingPad = ((MRP_WIN_RUN + 1) / 2) * 2;   // entries past the end of each tick ring (a whole thread run; even: 16-byte alignment of what follows)
 constexpr int kChunkTrades = 512;                  // most new trades of one chunk (a chunk of 128 rows brings ~260)
 constexpr int kTradeStage = kChunkTrades + 32;     // staged trade bytes of a chunk (chunk_trades + 16-byte rounding on both ends)
@@ -410,7 +401,6 @@ struct __align__(16) WinStatic {
     uint64_t full[kStages];            // mbarriers of the staging buffers
     double wt[kProdWarps][6];          // per-warp totals: x, +-x, d, d^2, EMA, counts (bit pattern)
     double wtS[kProdWarps][2];         // kSplit: the spread producers' per-warp totals d, d^2
-    uint32_t sE[kConsSplit ? 4 : 1][kCons];   // kConsSplit: the rows' tick cursors of the chunks in flight (chunk c in slot c & 3), from the planning group to the tick-axis group
     __align__(16) unsigned char stgT[kStages][kTradeStage];   // staged trade directions of the chunk (position JFprev - 1 onwards)
     double carryG;                     // the EMA after the chunk's last tick
     uint32_t excP1;                    // 1 + position of the last flagged tick (0 = none)
@@ -495,70 +485,11 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
         int stage = 0;
         uint32_t phase = 0u;   // staging buffer of chunk q and the parity of its mbarrier phase
         TM_DECL;
-#if MRP_WIN_PREFETCH
-        // Loop-carried: the NEXT chunk's plan fields and this thread's run of it, fetched out of the staging buffer BEFORE the current
-        // chunk's ring stores are issued — the shared-memory pipe is still draining those stores when the next iteration begins, and a
-        // load issued then waits 700-1400 cycles behind them.  With the run in registers the producers issue no load between the chunk
-        // barrier and the end of the tick arithmetic.  Needs the plans two chunks ahead (kDepth >= 2).
-        static_assert(kDepth >= 2 && MRP_WIN_PROD_REGS && !kSplit, "MRP_WIN_PREFETCH");
-        int n_mode = PLAN_END, n_nv = 0;
-        uint32_t n_TFp = 0u, n_TF = 0u, n_slotT = 0u, n_k0 = 0u;
-        double nm[kRun + 1], nd[kRun];
-#pragma unroll
-        for (int i = 0; i < kRun; ++i) { nm[i + 1] = 1.0; nd[i] = 0.0; }
-        nm[0] = 1.0;
-        auto fetch_run = [&](const int qn) {
-            const WinPlan& pn = sh.plan[qn & (kPlans - 1)];
-            n_mode = pn.mode;
-            if (n_mode != PLAN_RUN) return;
-            n_TFp = pn.TFprev;
-            n_TF = pn.TF;
-            n_slotT = pn.slotT;
-            mbar_wait(&sh.full[stage], phase);
-            const int stage_q = stage;
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            n_k0 = n_TFp + (uint32_t)(kRun * tid);
-            n_nv = n_k0 < n_TF ? (int)min(n_TF - n_k0, (uint32_t)kRun) : 0;
-            if (n_TF > n_TFp) {
-                const double* __restrict__ sm = stgM + stage_q * CTS + pn.shM;
-                const double* __restrict__ ss = stgS + stage_q * CTS + pn.shS;
-                const int i0 = (int)(n_k0 - pn.stg0);
-                const bool has_prev = n_k0 > pn.stg0;
-                const int ib = n_nv > 0 ? i0 : 1;          // threads without a run read the buffer's head
-#pragma unroll
-                for (int i = 0; i < kRun; ++i) {
-                    nm[i + 1] = sm[ib + i];
-                    nd[i] = ss[ib + i] - pivot;
-                }
-                nm[0] = sm[ib - 1];
-                if (n_nv == 0) nm[1] = 1.0;
-                if (!(n_nv > 0 && has_prev)) nm[0] = nm[1];   // the tick at the base has no predecessor: flat
-                if (__any_sync(0xffffffffu, n_nv < kRun)) {   // only the warp that holds the frontier has partial or empty runs
-#pragma unroll
-                    for (int i = 0; i < kRun; ++i)
-                        if (i >= n_nv) { nm[i + 1] = nm[i]; nd[i] = 0.0; }
-                }
-            }
-        };
-        fetch_run(0);
-        for (int q = 0;; ++q) {
-            if (n_mode != PLAN_RUN) break;
-            const uint32_t TFp = n_TFp, TF = n_TF, slotT_q = n_slotT;
-            TM(0);
-            TM(1);
-            if (TF > TFp) {
-                const uint32_t k0 = n_k0;
-                const int nv = n_nv;
-                double m[kRun + 1], d[kRun];
-#pragma unroll
-                for (int i = 0; i < kRun; ++i) { m[i + 1] = nm[i + 1]; d[i] = nd[i]; }
-                m[0] = nm[0];
-#else
         for (int q = 0;; ++q) {
             const WinPlan& pl = sh.plan[q & (kPlans - 1)];
             if (pl.mode != PLAN_RUN) break;
-            const uint32_t TFp = pl.TFprev, TF = pl.TF, slotT_q = pl.slotT;
-            // (the EMA at the frontier, sh.carryG, is read after the producers' barrier below)   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
+            const uint32_t TFp = pl.TFprev, TF = pl.TF;
+            if (lane == 4) car_d = sh.carryG;   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
             TM(0);
             mbar_wait(&sh.full[stage], phase);
             TM(1);
@@ -570,9 +501,7 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 const uint32_t k0 = TFp + (uint32_t)(kRun * tid);
                 const int i0 = (int)(k0 - pl.stg0);
                 const int nv = k0 < TF ? (int)min(TF - k0, (uint32_t)kRun) : 0;   // valid ticks of this thread
-#endif
 #if MRP_WIN_PROD_REGS
-#if !MRP_WIN_PREFETCH
                 // the run lives in registers, everything unrolled (more instruction-level parallelism, three times the code)
                 const bool has_prev = k0 > pl.stg0;
                 double m[kRun + 1], d[kRun];
@@ -592,7 +521,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                             if (i >= nv) { m[i + 1] = m[i]; d[i] = 0.0; }
                     }
                 }
-#endif
                 double x[kRun];
                 uint32_t umax = 0u, rsign = 0u, nneg = 0u, nmov = 0u;
 #pragma unroll
@@ -724,7 +652,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 TM(3);
                 bar_sync_n(1, kProd);
                 TM(4);
-                if (lane == 4) car_d = sh.carryG;   // the EMA at the frontier (written by the owner of the previous chunk's last tick, before the chunk barrier)
                 // across the warps: lane l (< 6) walks quantity l over the warp totals; the four sums and the EMA share one
                 // fused multiply-add (factor 1 or decay^352), the counters an integer add
                 double mine_d = 0.0, acc_d = car_d;
@@ -747,15 +674,12 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 uint32_t gNeg = (uint32_t)mC + (xc & 0xffffu), gMov = (uint32_t)(mC >> 32) + (xc >> 16);
                 car_d = acc_d;   // each lane keeps its own quantity's prefix for the next chunk: no broadcast
                 car_i = acc_i;
-#if MRP_WIN_PREFETCH
-                fetch_run(q + 1);   // the next run into registers while the pipe is quiet: the store burst below comes after it
-#endif
                 // the consumers have lifted the previous chunk's values out of the rings: its far-end entries may be overwritten
                 TM(5);
                 bar_sync_n(3, kWinThreads);
                 TM(6);
                 // into the rings: the prefix AFTER tick k lives at position k + 1.  The running sums continue from the offsets.
-                uint32_t slot = slotT_q + (uint32_t)(kRun * tid) + 1u;
+                uint32_t slot = pl.slotT + (uint32_t)(kRun * tid) + 1u;
                 if (slot >= (uint32_t)R) slot -= (uint32_t)R;
                 // linear stores from the thread's first slot (the rings are padded by one run); the overhang is copied below
                 double* __restrict__ pA = QA + slot;
@@ -801,9 +725,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 }
                 if (nv > 0 && k0 + (uint32_t)nv == TF) sh.carryG = gG;   // the EMA after the chunk's last tick
             } else {
-#if MRP_WIN_PREFETCH
-                fetch_run(q + 1);
-#endif
                 bar_sync_n(3, kWinThreads);
             }
             TM(7);
@@ -1002,7 +923,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                     int sl = (int)slotTe - (int)(TF - p);
                     return sl < 0 ? sl + R : sl;
                 };
-                if (!kConsSplit) {
                 const uint32_t s = sub_floor0(e, Wm), d0 = sub_floor0(e, Wd);
                 const int se = slot_of(e), ss0 = slot_of(s), sd = slot_of(d0);
                 const int cnt = (int)(e - s) - 1;
@@ -1029,9 +949,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 }
                 gat.negd = (int)((Ce - Cd) & 0xffffu);
                 gat.movd = (int)(((Ce >> 16) - (Cd >> 16)) & 0xffffu);
-                const uint32_t exc = sh.excP1;
-                gat.flagged = exc != 0u && e <= exc + Wmax + 1u;   // the window (or the entry just before it) may hold a flagged tick
-                }
                 // trades: [jb, je), reversal pairs (i-1, i) for i in (jb, je)
                 const uint32_t jb = sub_floor0(je, Wd);
                 auto tslot = [&](uint32_t p) {
@@ -1051,6 +968,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 gat.e = e;
                 gat.je = je;
                 gat.row = pg.c0 + ci;
+                const uint32_t exc = sh.excP1;
+                gat.flagged = exc != 0u && e <= exc + Wmax + 1u;   // the window (or the entry just before it) may hold a flagged tick
             }
         };
         auto finish = [&](const RowGather& gat) {
@@ -1061,10 +980,8 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
                 out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + gat.row] = (double)gat.neg;
             } else
             if (gat.row >= 0) {
-                if (!kConsSplit) {
-                    if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
-                    else finish_tick_row(out, N, P, sLog, pivot, gat);
-                }
+                if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
+                else finish_tick_row(out, N, P, sLog, pivot, gat);
                 const uint32_t jb = sub_floor0(gat.je, Wd);
                 write_trade_row(out, N, gat.row, sLog, (int)(gat.je - jb), gat.pos, gat.neg, gat.rev, gat.isum);
             }
@@ -1087,7 +1004,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             if (slotJe >= (uint32_t)RJ) slotJe -= (uint32_t)RJ;
             const long long c0n = pl.c0 + pl.nr;
             make_plan(q_new, c0n, TF, JF, slotTe, slotJe, pre_e, pre_j);
-            if (kConsSplit) sh.sE[q_new & 3][ci] = cur_e;
             const long long c2 = c0n + plan_nr;
             pre_e = pre_j = 0;
             if (c2 + ci < rb) {
@@ -1096,7 +1012,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             }
         };
         make_plan(0, ra, baseK, baseJ, 0u, 0u, pre_e, pre_j);
-        if (kConsSplit) sh.sE[0][ci] = cur_e;
         eq[1] = cur_e;
         jq[1] = cur_j;
         {   // candidates of chunk 1
@@ -1198,83 +1113,6 @@ k_windows(const DevInputs in, const DevOutputs out, const DevSegment* __restrict
             finish(gat);
         }
 #endif
-    } else if (kConsSplit && tid < kFirstTickCons + kCons) {
-        // ================================================================================ tick-axis consumers (kConsSplit): gather, finalise
-        // The second half of the consumer role on four warps of its own: the tick-axis window values of the previous chunk's rows and
-        // their five features; the planning group keeps the plan and the trade-axis rows.  No instruction is duplicated — each row's work
-        // is divided — so the longest consumer warp walks ~400 instead of ~750 instructions per chunk.
-        const int ki = tid - kFirstTickCons;
-        DirectParams dpm;
-        dpm.mid_window = Wm;
-        dpm.dir_window = Wd;
-        dpm.spread_divisor = P.spread_divisor;
-        dpm.ewm_alpha = P.ewm_alpha;
-        dpm.ewm_decay = P.ewm_decay;
-        auto gather_tick = [&](const WinPlan& pg, const uint32_t e, RowGather& gat) {
-            const uint32_t TF = pg.TF;
-            uint32_t slotTe = pg.slotT + (TF - pg.TFprev);
-            if (slotTe >= (uint32_t)R) slotTe -= (uint32_t)R;
-            gat.row = -1;
-            if (ki < pg.nr) {
-                auto slot_of = [&](uint32_t p) {   // ring slot of tick position p <= TF
-                    int sl = (int)slotTe - (int)(TF - p);
-                    return sl < 0 ? sl + R : sl;
-                };
-                const uint32_t s = sub_floor0(e, Wm), d0 = sub_floor0(e, Wd);
-                const int se = slot_of(e), ss0 = slot_of(s), sd = slot_of(d0);
-                const int cnt = (int)(e - s) - 1;
-                const double Ae = QA[se], Se = QS[se], D1e = QD1[se], D2e = QD2[se];
-                const uint32_t Ce = QC[se], Cd = QC[sd];
-                gat.Ge = QG[se];
-                gat.D1 = D1e - QD1[ss0];
-                gat.D2 = D2e - QD2[ss0];
-                gat.SA = gat.SS = gat.Gs1 = gat.xf = 0.0;
-                gat.negs = gat.movm = 0;
-                if (cnt > 0) {
-                    int s1 = ss0 + 1, s2;
-                    if (s1 == R) s1 = 0;
-                    s2 = s1 + 1;
-                    if (s2 == R) s2 = 0;
-                    const double A1 = QA[s1];
-                    const uint32_t C1 = QC[s1];
-                    gat.SA = Ae - A1;
-                    gat.SS = Se - QS[s1];
-                    gat.Gs1 = QG[s1];
-                    gat.xf = QA[s2] - A1;
-                    gat.negs = (int)((Ce - C1) & 0xffffu);
-                    gat.movm = (int)(((Ce >> 16) - (C1 >> 16)) & 0xffffu);
-                }
-                gat.negd = (int)((Ce - Cd) & 0xffffu);
-                gat.movd = (int)(((Ce >> 16) - (Cd >> 16)) & 0xffffu);
-                gat.e = e;
-                gat.row = pg.c0 + ki;
-                const uint32_t exc = sh.excP1;
-                gat.flagged = exc != 0u && e <= exc + Wmax + 1u;
-            }
-        };
-        auto finish_tick = [&](const RowGather& gat) {
-            if (gat.row >= 0) {
-                if (gat.flagged) direct_tick_row(mid, spread, gat.e, dpm, out.raw, out.counts, N, gat.row);
-                else finish_tick_row(out, N, P, sLog, pivot, gat);
-            }
-        };
-        __syncthreads();   // the first plans are visible
-        int q = 0;
-        for (;; ++q) {
-            const WinPlan& pl = sh.plan[q & (kPlans - 1)];
-            if (pl.mode != PLAN_RUN) break;
-            RowGather gat;
-            gat.row = -1;
-            if (q > 0) gather_tick(sh.plan[(q - 1) & (kPlans - 1)], sh.sE[(q - 1) & 3][ki], gat);
-            bar_arrive_n(3, kWinThreads);
-            finish_tick(gat);
-            __syncthreads();   // the rings hold chunk q
-        }
-        if (q > 0) {   // the last chunk
-            RowGather gat;
-            gather_tick(sh.plan[(q - 1) & (kPlans - 1)], sh.sE[(q - 1) & 3][ki], gat);
-            finish_tick(gat);
-        }
     } else {
         // ================================================================================ the trade warp: trades -> QT
         unsigned long long cJ = 0ull;    // the counters at the trade frontier
