@@ -22,7 +22,7 @@
 //
 // One CTA streams through one row segment in time order; the prefixes restart at the segment's first window (a halo
 // of 1802 ticks / 1502 trades — no halo ROWS), so their magnitude stays within ~100 window sums and a difference
-// keeps ~14 digits.  Work is split by warp role (288 threads, one CTA per SM: the rings take 222 KB), ONE CTA barrier per chunk of
+// keeps ~14 digits.  Work is split by warp role (288 threads, one CTA per SM: rings + staging take 215 KB), ONE CTA barrier per chunk of
 // <= 128 rows / 1408 ticks plus named barriers inside the roles:
 //   warps 0-3  producers: the chunk's new ticks, 11 consecutive ticks per thread out of a staging buffer the copy engine
 //              filled (cp.async.bulk + mbarrier, requested one chunk ahead; no thread issues a global load for a tick):
@@ -33,9 +33,10 @@
 //   warp 8     the trade prefixes (10 trades per lane and pass; a chunk's ~256 trades are one pass): everything but the ring
 //              stores happens before the "previous chunk has been gathered" barrier.
 // A snapshot that brings more new ticks / trades than a chunk holds simply advances the rings in several steps.
-// Code size matters here: three roles execute three instruction streams at once through one 32 KB instruction cache, so
-// the trade warp runs rolled loops, the ring-store loop exists once (wrap handled per element), and everything cold
-// (library square root, count columns, the quotient helper, direct_tick_row) is out of line.
+// Three roles execute three instruction streams at once through one 32 KB instruction cache, so the trade warp runs rolled loops,
+// the ring-store loop exists once (the rings are padded by one run; the rare overhang is copied to the head afterwards) and the
+// cold paths (library square root, count columns, direct_tick_row) are out of line.  The rows' finalisation, on the other hand, is
+// deliberately ONE basic block (selects, branch-free roots, inline quotients): its latency, not its size, was on the critical path.
 //
 // Ticks the fast formulation cannot represent — a non-positive / non-finite midprice, a 50 ms move of 2^-10 relative or
 // more (series range), a non-finite spread — contribute nothing to the prefixes and are flagged; every snapshot whose
@@ -90,7 +91,8 @@ constexpr int kTradeRun = 10;                      // consecutive trades per lan
 // The defaults are the fastest combination; none of the others is faster, which is the finding: the kernel is neither
 // copy-latency-bound (kDepth 1 -> 2 -> 3: 6.16 / 6.17 / 6.8 ms) nor instruction-cache-bound (the hot loops were cut from 44 KB to
 // 25-31 KB, the SM's instruction-cache hit rate went from 68 % to 97.7-99.9 % and the GPC-level cache from 91 % to 2-24 % of its request
-// peak: same time).  It runs at the issue rate of ONE warp per scheduler walking ~1000 dependent instructions per chunk.
+// peak: same time), and its time follows neither its instruction count nor its longest warp.  (Times below are from before the
+// finalisation became one basic block, which took the default from 6.02 to 5.30 ms.)
 //   MRP_WIN_DEPTH        chunks planned (and requested from the copy engine) ahead of the producers
 //   MRP_WIN_PROD_REGS    1: a producer thread keeps its 11-tick run in registers, everything unrolled; 0: short rolled loops
 //                        that overwrite the staged midprices with x in place (7 KB less code, but +20 % instructions: 8.2 ms
