@@ -256,10 +256,10 @@ __device__ __noinline__ void direct_tick_row(const double* __restrict__ mid, con
     write_tick_row(o, N, r, o_ewm, o_rv, o_dv, o_sv, ent, count, up_count, up, down, (int)(e - d0));
 }
 
-// a / n for a positive count n: reciprocal, product, ONE correction step (the quotient's remainder is exact in an fma) — the
-// correctly rounded quotient for the small integers that meet here, without a division and without a table
-__device__ __forceinline__ double div_by_count(double a, int n) {
-    const double b = (double)n, r = rcp_pos(b);
+// a / b for a positive count b with r = rcp_pos(b): product, ONE correction step (the quotient's remainder is exact in an fma) — the
+// correctly rounded quotient for the small integers that meet here, without a division and without a table; quotients over the
+// same count share the reciprocal
+__device__ __forceinline__ double quotient_by(double a, double b, double r) {
     const double q = a * r;
     return fma(fma(-q, b, a), r, q);
 }
@@ -269,10 +269,13 @@ __device__ __forceinline__ double div_by_count(double a, int n) {
 __device__ __forceinline__ void write_trade_row(const DevOutputs& out, int64_t N, int64_t r, const double* __restrict__ clog2c, int nd, int pos,
                                                 int neg, int rev, int isum) {
     const int tot = pos + neg;                                  // :261-269
-    const double rr = nd > 1 ? div_by_count((double)rev, nd) : 0.0;                                   // :239 — divides by size, not size-1
-    const double ab = nd > 0 ? div_by_count((double)isum, nd) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
+    // three quotients on two reciprocals, guarded denominators and selects: one basic block
+    const double bn = (double)(nd > 0 ? nd : 1), rn = rcp_pos(bn);
+    const double bt = (double)(tot > 0 ? tot : 1), rt = rcp_pos(bt);
+    const double rr = nd > 1 ? quotient_by((double)rev, bn, rn) : 0.0;                                        // :239 — divides by size, not size-1
+    const double ab = nd > 0 ? quotient_by((double)isum, bn, rn) : __longlong_as_double(0x7ff8000000000000ll);  // :246 — 0/0 = NaN with no trades
     // binary entropy = (T log2 T - pos log2 pos - neg log2 neg) / T
-    const double ent = tot > 0 ? div_by_count((clog2c[tot] - clog2c[pos]) - clog2c[neg], tot) : 0.0;
+    const double ent = tot > 0 ? quotient_by((clog2c[tot] - clog2c[pos]) - clog2c[neg], bt, rt) : 0.0;
     out.raw[(int64_t)MRP_F_REVERSAL_RATE * N + r] = rr;
     out.raw[(int64_t)MRP_F_AGGRESSOR_BIAS * N + r] = ab;
     out.raw[(int64_t)MRP_F_SHANNON_ENTROPY * N + r] = ent;
