@@ -49,11 +49,12 @@
 extern "C" {
 #endif
 
-#define MRP_FG_ABI_VERSION 7   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
+#define MRP_FG_ABI_VERSION 8   /* 3: + mrp_fg_download_rows; 4: + mrp_fg_vol_of_vol, mrp_fg_download_vol_of_vol;
                                   5: + mrp_fg_norm_moments, mrp_fg_mean_scale, mrp_fg_standardize;
                                   6: + mrp_fg_halo_rows(_for), mrp_fg_moments_rows, mrp_fg_norm_moments_rows;
                                   7: + mrp_fg_halo_query, mrp_fg_halo_export, mrp_fg_halo_import, mrp_fg_build_state,
-                                     mrp_fg_poison_state, mrp_fg_poison_apply */
+                                     mrp_fg_poison_state, mrp_fg_poison_apply;
+                                  8: + mrp_fg_plan_shape, mrp_fg_plan_host_chunks; mrp_fg_process_host takes raw == NULL or norm == NULL */
 
 /* status codes */
 #define MRP_FG_OK 0
@@ -293,6 +294,19 @@ int mrp_fg_moments_rows(mrp_fg_ctx* ctx, int64_t row_begin, int64_t row_end, dou
  * front of them — reproduces the whole-stream result on its own rows.  The one definition every caller uses. */
 int mrp_fg_halo_rows(const mrp_fg_ctx* ctx);
 int mrp_fg_halo_rows_for(const mrp_fg_params* p);   /* the same from parameters alone (NULL = defaults); needs no GPU */
+
+/* How a batch would be cut — host arithmetic, needs no GPU.  Rows per segment of the two segment kernels (chosen per batch against
+ * the device's multiprocessor count: waves x (segment + halo) is minimised; sm_count <= 0 = 148, a B200) and rows per normaliser
+ * tile (a divisor of norm_window) for `n_streams` streams delimited by row_offsets[n_streams + 1].  Results are bit-identical for
+ * a stream alone and inside a batch only when both are cut the same way; these are the two lengths that decide it.  Either out
+ * pointer may be NULL.  (No reference counterpart: the reference walks one row at a time.) */
+int mrp_fg_plan_shape(const mrp_fg_params* p, int32_t n_streams, const int64_t* row_offsets, int32_t sm_count, int64_t* segment_rows,
+                      int32_t* tile_rows);
+/* The chunk lengths mrp_fg_process_host uses for one stream of `rows` snapshots (chunk_rows as in that call; first_stream /
+ * last_stream: whether the stream opens / closes the call — the first chunks of a call are chunk/8, /4, /2 and the last ones halve
+ * what is left, because the first upload and the last download overlap nothing).  Writes at most `cap` lengths, returns their
+ * number (-1: bad argument).  Host arithmetic. */
+int mrp_fg_plan_host_chunks(int64_t rows, int64_t chunk_rows, int first_stream, int last_stream, int64_t* chunks, int cap);
 
 /* The step the reference's Python stage takes next (sklearn StandardScaler over the z-scored columns of ALL rows of ALL dates:
  * regime_classifier/python/classifier.py:35-37, data_checks.py:78-80), as three calls so that several GPUs / processes can combine:

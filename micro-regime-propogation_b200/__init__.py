@@ -11,7 +11,8 @@ The directory name carries a hyphen (it mirrors the reference repository's name)
 through the root-level shim module `mrp_b200` (see /mrp_b200.py): `import mrp_b200`.
 """
 from .cabi import (COUNTS, FEATURES, HaloInfo, NUM_COUNTS, NUM_FEATURES, Engine, HostView, MrpError, Params, SoaView,
-                   default_params, device_view, halo_rows, load, mean_scale, LIB_PATH, NORM_COMPENSATED, NORM_FAITHFUL)
+                   default_params, device_view, halo_rows, load, mean_scale, plan_host_chunks, plan_shape, LIB_PATH, NORM_COMPENSATED,
+                   NORM_FAITHFUL)
 
 __all__ = ["COUNTS", "FEATURES", "HaloInfo", "NUM_COUNTS", "NUM_FEATURES", "Engine", "HostView", "MrpError", "Params",
-           "SoaView", "default_params", "device_view", "halo_rows", "load", "mean_scale", "LIB_PATH", "NORM_COMPENSATED", "NORM_FAITHFUL"]
+           "SoaView", "default_params", "device_view", "halo_rows", "load", "mean_scale", "plan_host_chunks", "plan_shape", "LIB_PATH", "NORM_COMPENSATED", "NORM_FAITHFUL"]

@@ -384,6 +384,31 @@ class Engine:
         return int(self.lib.mrp_fg_launch_count(self.ctx))
 
 
+def plan_shape(row_offsets, params: Optional[Params] = None, sm_count: int = 0):
+    """mrp_fg_plan_shape: (rows per segment, rows per normaliser tile) for a batch with these row offsets (host arithmetic, no GPU)."""
+    p = params or default_params()
+    ro = np.ascontiguousarray(row_offsets, dtype=np.int64)
+    seg, tile = C.c_int64(0), C.c_int32(0)
+    lib = load()
+    lib.mrp_fg_plan_shape.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    rc = lib.mrp_fg_plan_shape(C.byref(p), len(ro) - 1, ro.ctypes.data, sm_count, C.byref(seg), C.byref(tile))
+    if rc:
+        raise MrpError(lib.mrp_fg_last_error().decode())
+    return int(seg.value), int(tile.value)
+
+
+def plan_host_chunks(rows: int, chunk_rows: int = 0, first_stream: bool = True, last_stream: bool = True):
+    """mrp_fg_plan_host_chunks: the chunk lengths mrp_fg_process_host cuts one stream into (host arithmetic, no GPU)."""
+    lib = load()
+    lib.mrp_fg_plan_host_chunks.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    n = lib.mrp_fg_plan_host_chunks(rows, chunk_rows, int(first_stream), int(last_stream), None, 0)
+    if n < 0:
+        raise MrpError("bad argument")
+    out = np.zeros(max(n, 1), np.int64)
+    lib.mrp_fg_plan_host_chunks(rows, chunk_rows, int(first_stream), int(last_stream), out.ctypes.data, n)
+    return out[:n].tolist()
+
+
 def halo_rows(params: Optional[Params] = None) -> int:
     """mrp_fg_halo_rows_for: rows of history a time shard / host chunk needs in front of its own rows (host arithmetic, no GPU)."""
     p = params or default_params()

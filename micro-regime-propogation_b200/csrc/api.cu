@@ -226,6 +226,31 @@ int pick_tile_rows(int W, int64_t n_rows) {
     return 0;
 }
 
+// Segment length of the two segment kernels for a batch: see setup_shape.
+int64_t pick_segment_rows(const int64_t* row_off, int S, int sm_count, int warm_rows) {
+    const int sms = std::max(1, sm_count);
+    int64_t seg_rows = 16384;
+    double best = 1e300;
+    for (int64_t cand = 4 * kThreads; cand <= 16384; cand += kThreads) {
+        int64_t nseg = 0;
+        for (int s2 = 0; s2 < S; ++s2) nseg += (row_off[s2 + 1] - row_off[s2] + cand - 1) / cand;
+        const int64_t waves = (nseg + sms - 1) / sms;
+        const double cost = (double)waves * (double)(cand + warm_rows);
+        if (cost <= best) { best = cost; seg_rows = cand; }   // ties: the longer segment (fewer halos)
+    }
+    return seg_rows;
+}
+
+constexpr int64_t kDefaultHostChunk = 2 << 20;   // measured at 50 M rows: 1 / 2 / 3 / 4 Mi rows -> 489 / 481 / 482 / 491 ms
+// Length of the chunk of mrp_fg_process_host that starts `rem` rows before the end of its stream: see mrp_fg_process_host.
+int64_t next_host_chunk(int64_t rem, int64_t chunk_rows, int& head, bool last_stream) {
+    const int64_t min_chunk = std::max<int64_t>(1, chunk_rows >> 3);
+    int64_t take = std::min(rem, chunk_rows);
+    if (head < 3 && rem > 2 * chunk_rows) take = std::max<int64_t>(1, chunk_rows >> (3 - head++));
+    else if (last_stream && rem <= 2 * chunk_rows && rem > min_chunk) take = (rem + 1) / 2;
+    return take;
+}
+
 // Rows after which both row-axis EMAs have forgotten their start (decay^rows < 1e-17 for the slower one; also covers the
 // return lag), rounded up to whole 128-row blocks.  -1: the alphas are out of range.
 int ema_warm_rows_for(const mrp_fg_params& p) {
@@ -381,20 +406,9 @@ int setup_shape(mrp_fg_ctx* c, const mrp_fg_soa_view* v) {
     // row segments: enough CTAs to fill 148 SMs several times over, long enough to amortise the window halo
     // Both segment kernels run one CTA per SM, so a launch costs waves x (segment + halo): the halo (one EMA warm-up of the book pass,
     // one window of ticks) is paid per segment, an unfilled last wave per launch.  Pick the whole-chunk length that minimises that
-    // product for THIS batch (streams are cut separately).  50 M rows: 16 128-16 384 rows as before; 32 x 46 600 rows: 5 376 rows,
+    // product for THIS batch (streams are cut separately).  50 M rows: 16 128-16 384 rows as before; 32 x 46 600 rows: 5 632 rows,
     // 288 segments = two waves, instead of 2 304 rows in five.
-    int64_t seg_rows = 16384;
-    {
-        const int sms = std::max(1, c->sm_count);
-        double best = 1e300;
-        for (int64_t cand = 4 * kThreads; cand <= 16384; cand += kThreads) {
-            int64_t nseg = 0;
-            for (int s2 = 0; s2 < S; ++s2) nseg += (c->row_off[s2 + 1] - c->row_off[s2] + cand - 1) / cand;
-            const int64_t waves = (nseg + sms - 1) / sms;
-            const double cost = (double)waves * (double)(cand + c->dp.ema_warm_rows);
-            if (cost <= best) { best = cost; seg_rows = cand; }   // ties: the longer segment (fewer halos)
-        }
-    }
+    int64_t seg_rows = pick_segment_rows(c->row_off.data(), S, c->sm_count, c->dp.ema_warm_rows);
     if (const char* e = std::getenv("MRP_FG_SEGMENT_ROWS")) {
         long v2 = std::atol(e);
         if (v2 >= 1) seg_rows = v2;
@@ -696,7 +710,7 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
     if (!v->buy_vol || !v->sell_vol || !v->adds)
         return fail(MRP_FG_ERR_INVALID, "mrp_fg_process_host needs buy_vol / sell_vol / adds in the view (mrp_fg_build_state works on a bound batch)");
     const int64_t H = mrp_fg_halo_rows(c);
-    if (chunk_rows <= 0) chunk_rows = 2 << 20;   // measured at 50 M rows: 1 / 2 / 3 / 4 Mi rows -> 489 / 481 / 482 / 491 ms
+    if (chunk_rows <= 0) chunk_rows = kDefaultHostChunk;
     const int64_t wmax = std::max(c->p.mid_window, c->p.dir_window + 1);
     constexpr int kLanes = mrp_fg_ctx::kLanes;
     for (int i = 0; i < kLanes; ++i) {
@@ -738,15 +752,10 @@ int mrp_fg_process_host(mrp_fg_ctx* c, const mrp_fg_soa_view* v, double* raw, do
         // Chunk schedule: the first chunk's upload and the last chunk's download overlap nothing, so the call starts with
         // chunk/8, chunk/4, chunk/2 and ends by halving what is left down to chunk/8 (measured at 50 M rows, 2 Mi-row chunks:
         // the exposed head and tail shrink from ~40 ms to ~10 ms of a 480 ms call)
-        const int64_t min_chunk = std::max<int64_t>(1, chunk_rows >> 3);
         int head = s == 0 ? 0 : 3;
         int64_t b = r0;
         for (int64_t a = r0; a < r1; a = b, li = (li + 1) % kLanes) {
-            const int64_t rem = r1 - a;
-            int64_t take = std::min(rem, chunk_rows);
-            if (head < 3 && rem > 2 * chunk_rows) take = std::max<int64_t>(1, chunk_rows >> (3 - head++));
-            else if (s == S - 1 && rem <= 2 * chunk_rows && rem > min_chunk) take = (rem + 1) / 2;
-            b = a + take;
+            b = a + next_host_chunk(r1 - a, chunk_rows, head, s == S - 1);
             const int64_t e0 = std::max(r0, a - H);           // first halo row
             const int64_t n = b - e0;
             int64_t tb = 0, jb = 0;                            // tick / trade bases: the slice's "stream start"
@@ -1100,6 +1109,41 @@ int mrp_fg_halo_rows_for(const mrp_fg_params* p) {
 }
 
 int mrp_fg_halo_rows(const mrp_fg_ctx* c) { return c ? mrp_fg_halo_rows_for(&c->p) : -1; }
+
+int mrp_fg_plan_shape(const mrp_fg_params* p, int32_t n_streams, const int64_t* row_offsets, int32_t sm_count, int64_t* segment_rows,
+                      int32_t* tile_rows) {
+    mrp_fg_params d;
+    if (!p) {
+        mrp_fg_default_params(&d);
+        p = &d;
+    }
+    if (n_streams < 1 || !row_offsets) return fail(MRP_FG_ERR_INVALID, "n_streams / row_offsets");
+    for (int s = 0; s < n_streams; ++s)
+        if (row_offsets[s + 1] < row_offsets[s]) return fail(MRP_FG_ERR_INVALID, "row_offsets must be non-decreasing");
+    const int warm = ema_warm_rows_for(*p);
+    if (warm < 0) return fail(MRP_FG_ERR_INVALID, "EMA alphas must be in (0,1]");
+    long forced = 0;
+    if (const char* e = std::getenv("MRP_FG_SEGMENT_ROWS")) forced = std::atol(e);
+    if (segment_rows) *segment_rows = forced >= 1 ? forced : pick_segment_rows(row_offsets, n_streams, sm_count > 0 ? sm_count : 148, warm);
+    if (tile_rows) {
+        const int t = pick_tile_rows(p->norm_window, row_offsets[n_streams]);
+        if (t <= 0) return fail(MRP_FG_ERR_INVALID, "norm_window above 4096 needs a divisor in [16,4096]");
+        *tile_rows = t;
+    }
+    return MRP_FG_OK;
+}
+
+int mrp_fg_plan_host_chunks(int64_t rows, int64_t chunk_rows, int first_stream, int last_stream, int64_t* chunks, int cap) {
+    if (rows < 0 || (cap > 0 && !chunks)) return -1;
+    if (chunk_rows <= 0) chunk_rows = kDefaultHostChunk;
+    int head = first_stream ? 0 : 3, n = 0;
+    for (int64_t a = 0; a < rows; ++n) {
+        const int64_t take = next_host_chunk(rows - a, chunk_rows, head, last_stream != 0);
+        if (n < cap) chunks[n] = take;
+        a += take;
+    }
+    return n;
+}
 
 int mrp_fg_mean_scale(const double* moments, double* mean_scale) {
     if (!moments || !mean_scale) return fail(MRP_FG_ERR_INVALID, "NULL argument");
