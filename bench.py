@@ -11,7 +11,10 @@ weak scaling, no data-path collective; the only collective is the NCCL all-reduc
 moments after the pass (and the timing barrier).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over ranks);
-`e2e` goes through the C ABI with pinned HOST buffers (H2D + pass + D2H inside the timed region).
+`e2e` goes through the C ABI with pinned HOST buffers (H2D + pass + D2H inside the timed region); the record also carries the
+bytes and GB/s per direction, `ceiling` (the SAME pinned buffers and byte counts moved by plain copies, no kernels: what the
+host's wire allows at this N), `frac_of_copy_ceiling`, and `norm_only` (the call with raw = NULL; not the headline).  For N > 1
+the line also carries `timeshard`: ONE stream of N x 50 M rows split by time with the halo exchange inside the step.
 `--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified reference
 compiled from /root/reference; falls back to the oracle port) on the host cores.
 """
