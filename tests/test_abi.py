@@ -131,3 +131,24 @@ def test_cmake_sm_100a_target_builds(tmp_path):
                           capture_output=True, text=True).stdout
     archs = {l.split(".")[-2] for l in dump.splitlines() if ".cubin" in l}
     assert archs == {"sm_100a"}, archs
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/mrp_fg.h compiles as C99 and a C program linked against libmrp_fg.so runs the host-only entry points (and gets a clean
+    refusal from mrp_fg_create when there is no GPU)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not installed")
+    exe = tmp_path / "abi_smoke"
+    libdir = os.path.dirname(mrp_b200.LIB_PATH)
+    env = dict(os.environ)
+    env.pop("CC", None)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L", libdir, "-lmrp_fg", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "abi_smoke ok" in r.stdout, (r.returncode, r.stdout, r.stderr[-2000:])
